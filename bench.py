@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""bench.py -- paths/sec scored (len<=6, d=256) on N B200s, BASELINE.json configs[1].
+
+A "step" = one pass of the hot path (3 gathers -> LSTM over T=6 -> head -> LSE pool -> sigmoid) over one batch of
+65 536 synthetic KG paths, dims convention A (d_t=d_e=d_r=H=256, D=768), V_e=2 851 220 (config.sh:24-26).
+  value : whole-job paths/s with the batch already resident in HBM (kprn_forward_device), CUDA-event timed
+  e2e   : the same metric through the reference-facing call with HOST buffers (kprn_forward: pinned staging,
+          H2D of the ids, kernels, D2H of the scores inside the timed region)
+  roofline / cpu_baseline : see DESIGN.md "Measurement"
+--impl reference times the CPU restatement (oracle port; Torch7 cannot run here) on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+T = 6
+L = 46
+V_E = 2851220
+N_PATHS = 65536
+
+
+def flops_per_path(d_t, d_e, d_r, H):
+    D = d_t + d_e + d_r
+    return T * 2 * (D + H) * 4 * H + 2 * H * L            # SURVEY.md 8d / BASELINE.md section 3
+
+
+def gather_bytes_per_path(d_t, d_e, d_r):
+    return T * (3 * 4 + 4 * (d_t + d_e + d_r))
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return j, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self._stop_evt = threading.Event()
+        self.proc = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            return
+        for line in self.proc.stdout:
+            if self._stop_evt.is_set():
+                break
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        self._stop_evt.set()
+        if self.proc is not None:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
+
+    def summary(self):
+        sm, mx = [], []
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for k, nm in enumerate(names):
+                if len(r) > 3 + k and r[3 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def make_batches(n_batches, n_paths, seed=12345):
+    from kprn_b200 import synth
+    out = []
+    for b in range(n_batches):
+        ids = synth.make_paths(n_paths, T=T, V_e=V_E, seed=seed + 17 * b, length_mode="realistic", entity_mode="zipf")
+        seg = synth.make_segments(n_paths, seed=seed + 17 * b, mode="realistic")
+        out.append((ids, seg))
+    return out
+
+
+def cpu_port_throughput(d, budget_s=15.0, threads=None):
+    """Times the fp64 CPU restatement (oracle port) on a bounded sample of the same workload."""
+    from kprn_b200 import synth
+    from oracle.kprn_oracle import Oracle
+    ids_all = synth.make_paths(N_PATHS, T=T, V_e=V_E, seed=12345)
+    # compact the entity table to the rows this sample touches (same arithmetic, bounded host memory)
+    def run(n):
+        ids = ids_all[:n].copy()
+        uniq, inv = np.unique(ids[:, :, 1], return_inverse=True)
+        ids[:, :, 1] = inv.reshape(n, T) + 1
+        o = Oracle(T=T, d_t=d, d_e=d, d_r=d, H=d, L=L, V_e=len(uniq))
+        params = o.init_params(12345)
+        seg = synth.make_segments(n, seed=12345)
+        o.forward(params, ids[:min(n, 64)], np.array([0, min(n, 64)], dtype=np.int32))   # warm-up
+        t0 = time.perf_counter()
+        o.forward(params, ids, seg)
+        return time.perf_counter() - t0
+    n = 256
+    dt = run(n)
+    rate = n / dt
+    n2 = int(min(N_PATHS, max(256, rate * budget_s)))
+    n2 = (n2 // 64) * 64
+    dt2 = run(n2)
+    return n2 / dt2, n2, dt2, Oracle.num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    d = args.d
+    times, n_s = [], 0
+    total = args.steps + args.warmup
+    budget = max(2.0, min(20.0, 150.0 / total))
+    vals = []
+    for i in range(total):
+        v, n_s, dt, cores = cpu_port_throughput(d, budget_s=budget)
+        if i >= args.warmup:
+            vals.append(v); times.append(dt)
+    value = float(np.mean(vals))
+    line = {"impl": "reference", "metric": "paths/sec scored", "value": value, "unit": "paths/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(times)),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(d, args.paths, args.gpus),
+            "cpu_baseline": {"value": value, "unit": "paths/s", "cores": cores, "kind": "port",
+                             "sample": "%d paths of the %d-path batch per step, fp64 C restatement with OpenMP "
+                                       "(Torch7 cannot run in this image)" % (n_s, args.paths)},
+            "e2e": {"value": value, "unit": "paths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(d, n_paths, gpus):
+    return {"workload": "BASELINE configs[1]: KG paths len<=6 (T=6, left-padded), d=%d convention A "
+                        "(d_t=d_e=d_r=H=%d, D=%d), %d paths/GPU/step, forward+pool (LSTM, L=46, LSE, sigmoid)" % (d, d, 3 * d, n_paths),
+            "paths_per_gpu": n_paths, "T": T, "d": d, "V_e": V_E, "segments": "1+Geom(0.57) paths per (user,item), CSR",
+            "entities": "Zipf(1.05) over 2.85M rows", "parallelism": "paths sharded x%d, no data-path collective" % gpus,
+            "l2": "8 rotating input batches; per-step working set (gathered rows + activations) exceeds the 126 MB L2"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--d", type=int, default=256)
+    ap.add_argument("--paths", type=int, default=N_PATHS)
+    ap.add_argument("--precision", type=int, default=-1, help="-1 auto (tensor-core split if supported), 0 fp32, 1 split, 2 fast")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from kprn_b200 import engine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    d = args.d
+    n_paths = args.paths
+    prec = args.precision
+    eng = None
+    if prec < 0:
+        try:
+            eng = engine.Engine(T=T, d_t=d, d_e=d, d_r=d, H=d, L=L, V_e=V_E, precision=engine.PREC_TC_SPLIT, device=local)
+            prec = engine.PREC_TC_SPLIT
+        except engine.KprnError:
+            eng = None
+    if eng is None:
+        prec = max(prec, 0) if args.precision >= 0 else engine.PREC_FP32
+        eng = engine.Engine(T=T, d_t=d, d_e=d, d_r=d, H=d, L=L, V_e=V_E, precision=prec, device=local)
+    eng.init_uniform(0.1, 12345)
+    eng.zero_row(engine.TABLE_TYPE, 6)
+    eng.zero_row(engine.TABLE_ENTITY, V_E)
+    eng.zero_row(engine.TABLE_RELATION, 9)
+    stream = torch.cuda.current_stream()
+    eng.set_stream(stream.cuda_stream)
+
+    NB = 8
+    batches = make_batches(NB, n_paths, seed=12345 + 1000 * rank)
+    dev = []
+    for ids, seg in batches:
+        dev.append((torch.from_numpy(ids).cuda(), torch.from_numpy(seg).cuda(), len(seg) - 1))
+    max_s = max(s for _, _, s in dev)
+    d_scores = torch.empty(max_s, dtype=torch.float32, device="cuda")
+
+    def step_device(i):
+        ids_t, seg_t, S = dev[i % NB]
+        eng.forward_device(ids_t.data_ptr(), seg_t.data_ptr(), n_paths, S, train=False, d_scores=d_scores.data_ptr())
+
+    try:
+        step_device(0)
+    except engine.KprnError as err:
+        if args.precision < 0 and prec != engine.PREC_FP32:
+            eng.close()
+            prec = engine.PREC_FP32
+            eng = engine.Engine(T=T, d_t=d, d_e=d, d_r=d, H=d, L=L, V_e=V_E, precision=prec, device=local)
+            eng.init_uniform(0.1, 12345)
+            eng.set_stream(stream.cuda_stream)
+            step_device(0)
+        else:
+            raise
+    for i in range(args.warmup):
+        step_device(i)
+    eng.sync()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    # ---- value: device-resident, CUDA events on the launching stream ----
+    eng.launch_count(reset=True)
+    eng.profile(True)
+    eng.profile_read(reset=True)
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for i in range(args.steps):
+        step_device(i)
+    ev1.record(stream)
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    launches = eng.launch_count(reset=True)
+    gate_ms, gate_n = eng.profile_read(reset=True)
+    eng.profile(False)
+    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_per_step = ms_total / args.steps
+    value = world * n_paths / (ms_per_step * 1e-3)
+
+    # ---- e2e: host buffers through the reference-facing call ----
+    host = [(np.ascontiguousarray(ids), np.ascontiguousarray(seg)) for ids, seg in batches]
+    for i in range(3):
+        eng.forward(host[i % NB][0], host[i % NB][1])
+    barrier()
+    t0 = time.perf_counter()
+    h2d = d2h = 0
+    for i in range(args.steps):
+        ids, seg = host[i % NB]
+        sc = eng.forward(ids, seg)
+        h2d += ids.nbytes + seg.nbytes
+        d2h += sc.nbytes
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = float(te.item())
+    e2e_value = world * n_paths * args.steps / e2e_s
+    time.sleep(0.2)
+    sampler.stop()
+
+    if rank == 0:
+        pk, pk_src = peaks()
+        fpp = flops_per_path(d, d, d, d)
+        mode = {0: "fp32 FFMA (CUDA cores)", 1: "tcgen05 kind::f16, 3-pass hi/lo split", 2: "tcgen05 kind::f16 single pass"}[prec]
+        mult = {0: 1, 1: 3, 2: 1}[prec]
+        roof = {"bound": "tensor", "unit": "TFLOP/s", "peak": pk["bf16_tflops_sustained"],
+                "peak_source": pk_src + " bf16_tflops_sustained (kernel timed inside a long step)",
+                "kernel": "gate phase (x-projection + recurrent LSTM kernels)", "mode": mode, "mma_multiplicity": mult,
+                "traffic": None}
+        if gate_n > 0 and gate_ms > 0:
+            per_launch_ms = gate_ms / gate_n
+            ach = fpp * n_paths / (per_launch_ms * 1e-3) / 1e12
+            roof.update({"achieved": ach, "frac": ach / roof["peak"], "launch_ms": per_launch_ms,
+                         "share_of_step": gate_ms / (ms_total / world if world == 1 else ms_total),
+                         "algorithmic_flops_per_launch": fpp * n_paths})
+        else:
+            ach = fpp * n_paths / (ms_per_step * 1e-3) / 1e12
+            roof.update({"achieved": ach, "frac": ach / roof["peak"], "launch_ms": ms_per_step,
+                         "note": "gate kernels not separately timed; whole step used"})
+        line = {"metric": "paths/sec scored", "value": value, "unit": "paths/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32" if prec == 0 else "f32 (bf16x3 split MMA, fp32 accumulate)", "data": "synthetic",
+                "config": workload_config(d, n_paths, world),
+                "e2e": {"value": e2e_value, "unit": "paths/s", "h2d_bytes_per_step": h2d // args.steps,
+                        "d2h_bytes_per_step": d2h // args.steps},
+                "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roof,
+                "hbm": {"gather_gbs": gather_bytes_per_path(d, d, d) * value / world / 1e9, "peak_gbs": pk["hbm_gbs"]}}
+        if not args.no_cpu_baseline:
+            v, n_s, dt, cores = cpu_port_throughput(d, budget_s=15.0)
+            line["cpu_baseline"] = {"value": v, "unit": "paths/s", "cores": cores, "kind": "port",
+                                    "sample": "%d paths of the batch, fp64 C restatement + OpenMP, %.1f s" % (n_s, dt)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    eng.close()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

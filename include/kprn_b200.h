@@ -1,0 +1,157 @@
+/*
+ * kprn_b200.h -- C ABI of the B200-native KPRN path-scoring engine (libkprn_b200.so).
+ *
+ * This is the drop-in boundary for ONE hot path of eBay/KPRN: what a LuaJIT-FFI shim
+ * (kprn_b200/lua/kprn_b200.lua, same declarations via ffi.cdef) binds instead of the
+ * reference's Torch7 nn graph.  Citations are relative to
+ * /root/reference/release/songPathRnn/ ("SP/").
+ *
+ * Conventions: C99, no C++ types, no callbacks.  Every function returns 0 on success or a
+ * non-zero KPRN_E* code; kprn_last_error() gives the thread-local message (the Lua shim
+ * turns it into error(), Torch7's convention).  Host pointers are owned by the caller and
+ * are not retained after the call returns.  Device memory is owned by the ctx.  A ctx is
+ * bound to one CUDA device and is not re-entrant; one ctx per host thread / Lua state.
+ * One process per GPU; multi-GPU runs exchange only the buffers exposed by
+ * kprn_params_device / kprn_grads_device (host side: NCCL all-reduce).
+ *
+ * There is NO CPU fallback: if no CUDA device is usable every call fails with KPRN_ECUDA.
+ */
+#ifndef KPRN_B200_H
+#define KPRN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KPRN_OK 0
+#define KPRN_EINVAL 1   /* bad argument / id out of range / shape mismatch */
+#define KPRN_ECUDA 2    /* CUDA runtime or launch failure, or no device    */
+#define KPRN_ESTATE 3   /* call order violated (e.g. backward before forward) */
+#define KPRN_ENOMEM 4
+
+/* cell: SP/model/OneModel.lua:235-254 */
+#define KPRN_CELL_LSTM 0 /* nn.FastLSTM(D,H), -rnnType lstm */
+#define KPRN_CELL_RNN 1  /* ReLU Elman RNN + MaskZero, -rnnType rnn (shipped config.sh:33) */
+/* pool: SP/model/OneModel.lua:284-293, SP/eval/test_from_checkpoint.lua:70-79 */
+#define KPRN_POOL_LSE 0  /* topK=2: nn.LogSumExp(2) (SP/model/module/LogSumExp.lua) */
+#define KPRN_POOL_MAX 1  /* topK=0: nn.Max(2) */
+#define KPRN_POOL_TOPK 2 /* topK=1: nn.TopK(k,2) + nn.Mean(2) (SP/model/module/TopK.lua) */
+/* precision of the gate GEMMs */
+#define KPRN_PREC_FP32 0     /* CUDA-core FFMA, fp32 everywhere */
+#define KPRN_PREC_TC_SPLIT 1 /* tcgen05 kind::f16, 3-pass hi/lo split (parity mode on tensor cores) */
+#define KPRN_PREC_TC_FAST 2  /* tcgen05 kind::f16, single pass (NOT parity-certified) */
+/* tables for kprn_zero_row */
+#define KPRN_TABLE_TYPE 0
+#define KPRN_TABLE_ENTITY 1
+#define KPRN_TABLE_RELATION 2
+
+typedef struct kprn_ctx kprn_ctx;
+
+/* Model + engine configuration.  Replaces the torch.CmdLine flags of SP/model/OneModel.lua:27-87
+ * that shape the hot path (-relationEmbeddingDim, -entityTypeEmbeddingDim, -entityEmbeddingDim,
+ * -rnnHidSize, -relationVocabSize, -entityVocabSize, -entityTypeVocabSize, -rnnType, -topK, -k)
+ * and the hard-coded labelDimension=46 (OneModel.lua:119) / classId (MyOptimizer.lua:126). */
+typedef struct kprn_config {
+    int32_t T;            /* steps per path (movie_data_format.sh:2 "-m 6") */
+    int32_t d_t, d_e, d_r;/* embedding widths: type, entity, relation; D = d_t+d_e+d_r */
+    int32_t H;            /* rnnHidSize */
+    int32_t L;            /* labelDimension (46 in the reference) */
+    int64_t V_t, V_e, V_r;/* vocabulary sizes (rows of the three nn.LookupTable) */
+    int32_t cell;         /* KPRN_CELL_* */
+    int32_t head_layers;  /* 1 = nn.Linear(H,L) (OneModel.lua:275); 2 = Linear(H,H)-ReLU-Linear(H,L) */
+    int32_t pool;         /* KPRN_POOL_* */
+    int32_t topk;         /* k of KPRN_POOL_TOPK */
+    float inv_gamma;      /* LSE temperature, 1.0 = reference */
+    int32_t class_id;     /* 1-based column selected by nn.Select(2,classId) */
+    int32_t precision;    /* KPRN_PREC_* */
+    int32_t device;       /* CUDA device ordinal */
+    int32_t reserved;
+} kprn_config;
+
+const char* kprn_last_error(void);
+const char* kprn_version(void);
+
+/* ctx lifetime. kprn_create allocates parameters (zero-filled), gradients and optimizer state on
+ * cfg->device.  Replaces the graph construction of SP/model/OneModel.lua:203-294. */
+int kprn_create(const kprn_config* cfg, kprn_ctx** out);
+int kprn_destroy(kprn_ctx* ctx);
+/* run subsequent work on an existing cudaStream_t (void* to keep the header CUDA-free); NULL = ctx's own stream */
+int kprn_set_stream(kprn_ctx* ctx, void* cuda_stream);
+int kprn_sync(kprn_ctx* ctx);
+
+/* Flat parameter vector, order E_type,E_entity,E_relation,Wx,bx,Wh,[bh],[W1,b1],Wo,bo -- the DFS order
+ * of nn.Module:getParameters() that MyOptimizer.lua:42 flattens.  offsets[11] in that order
+ * (E_t,E_e,E_r,Wx,bx,Wh,bh,W1,b1,Wo,bo), -1 when absent. */
+int kprn_param_count(kprn_ctx* ctx, int64_t* n);
+int kprn_param_offsets(kprn_ctx* ctx, int64_t* offsets11);
+int kprn_set_params(kprn_ctx* ctx, const float* host, int64_t n);       /* checkpoints / tests (torch.load) */
+int kprn_set_params_f64(kprn_ctx* ctx, const double* host, int64_t n);  /* Torch7 CPU checkpoints are DoubleTensor */
+int kprn_get_params(kprn_ctx* ctx, float* host, int64_t n);             /* saver hook OneModel.lua:393-401 */
+int kprn_get_grads(kprn_ctx* ctx, float* host, int64_t n);
+int kprn_init_uniform(kprn_ctx* ctx, float scale, uint64_t seed);       /* param:uniform(-s,s), OneModel.lua:306-309 */
+/* raw device views for the host-side NCCL all-reduce (one process per GPU) */
+int kprn_params_device(kprn_ctx* ctx, float** dptr, int64_t* n);
+int kprn_grads_device(kprn_ctx* ctx, float** dptr, int64_t* n);
+
+/* params[1][idx]:zero() of MyOptimizer:zeroPadTokens (MyOptimizer.lua:74-93); row is 1-based. */
+int kprn_zero_row(kprn_ctx* ctx, int table, int64_t row_1based);
+
+/*
+ * model:forward(inputs) of MyOptimizer.lua:189 / test_from_checkpoint.lua:109 for the fused graph
+ * MapReduce(predictor_net, reducer) -> Sigmoid -> Select(2,classId)   (OneModel.lua:294).
+ *   ids         [N,T,3] int32, 1-based, columns (type, entity, relation)   (Batcher.lua:43-54 data)
+ *   seg_offsets [S+1] CSR offsets over consecutive paths; NULL + paths_per_seg>0 = dense bucket [S,P]
+ *   out_scores  [S]   sigmoid(pool)[:,class_id]          (may be NULL)
+ *   out_logits  [S,L] pooled logits before the sigmoid   (may be NULL)
+ * train != 0 keeps the activations needed by kprn_backward.
+ * Host-pointer variant: copies in/out through pinned staging inside the timed call.
+ */
+int kprn_forward(kprn_ctx* ctx, const int32_t* ids, const int32_t* seg_offsets, int64_t N, int64_t S,
+                 int32_t paths_per_seg, int32_t train, float* out_scores, float* out_logits);
+/* same, reference tensor layout: data[B,P,T,3] DoubleTensor of 1-based ids (SP/util/Util.lua:121-201) */
+int kprn_forward_f64ids(kprn_ctx* ctx, const double* ids_f64, int64_t B, int64_t P, int32_t train,
+                        float* out_scores, float* out_logits);
+/* device-pointer variant: everything already resident in HBM, fully asynchronous on the ctx stream */
+int kprn_forward_device(kprn_ctx* ctx, const int32_t* d_ids, const int32_t* d_seg_offsets, int64_t N, int64_t S,
+                        int32_t train, float* d_out_scores, float* d_out_logits);
+/* per-path head outputs s[N,L] of the last forward (MapReduce's "mapped", MapReduce.lua:33) -- tests/diagnostics */
+int kprn_get_path_logits(kprn_ctx* ctx, float* host, int64_t n_floats);
+
+/* criterion:forward + criterion:backward (MyOptimizer.lua:193-194) on the scores of the last forward;
+ * caches dL/dscore for kprn_backward.  BCE = nn.BCECriterion (OneModel.lua:300), labels[S] in {0,1}. */
+int kprn_loss_bce(kprn_ctx* ctx, const float* labels, int64_t S, float* loss);
+/* nn.BPRLoss (SP/model/criterion/BPRLoss.lua:18-32) over pairs of segments of the last forward:
+ * input = { scores[pos_seg[i]], scores[neg_seg[i]] } (0-based segment indices), reference's gradient
+ * (not divided by n).  apply_to_logits != 0 pairs the pooled class logits instead of the sigmoid scores. */
+int kprn_loss_bpr(kprn_ctx* ctx, const int32_t* pos_seg, const int32_t* neg_seg, int64_t n_pairs,
+                  int32_t apply_to_logits, float* loss);
+
+/* model:backward(inputs, df_do) (MyOptimizer.lua:195): BPTT through pool, head, cell and the three
+ * lookup tables; ACCUMULATES into the gradient buffer (accGradParameters), times `scale`.
+ * grad_scores [S] = dL/dscore from the caller, or NULL to use the cached loss gradient. */
+int kprn_backward(kprn_ctx* ctx, const float* grad_scores, float scale);
+int kprn_zero_grad(kprn_ctx* ctx);                      /* model:zeroGradParameters(), MyOptimizer.lua:186 */
+int kprn_grad_norm(kprn_ctx* ctx, float* norm);         /* gradParameters:norm(), MyOptimizer.lua:198 */
+int kprn_grad_scale(kprn_ctx* ctx, float s);            /* gradParameters:mul(), MyOptimizer.lua:200 */
+int kprn_grad_add_params(kprn_ctx* ctx, float l2);      /* gradParameters:add(l2, parameters), :203/:212 */
+/* optim.adam on the flat vector (OneModel.lua:340-355, MyOptimizer.lua:218); dense like the reference. */
+int kprn_adam_step(kprn_ctx* ctx, float lr, float beta1, float beta2, float eps);
+/* one whole MyOptimizer:trainBatch (MyOptimizer.lua:177-221) with BCE: zero pad rows -> zero grad ->
+ * forward -> BCE -> backward -> [clip + l2] -> Adam -> zero pad rows.  pad_rows[3] 1-based, 0 = none. */
+int kprn_train_batch_bce(kprn_ctx* ctx, const int32_t* ids, const int32_t* seg_offsets, int64_t N, int64_t S,
+                         const float* labels, const int64_t* pad_rows3, int32_t regularize, int32_t use_clip,
+                         float clip_norm, float l2, float lr, float beta1, float beta2, float eps, float* loss);
+
+/* counters for bench.py: kernels launched by this library since the last reset */
+int kprn_launch_count(kprn_ctx* ctx, int64_t* n, int32_t reset);
+/* device time (ms) of the dominant kernel class accumulated since reset, measured with CUDA events
+ * on the ctx stream when profiling is enabled (kprn_profile(ctx,1)); 0 otherwise. */
+int kprn_profile(kprn_ctx* ctx, int32_t enable);
+int kprn_profile_read(kprn_ctx* ctx, float* ms_gate_kernels, int64_t* n_gate_launches, int32_t reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KPRN_B200_H */

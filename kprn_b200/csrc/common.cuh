@@ -1,0 +1,106 @@
+// common.cuh -- ctx layout and helpers shared by the kprn_b200 translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/kprn_b200.h"
+
+namespace kprn {
+
+struct Layout {
+    int64_t E_t, E_e, E_r, Wx, bx, Wh, bh, W1, b1, Wo, bo, total;
+    int32_t G, D;
+};
+
+// Growable device buffer.
+struct DBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct TcState;  // tensor-core path state (tc_path.cu)
+
+}  // namespace kprn
+
+struct kprn_ctx {
+    kprn_config cfg;
+    kprn::Layout lay;
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    float* d_params = nullptr;
+    float* d_grads = nullptr;
+    float* d_m = nullptr;
+    float* d_v = nullptr;
+    int64_t adam_t = 0;
+    uint64_t params_version = 1;   // bumped on every parameter mutation (tc path repacks weights)
+    // last-forward state
+    int64_t N = 0, S = 0;
+    bool have_fwd = false, have_train_cache = false, have_loss_grad = false;
+    bool ids_on_host_copy = false;
+    const int32_t* d_ids = nullptr;      // ids of the last forward (ctx-owned copy or caller's device ptr)
+    const int32_t* d_seg = nullptr;
+    kprn::DBuf ids_buf, seg_buf, path_logits, seg_logits, scores, dscores, dseg_logits, labels, tmp_small;
+    kprn::DBuf act, cst, hst, z1;                  // training caches [N,T,G] [N,T,H] [N,T,H] [N,H]
+    kprn::DBuf ws_x, ws_xw, ws_h0, ws_h1, ws_c, ws_dg, ws_dx, ws_dh, ws_dc, ws_ds, ws_dz;
+    kprn::DBuf pair_buf;
+    int32_t* d_err = nullptr;           // device error flag (bad ids)
+    // pinned staging
+    void* h_stage = nullptr;
+    size_t h_stage_cap = 0;
+    int64_t launches = 0;
+    bool profiling = false;
+    float prof_ms = 0.f;
+    int64_t prof_launches = 0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_pending;
+    kprn::TcState* tc = nullptr;
+};
+
+namespace kprn {
+
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+#define KPRN_CUDA(expr)                                                        \
+    do {                                                                       \
+        cudaError_t _e = (expr);                                               \
+        if (_e != cudaSuccess) return kprn::cuda_fail(_e, #expr, __FILE__, __LINE__); \
+    } while (0)
+
+#define KPRN_TRY(expr)              \
+    do {                            \
+        int _rc = (expr);           \
+        if (_rc != KPRN_OK) return _rc; \
+    } while (0)
+
+#define KPRN_LAUNCH_CHECK(ctx)                                                  \
+    do {                                                                        \
+        (ctx)->launches++;                                                      \
+        cudaError_t _e = cudaGetLastError();                                    \
+        if (_e != cudaSuccess) return kprn::cuda_fail(_e, "kernel launch", __FILE__, __LINE__); \
+    } while (0)
+
+int ensure(DBuf& b, size_t bytes);
+int ensure_stage(kprn_ctx* ctx, size_t bytes);
+
+static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---- fp32 CUDA-core path (kernels_simple.cu) ----
+int simple_forward(kprn_ctx* ctx, const int32_t* d_ids, const int32_t* d_seg, int64_t N, int64_t S, bool train);
+int simple_backward(kprn_ctx* ctx, float scale);
+int pool_forward(kprn_ctx* ctx, const int32_t* d_seg, int64_t S, float* d_out_scores, float* d_out_logits);
+int head_forward(kprn_ctx* ctx, const float* d_hT, int64_t ldh, int64_t n0, int64_t nb, float* z1_opt);
+
+// generic fp32 GEMM: C[m,n] (=|+=) alpha * sum_k A(m,k) B(k,n); element strides given explicitly.
+int sgemm(kprn_ctx* ctx, int64_t M, int64_t N, int64_t K, const float* A, int64_t sAm, int64_t sAk,
+          const float* B, int64_t sBk, int64_t sBn, float* C, int64_t ldc, bool accumulate, int splitk = 1);
+
+// ---- tensor-core path (tc_path.cu) ----
+bool tc_supported(const kprn_ctx* ctx);
+int tc_forward(kprn_ctx* ctx, const int32_t* d_ids, const int32_t* d_seg, int64_t N, int64_t S, bool train);
+void tc_destroy(kprn_ctx* ctx);
+
+}  // namespace kprn

@@ -1,0 +1,142 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the fp64 oracle on the same inputs.
+Tolerance: 1e-4 relative (tests/util.py:assert_rel), the figure BASELINE.json's north_star states for fp32."""
+import numpy as np
+import pytest
+
+from tests.util import assert_rel, engine_for, make_case
+
+pytestmark = pytest.mark.gpu
+
+FWD_CASES = [
+    dict(N=200, seed=1),
+    dict(N=333, seed=2, d_t=5, d_e=10, d_r=5, H=25),                     # reference ratio, odd sizes
+    dict(N=1000, seed=3, T=3, d_t=32, d_e=32, d_r=32, H=32, V_e=5000),   # BASELINE configs[0]
+    dict(N=64, seed=4, seg_mode="dense", fixed_p=4),
+    dict(N=257, seed=5, cell=1),
+    dict(N=257, seed=6, pool=1),
+    dict(N=257, seed=7, pool=2, topk=2),
+    dict(N=257, seed=8, head_layers=2, L=1),
+    dict(N=257, seed=9, inv_gamma=0.5),
+    dict(N=1, seed=10),
+]
+
+
+@pytest.mark.parametrize("kw", FWD_CASES)
+def test_forward_matches_oracle_fp32(kw):
+    o, params, ids, seg, labels = make_case(**kw)
+    ref = o.forward(params, ids, seg)
+    e = engine_for(o, precision=0)
+    e.set_params(params)
+    scores, logits = e.forward(ids, seg, want_logits=True)
+    assert_rel(e.path_logits(ids.shape[0]), ref["path_logits"], what="path_logits")
+    assert_rel(logits, ref["seg_logits"], what="seg_logits")
+    assert_rel(scores, ref["scores"], what="scores")
+    e.close()
+
+
+@pytest.mark.parametrize("kw", FWD_CASES[:9])
+def test_bce_backward_matches_oracle(kw):
+    o, params, ids, seg, labels = make_case(**kw)
+    ref = o.forward(params, ids, seg, cache=True)
+    loss_ref, dsc = o.bce(ref["scores"], labels)
+    g_ref = o.backward(params, ids, seg, ref, dsc)
+    e = engine_for(o, precision=0)
+    e.set_params(params)
+    e.zero_grad()
+    e.forward(ids, seg, train=True)
+    loss = e.loss_bce(labels)
+    assert abs(loss - loss_ref) <= 1e-4 * abs(loss_ref)
+    e.backward()
+    g = e.get_grads()
+    for name, shp in o.shapes().items():
+        assert_rel(o.view(g, name), o.view(g_ref, name), what="grad " + name)
+    # accGradParameters accumulates: a second backward with scale doubles + scales
+    e.backward(scale=0.5)
+    assert_rel(e.get_grads(), 1.5 * g_ref, what="accumulated grads")
+    e.close()
+
+
+def test_bpr_loss_and_grad_match_oracle():
+    o, params, ids, seg, labels = make_case(N=300, seed=11)
+    ref = o.forward(params, ids, seg, cache=True)
+    S = len(seg) - 1
+    rng = np.random.default_rng(0)
+    pos = rng.integers(0, S, 64).astype(np.int32)
+    neg = rng.integers(0, S, 64).astype(np.int32)
+    loss_ref, dp, dn = o.bpr(ref["scores"][pos], ref["scores"][neg])
+    dsc = np.zeros(S)
+    np.add.at(dsc, pos, dp)
+    np.add.at(dsc, neg, dn)
+    g_ref = o.backward(params, ids, seg, ref, dsc)
+    e = engine_for(o)
+    e.set_params(params)
+    e.zero_grad()
+    e.forward(ids, seg, train=True)
+    loss = e.loss_bpr(pos, neg)
+    assert abs(loss - loss_ref) <= 1e-4 * abs(loss_ref)
+    e.backward()
+    assert_rel(e.get_grads(), g_ref, what="bpr grads")
+    e.close()
+
+
+def test_external_grad_scores_and_f64_ids_layout():
+    o, params, ids, seg, labels = make_case(N=64, seed=12, seg_mode="dense", fixed_p=4)
+    ref = o.forward(params, ids, seg, cache=True)
+    e = engine_for(o)
+    e.set_params(params)
+    data = ids.reshape(16, 4, o.cfg.T, 3).astype(np.float64)     # Batcher tensor: [B,P,T,3] DoubleTensor
+    scores = e.forward_f64ids(data, train=True)
+    assert_rel(scores, ref["scores"], what="scores via f64 ids")
+    rng = np.random.default_rng(1)
+    dsc = rng.normal(size=16)
+    g_ref = o.backward(params, ids, seg, ref, dsc)
+    e.zero_grad()
+    e.backward(grad_scores=dsc)
+    assert_rel(e.get_grads(), g_ref, what="grads from external dL/dscore")
+    e.close()
+
+
+def test_train_batch_matches_oracle_trainBatch():
+    """MyOptimizer:trainBatch (MyOptimizer.lua:177-221): pad zero -> fwd -> BCE -> bwd -> clip+l2 -> Adam -> pad zero."""
+    o, params, ids, seg, labels = make_case(N=200, seed=13)
+    c = o.cfg
+    pads = (c.V_t, c.V_e, c.V_r)
+    e = engine_for(o)
+    p0 = params.copy()
+    p0[:] += 0.0
+    e.set_params(p0)
+    P = p0.copy()
+    m = np.zeros_like(P); v = np.zeros_like(P)
+    for step in (1, 2, 3):
+        loss = e.train_batch_bce(ids, seg, labels, pad_rows=pads, regularize=True, use_clip=True, clip_norm=0.05, l2=1e-3)
+        for tbl, row in enumerate(pads):
+            o.zero_row(P, tbl, row)
+        fwd = o.forward(P, ids, seg, cache=True)
+        loss_ref, dsc = o.bce(fwd["scores"], labels.astype(np.float64))
+        g = o.backward(P, ids, seg, fwd, dsc)
+        o.clip_l2(g, P, True, 0.05, 1e-3)
+        o.adam(P, g, m, v, step)
+        for tbl, row in enumerate(pads):
+            o.zero_row(P, tbl, row)
+        assert abs(loss - loss_ref) <= 2e-4 * abs(loss_ref)
+    # Adam normalises by sqrt(v): early steps move every touched parameter by ~lr, so compare the update itself
+    upd, upd_ref = e.get_params() - p0, P - p0
+    assert_rel(upd, upd_ref, rtol=2e-3, what="parameter update after 3 Adam steps")
+    e.close()
+
+
+def test_errors_are_loud():
+    from kprn_b200.engine import KprnError
+    o, params, ids, seg, labels = make_case(N=32, seed=14)
+    e = engine_for(o)
+    e.set_params(params)
+    bad = ids.copy(); bad[3, 2, 1] = o.cfg.V_e + 1
+    with pytest.raises(KprnError):
+        e.forward(bad, seg)
+    with pytest.raises(KprnError):
+        e.backward()                      # no training forward yet
+    badseg = seg.copy(); badseg[-1] -= 1
+    with pytest.raises(KprnError):
+        e.forward(ids, badseg)
+    e.forward(ids, seg)                   # still usable afterwards
+    e.close()
