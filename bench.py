@@ -210,7 +210,9 @@ def main():
     eng.zero_row(engine.TABLE_TYPE, 6)
     eng.zero_row(engine.TABLE_ENTITY, V_E)
     eng.zero_row(engine.TABLE_RELATION, 9)
-    stream = torch.cuda.current_stream()
+    # a non-default stream: the legacy default stream has handle 0, which the ABI reads as "ctx's own stream"
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     eng.set_stream(stream.cuda_stream)
 
     NB = 8

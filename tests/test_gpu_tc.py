@@ -1,0 +1,77 @@
+"""GPU parity tests for the tcgen05 tensor-core path (KPRN_PREC_TC_SPLIT = bf16x3 split, fp32 accumulate in TMEM)
+against the fp64 oracle, 1e-4 relative (tests/util.py:assert_rel)."""
+import numpy as np
+import pytest
+
+from tests.util import assert_rel, engine_for, make_case
+
+pytestmark = pytest.mark.gpu
+
+TC_CASES = [
+    dict(N=128, seed=1, d_t=8, d_e=64, d_r=8, H=64, V_e=500),
+    dict(N=300, seed=2, d_t=16, d_e=128, d_r=16, H=128, V_e=2000),                 # ragged last tile
+    dict(N=1000, seed=3, d_t=32, d_e=256, d_r=32, H=256, V_e=5000),
+    dict(N=333, seed=4, d_t=50, d_e=100, d_r=50, H=250, V_e=3000),                 # reference default dims (padded to 128/256)
+    dict(N=1, seed=5, d_t=8, d_e=64, d_r=8, H=64, V_e=500),
+    dict(N=1000, seed=6, T=3, d_t=32, d_e=32, d_r=32, H=32, V_e=5000),            # BASELINE configs[0] dims
+    dict(N=40000, seed=7, d_t=8, d_e=64, d_r=8, H=64, V_e=50000),                  # > 148 tiles: persistent loop
+    dict(N=500, seed=8, d_t=8, d_e=64, d_r=8, H=64, V_e=500, pool=1),
+    dict(N=500, seed=9, d_t=8, d_e=64, d_r=8, H=64, V_e=500, head_layers=2, L=1),
+]
+
+
+@pytest.mark.parametrize("kw", TC_CASES)
+def test_tc_forward_matches_oracle(kw):
+    o, params, ids, seg, labels = make_case(**kw)
+    ref = o.forward(params, ids, seg)
+    e = engine_for(o, precision=1)
+    e.set_params(params)
+    scores, logits = e.forward(ids, seg, want_logits=True)
+    assert_rel(e.path_logits(ids.shape[0]), ref["path_logits"], what="path_logits")
+    assert_rel(logits, ref["seg_logits"], what="seg_logits")
+    assert_rel(scores, ref["scores"], what="scores")
+    # a second call with changed parameters must repack the weights
+    p2 = params.copy()
+    o.view(p2, "Wh")[:] *= 0.5
+    e.set_params(p2)
+    ref2 = o.forward(p2, ids, seg)
+    assert_rel(e.forward(ids, seg), ref2["scores"], what="scores after parameter update")
+    e.close()
+
+
+def test_tc_big_dims_d256_full_batch_properties():
+    """BASELINE size (d=256, 65 536 paths): size-independent properties instead of the (slow) oracle:
+    (1) segment-permutation invariance, (2) agreement with the fp32 CUDA-core engine on the same inputs."""
+    from kprn_b200 import synth
+    from kprn_b200.engine import Engine
+    N, V_e, d = 65536, 200000, 256
+    ids = synth.make_paths(N, V_e=V_e, seed=1)
+    seg = synth.make_segments(N, mode="dense", fixed_p=4)
+    outs = []
+    for prec in (1, 0):
+        e = Engine(d_t=d, d_e=d, d_r=d, H=d, V_e=V_e, precision=prec)
+        e.init_uniform(0.1, 7)
+        e.zero_row(1, V_e)
+        s1 = e.forward(ids, seg)
+        perm = np.arange(N).reshape(-1, 4)[:, ::-1].reshape(-1)
+        s2 = e.forward(ids[perm], seg)
+        assert_rel(s2, s1, rtol=1e-5, what="segment permutation invariance")
+        outs.append(s1)
+        e.close()
+    assert_rel(outs[0], outs[1], what="tensor-core vs fp32 engine at d=256, N=65536")
+
+
+def test_tc_train_forward_and_backward_run():
+    """precision=1 with train=1 keeps the fp32 training caches; gradients still match the oracle."""
+    o, params, ids, seg, labels = make_case(N=256, seed=10, d_t=8, d_e=64, d_r=8, H=64, V_e=500)
+    ref = o.forward(params, ids, seg, cache=True)
+    loss_ref, dsc = o.bce(ref["scores"], labels)
+    g_ref = o.backward(params, ids, seg, ref, dsc)
+    e = engine_for(o, precision=1)
+    e.set_params(params)
+    e.zero_grad()
+    e.forward(ids, seg, train=True)
+    e.loss_bce(labels)
+    e.backward()
+    assert_rel(e.get_grads(), g_ref, what="grads")
+    e.close()
