@@ -203,7 +203,7 @@ static int check_err_flag(kprn_ctx* ctx) {
 static int params_changed(kprn_ctx* ctx) { ctx->params_version++; return KPRN_OK; }
 
 static int forward_device_impl(kprn_ctx* ctx, const int32_t* d_ids, const int32_t* d_seg, int64_t N, int64_t S,
-                               bool train, float* d_out_scores, float* d_out_logits) {
+                               bool train, bool want_logits, float* d_out_scores, float* d_out_logits) {
     const kprn_config& c = ctx->cfg;
     if (N <= 0 || S <= 0) { set_error("empty batch: N=%lld S=%lld", (long long)N, (long long)S); return KPRN_EINVAL; }
     if (N * (int64_t)c.T * 3 >= (1ll << 40)) { set_error("batch too large"); return KPRN_EINVAL; }
@@ -213,6 +213,8 @@ static int forward_device_impl(kprn_ctx* ctx, const int32_t* d_ids, const int32_
     KPRN_LAUNCH_CHECK(ctx);
     ctx->N = N; ctx->S = S; ctx->d_ids = d_ids; ctx->d_seg = d_seg;
     ctx->have_loss_grad = false;
+    // scores-only fast path: nothing downstream of nn.Select(2,classId) needs the other L-1 columns
+    ctx->cls_only = !train && !want_logits && c.head_layers == 1;
     bool use_tc = c.precision != KPRN_PREC_FP32 && tc_supported(ctx);
     if (c.precision != KPRN_PREC_FP32 && !use_tc) {
         set_error("precision mode %d (tensor cores) does not support this configuration", c.precision);
@@ -417,13 +419,13 @@ int kprn_forward_device(kprn_ctx* ctx, const int32_t* d_ids, const int32_t* d_se
                         float* d_out_scores, float* d_out_logits) {
     KPRN_TRY(check_ctx(ctx));
     if (!d_ids || !d_seg) { set_error("forward_device: null ids/seg"); return KPRN_EINVAL; }
-    return forward_device_impl(ctx, d_ids, d_seg, N, S, train != 0, d_out_scores, d_out_logits);
+    return forward_device_impl(ctx, d_ids, d_seg, N, S, train != 0, d_out_logits != nullptr, d_out_scores, d_out_logits);
 }
 
 static int forward_host_common(kprn_ctx* ctx, int64_t N, int64_t S, int32_t train, float* out_scores, float* out_logits) {
     // ids / seg are already on the device in ctx->ids_buf / ctx->seg_buf
     const kprn_config& c = ctx->cfg;
-    KPRN_TRY(forward_device_impl(ctx, ctx->ids_buf.as<int32_t>(), ctx->seg_buf.as<int32_t>(), N, S, train != 0, nullptr, nullptr));
+    KPRN_TRY(forward_device_impl(ctx, ctx->ids_buf.as<int32_t>(), ctx->seg_buf.as<int32_t>(), N, S, train != 0, out_logits != nullptr, nullptr, nullptr));
     size_t need = sizeof(float) * (size_t)(S + S * c.L);
     KPRN_TRY(ensure_stage(ctx, need));
     float* hs = (float*)ctx->h_stage;
@@ -484,6 +486,7 @@ int kprn_forward_f64ids(kprn_ctx* ctx, const double* ids_f64, int64_t B, int64_t
 int kprn_get_path_logits(kprn_ctx* ctx, float* host, int64_t n_floats) {
     KPRN_TRY(check_ctx(ctx));
     if (!ctx->have_fwd) { set_error("get_path_logits: no forward yet"); return KPRN_ESTATE; }
+    if (ctx->cls_only) { set_error("get_path_logits: the last forward was scores-only (request logits or train=1 to materialise all L columns)"); return KPRN_ESTATE; }
     if (!host || n_floats != ctx->N * ctx->cfg.L) { set_error("get_path_logits: expected %lld floats", (long long)(ctx->N * ctx->cfg.L)); return KPRN_EINVAL; }
     KPRN_CUDA(cudaMemcpyAsync(host, ctx->path_logits.p, sizeof(float) * n_floats, cudaMemcpyDeviceToHost, ctx->stream));
     KPRN_CUDA(cudaStreamSynchronize(ctx->stream));

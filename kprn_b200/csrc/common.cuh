@@ -41,6 +41,7 @@ struct kprn_ctx {
     int64_t N = 0, S = 0;
     bool have_fwd = false, have_train_cache = false, have_loss_grad = false;
     bool ids_on_host_copy = false;
+    bool cls_only = false;          // last forward materialised only the class column (scores-only fast path)
     const int32_t* d_ids = nullptr;      // ids of the last forward (ctx-owned copy or caller's device ptr)
     const int32_t* d_seg = nullptr;
     kprn::DBuf ids_buf, seg_buf, path_logits, seg_logits, scores, dscores, dseg_logits, labels, tmp_small;
@@ -93,6 +94,7 @@ int simple_forward(kprn_ctx* ctx, const int32_t* d_ids, const int32_t* d_seg, in
 int simple_backward(kprn_ctx* ctx, float scale);
 int pool_forward(kprn_ctx* ctx, const int32_t* d_seg, int64_t S, float* d_out_scores, float* d_out_logits);
 int head_forward(kprn_ctx* ctx, const float* d_hT, int64_t ldh, int64_t n0, int64_t nb, float* z1_opt);
+int head_forward_cls(kprn_ctx* ctx, const float* d_hT, int64_t ldh, int64_t n0, int64_t nb);
 
 // generic fp32 GEMM: C[m,n] (=|+=) alpha * sum_k A(m,k) B(k,n); element strides given explicitly.
 int sgemm(kprn_ctx* ctx, int64_t M, int64_t N, int64_t K, const float* A, int64_t sAm, int64_t sAk,

@@ -147,16 +147,41 @@ int head_forward(kprn_ctx* ctx, const float* d_hT, int64_t ldh, int64_t n0, int6
     return KPRN_OK;
 }
 
+// scores-only fast path: only column classId of nn.Linear(H,L) feeds nn.Select(2,classId) (MyOptimizer.lua:126,
+// test_from_checkpoint.lua:82), so a scoring pass needs one dot product per path.  One warp per path.
+__global__ void head_cls_kernel(const float* __restrict__ hT, int64_t ldh, const float* __restrict__ wrow, const float* __restrict__ b, int H,
+                                int64_t nb, float* __restrict__ out, int L, int cls) {
+    int64_t p = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (p >= nb) return;
+    int lane = threadIdx.x & 31;
+    const float* h = hT + p * ldh;
+    float acc = 0.f;
+    for (int k = lane; k < H; k += 32) acc = fmaf(h[k], wrow[k], acc);
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) out[p * L + cls] = acc + *b;
+}
+
+int head_forward_cls(kprn_ctx* ctx, const float* d_hT, int64_t ldh, int64_t n0, int64_t nb) {
+    const kprn_config& c = ctx->cfg;
+    const Layout& l = ctx->lay;
+    const int cls = c.class_id - 1;
+    float* pl = ctx->path_logits.as<float>() + n0 * c.L;
+    head_cls_kernel<<<(unsigned)cdiv(nb, 8), 256, 0, ctx->stream>>>(d_hT, ldh, ctx->d_params + l.Wo + (int64_t)cls * c.H, ctx->d_params + l.bo + cls, c.H,
+                                                                    nb, pl, c.L, cls);
+    KPRN_LAUNCH_CHECK(ctx);
+    return KPRN_OK;
+}
+
 // A6+A7: MapReduce views (MapReduce.lua:32-47) + reducer + nn.Sigmoid + nn.Select(2,classId).
 //   LSE: module/LogSumExp.lua:13-30; max: nn.Max(2); top-k mean: module/TopK.lua + nn.Mean(2).
 // One thread per (segment, column); adjacent threads read adjacent columns (coalesced).
 __global__ void pool_fwd_kernel(const float* __restrict__ s, const int32_t* __restrict__ seg, int64_t S, int L,
-                                int pool, int topk, float ig, int cls, float* __restrict__ seg_logits,
+                                int pool, int topk, float ig, int cls, int col0, int ncols, float* __restrict__ seg_logits,
                                 float* __restrict__ scores, float* __restrict__ out_scores, float* __restrict__ out_logits) {
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= S * L) return;
-    int64_t k = idx / L;
-    int j = (int)(idx % L);
+    if (idx >= S * ncols) return;
+    int64_t k = idx / ncols;
+    int j = col0 + (int)(idx % ncols);
     int64_t a = seg[k], b = seg[k + 1];
     float out = 0.f;
     if (b > a) {
@@ -202,8 +227,9 @@ int pool_forward(kprn_ctx* ctx, const int32_t* d_seg, int64_t S, float* d_out_sc
     KPRN_TRY(ensure(ctx->seg_logits, sizeof(float) * S * c.L));
     KPRN_TRY(ensure(ctx->scores, sizeof(float) * S));
     float ig = c.inv_gamma == 0.f ? 1.f : c.inv_gamma;
-    pool_fwd_kernel<<<(unsigned)cdiv(S * c.L, 256), 256, 0, ctx->stream>>>(
-        ctx->path_logits.as<float>(), d_seg, S, c.L, c.pool, c.topk, ig, c.class_id - 1,
+    const int col0 = ctx->cls_only ? c.class_id - 1 : 0, ncols = ctx->cls_only ? 1 : c.L;
+    pool_fwd_kernel<<<(unsigned)cdiv(S * ncols, 256), 256, 0, ctx->stream>>>(
+        ctx->path_logits.as<float>(), d_seg, S, c.L, c.pool, c.topk, ig, c.class_id - 1, col0, ncols,
         ctx->seg_logits.as<float>(), ctx->scores.as<float>(), d_out_scores, d_out_logits);
     KPRN_LAUNCH_CHECK(ctx);
     return KPRN_OK;
@@ -284,7 +310,8 @@ int simple_forward(kprn_ctx* ctx, const int32_t* d_ids, const int32_t* d_seg, in
         }
         const float* hT = train ? ctx->hst.as<float>() + (n0 * T + (T - 1)) * H : ctx->ws_h0.as<float>();
         float* z1 = c.head_layers == 2 ? (train ? ctx->z1.as<float>() + n0 * H : ctx->z1.as<float>()) : nullptr;
-        KPRN_TRY(head_forward(ctx, hT, train ? (int64_t)T * H : H, n0, nb, z1));
+        if (ctx->cls_only) KPRN_TRY(head_forward_cls(ctx, hT, train ? (int64_t)T * H : H, n0, nb));
+        else KPRN_TRY(head_forward(ctx, hT, train ? (int64_t)T * H : H, n0, nb, z1));
     }
     (void)S; (void)d_seg;
     return KPRN_OK;

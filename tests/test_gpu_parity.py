@@ -140,3 +140,20 @@ def test_errors_are_loud():
         e.forward(ids, badseg)
     e.forward(ids, seg)                   # still usable afterwards
     e.close()
+
+
+@pytest.mark.parametrize("precision", [0, 1])
+def test_scores_only_fast_path_equals_full(precision):
+    """forward without logits materialises only column classId (nn.Select(2,classId)); scores must be identical."""
+    from kprn_b200.engine import KprnError
+    o, params, ids, seg, labels = make_case(N=700, seed=21, d_t=8, d_e=64, d_r=8, H=64, V_e=500)
+    ref = o.forward(params, ids, seg)
+    e = engine_for(o, precision=precision)
+    e.set_params(params)
+    s_fast = e.forward(ids, seg)
+    with pytest.raises(KprnError):
+        e.path_logits(ids.shape[0])
+    s_full, _ = e.forward(ids, seg, want_logits=True)
+    assert_rel(s_fast, ref["scores"], what="scores-only")
+    assert_rel(s_fast, s_full, rtol=1e-6, what="scores-only vs full")
+    e.close()
