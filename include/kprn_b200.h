@@ -146,10 +146,12 @@ int kprn_train_batch_bce(kprn_ctx* ctx, const int32_t* ids, const int32_t* seg_o
 
 /* counters for bench.py: kernels launched by this library since the last reset */
 int kprn_launch_count(kprn_ctx* ctx, int64_t* n, int32_t reset);
-/* device time (ms) of the dominant kernel class accumulated since reset, measured with CUDA events
- * on the ctx stream when profiling is enabled (kprn_profile(ctx,1)); 0 otherwise. */
+/* device time (ms) measured with CUDA events on the ctx stream while profiling is enabled (kprn_profile(ctx,1)),
+ * accumulated since the last reset: slot 0 = whole gate phase of a forward (gathers + LSTM + head), slot 1 = the
+ * x-projection kernel ("proj"), slot 2 = the recurrent kernel ("recur"); n3 = number of launches per slot.
+ * Slots 1-2 are zero on the fp32 CUDA-core engine. */
 int kprn_profile(kprn_ctx* ctx, int32_t enable);
-int kprn_profile_read(kprn_ctx* ctx, float* ms_gate_kernels, int64_t* n_gate_launches, int32_t reset);
+int kprn_profile_read(kprn_ctx* ctx, float* ms3, int64_t* n3, int32_t reset);
 
 #ifdef __cplusplus
 }

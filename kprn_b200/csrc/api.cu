@@ -50,6 +50,22 @@ int ensure_stage(kprn_ctx* ctx, size_t bytes) {
     return KPRN_OK;
 }
 
+int prof_begin(kprn_ctx* ctx, cudaEvent_t* e0) {
+    *e0 = nullptr;
+    if (!ctx->profiling) return KPRN_OK;
+    KPRN_CUDA(cudaEventCreate(e0));
+    KPRN_CUDA(cudaEventRecord(*e0, ctx->stream));
+    return KPRN_OK;
+}
+int prof_end(kprn_ctx* ctx, cudaEvent_t e0, int slot) {
+    if (!ctx->profiling || !e0) return KPRN_OK;
+    cudaEvent_t e1;
+    KPRN_CUDA(cudaEventCreate(&e1));
+    KPRN_CUDA(cudaEventRecord(e1, ctx->stream));
+    ctx->prof_pending.push_back({e0, e1, slot});
+    return KPRN_OK;
+}
+
 static void make_layout(const kprn_config& c, Layout& l) {
     int64_t o = 0;
     l.D = c.d_t + c.d_e + c.d_r;
@@ -220,18 +236,11 @@ static int forward_device_impl(kprn_ctx* ctx, const int32_t* d_ids, const int32_
         set_error("precision mode %d (tensor cores) does not support this configuration", c.precision);
         return KPRN_EINVAL;
     }
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
-    if (ctx->profiling) {
-        KPRN_CUDA(cudaEventCreate(&e0));
-        KPRN_CUDA(cudaEventCreate(&e1));
-        KPRN_CUDA(cudaEventRecord(e0, ctx->stream));
-    }
+    cudaEvent_t e0;
+    KPRN_TRY(prof_begin(ctx, &e0));
     if (use_tc) KPRN_TRY(tc_forward(ctx, d_ids, d_seg, N, S, train));
     else KPRN_TRY(simple_forward(ctx, d_ids, d_seg, N, S, train));
-    if (ctx->profiling) {
-        KPRN_CUDA(cudaEventRecord(e1, ctx->stream));
-        ctx->prof_pending.emplace_back(e0, e1);
-    }
+    KPRN_TRY(prof_end(ctx, e0, 0));
     KPRN_TRY(pool_forward(ctx, d_seg, S, d_out_scores, d_out_logits));
     ctx->have_fwd = true;
     ctx->have_train_cache = train;
@@ -301,7 +310,7 @@ int kprn_destroy(kprn_ctx* ctx) {
                     &ctx->ws_x, &ctx->ws_xw, &ctx->ws_h0, &ctx->ws_h1, &ctx->ws_c, &ctx->ws_dg, &ctx->ws_dx,
                     &ctx->ws_dh, &ctx->ws_dc, &ctx->ws_ds, &ctx->ws_dz, &ctx->pair_buf};
     for (DBuf* b : bufs) if (b->p) cudaFree(b->p);
-    for (auto& pr : ctx->prof_pending) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+    for (auto& pr : ctx->prof_pending) { cudaEventDestroy(pr.e0); cudaEventDestroy(pr.e1); }
     if (ctx->d_params) cudaFree(ctx->d_params);
     if (ctx->d_grads) cudaFree(ctx->d_grads);
     if (ctx->d_m) cudaFree(ctx->d_m);
@@ -666,18 +675,20 @@ int kprn_profile(kprn_ctx* ctx, int32_t enable) {
     return KPRN_OK;
 }
 
-int kprn_profile_read(kprn_ctx* ctx, float* ms, int64_t* n, int32_t reset) {
+int kprn_profile_read(kprn_ctx* ctx, float* ms3, int64_t* n3, int32_t reset) {
     KPRN_TRY(check_ctx(ctx));
     KPRN_CUDA(cudaStreamSynchronize(ctx->stream));
     for (auto& pr : ctx->prof_pending) {
         float t = 0.f;
-        if (cudaEventElapsedTime(&t, pr.first, pr.second) == cudaSuccess) { ctx->prof_ms += t; ctx->prof_launches++; }
-        cudaEventDestroy(pr.first); cudaEventDestroy(pr.second);
+        if (cudaEventElapsedTime(&t, pr.e0, pr.e1) == cudaSuccess) { ctx->prof_ms[pr.slot] += t; ctx->prof_launches[pr.slot]++; }
+        cudaEventDestroy(pr.e0); cudaEventDestroy(pr.e1);
     }
     ctx->prof_pending.clear();
-    if (ms) *ms = ctx->prof_ms;
-    if (n) *n = ctx->prof_launches;
-    if (reset) { ctx->prof_ms = 0.f; ctx->prof_launches = 0; }
+    for (int i = 0; i < 3; ++i) {
+        if (ms3) ms3[i] = ctx->prof_ms[i];
+        if (n3) n3[i] = ctx->prof_launches[i];
+        if (reset) { ctx->prof_ms[i] = 0.f; ctx->prof_launches[i] = 0; }
+    }
     return KPRN_OK;
 }
 

@@ -54,9 +54,10 @@ struct kprn_ctx {
     size_t h_stage_cap = 0;
     int64_t launches = 0;
     bool profiling = false;
-    float prof_ms = 0.f;
-    int64_t prof_launches = 0;
-    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_pending;
+    float prof_ms[3] = {0.f, 0.f, 0.f};
+    int64_t prof_launches[3] = {0, 0, 0};
+    struct ProfSpan { cudaEvent_t e0, e1; int slot; };
+    std::vector<ProfSpan> prof_pending;
     kprn::TcState* tc = nullptr;
 };
 
@@ -86,6 +87,9 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 
 int ensure(DBuf& b, size_t bytes);
 int ensure_stage(kprn_ctx* ctx, size_t bytes);
+// profiling spans (no-ops unless ctx->profiling)
+int prof_begin(kprn_ctx* ctx, cudaEvent_t* e0);
+int prof_end(kprn_ctx* ctx, cudaEvent_t e0, int slot);
 
 static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

@@ -699,8 +699,11 @@ int tc_forward(kprn_ctx* ctx, const int32_t* d_ids, const int32_t* d_seg, int64_
         a.E_hi = s->E_hi; a.E_lo = s->E_lo; a.W = s->WxE; a.XW = s->xw.as<float>();
         a.KE = s->KE; a.KSe = s->KSe; a.NOH = s->NOH; a.NS = s->NS; a.NCH = s->NCH; a.G4 = s->G4; a.num_tiles = ptiles * c.T; a.passes = passes;
         int64_t grid = a.num_tiles < s->num_sms ? a.num_tiles : s->num_sms;
+        cudaEvent_t e0;
+        KPRN_TRY(prof_begin(ctx, &e0));
         proj_kernel<<<(unsigned)grid, NUM_THREADS, proj_smem(s->KE, s->NOH), ctx->stream>>>(a);
         KPRN_LAUNCH_CHECK(ctx);
+        KPRN_TRY(prof_end(ctx, e0, 1));
     }
     {
         RecurArgs a;
@@ -710,10 +713,13 @@ int tc_forward(kprn_ctx* ctx, const int32_t* d_ids, const int32_t* d_seg, int64_
         a.num_tiles = ptiles; a.passes = passes;
 
         int64_t grid = ptiles < s->num_sms ? ptiles : s->num_sms;
+        cudaEvent_t e0;
+        KPRN_TRY(prof_begin(ctx, &e0));
         if (s->Hp == 64) recur_kernel<64><<<(unsigned)grid, NUM_THREADS, recur_smem(64), ctx->stream>>>(a);
         else if (s->Hp == 128) recur_kernel<128><<<(unsigned)grid, NUM_THREADS, recur_smem(128), ctx->stream>>>(a);
         else recur_kernel<256><<<(unsigned)grid, NUM_THREADS, recur_smem(256), ctx->stream>>>(a);
         KPRN_LAUNCH_CHECK(ctx);
+        KPRN_TRY(prof_end(ctx, e0, 2));
     }
     // A5: head on the last hidden state (fp32 CUDA cores; 0.2 % of the flops)
     if (ctx->cls_only) {

@@ -282,6 +282,7 @@ class Engine:
         _chk(self.lib.kprn_profile(self.h, int(enable)))
 
     def profile_read(self, reset=True):
-        ms, n = C.c_float(), C.c_int64()
-        _chk(self.lib.kprn_profile_read(self.h, C.byref(ms), C.byref(n), int(reset)))
-        return float(ms.value), int(n.value)
+        """Returns ([ms_gate_phase, ms_proj, ms_recur], [n, n, n]) accumulated while profiling was enabled."""
+        ms, n = (C.c_float * 3)(), (C.c_int64 * 3)()
+        _chk(self.lib.kprn_profile_read(self.h, ms, n, int(reset)))
+        return [float(x) for x in ms], [int(x) for x in n]

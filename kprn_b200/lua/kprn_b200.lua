@@ -61,7 +61,7 @@ int kprn_train_batch_bce(kprn_ctx* ctx, const int32_t* ids, const int32_t* seg_o
                          float clip_norm, float l2, float lr, float beta1, float beta2, float eps, float* loss);
 int kprn_launch_count(kprn_ctx* ctx, int64_t* n, int32_t reset);
 int kprn_profile(kprn_ctx* ctx, int32_t enable);
-int kprn_profile_read(kprn_ctx* ctx, float* ms_gate_kernels, int64_t* n_gate_launches, int32_t reset);
+int kprn_profile_read(kprn_ctx* ctx, float* ms3, int64_t* n3, int32_t reset);
 ]]
 
 local C = ffi.load(os.getenv('KPRN_B200_LIB') or 'kprn_b200')

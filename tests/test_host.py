@@ -1,0 +1,79 @@
+"""CPU tests of the host-side logic around the path: .int reader, Batcher mirrors, CSR conversion, partitioning."""
+import numpy as np
+
+from kprn_b200 import dist, io, synth
+
+
+def _bucket(B, P, T=6, seed=0):
+    ids = synth.make_paths(B * P, T=T, V_e=100, seed=seed, length_mode="stress").reshape(B, P, T, 3)
+    labels = synth.make_labels(B, seed)
+    return labels, ids
+
+
+def test_int_file_round_trip_and_add_one(tmp_path):
+    labels, data = _bucket(7, 3)
+    p = tmp_path / "train.txt.3.int"
+    io.write_int_file(str(p), labels, data)
+    first = p.read_text().splitlines()[0]
+    lab, paths = first.split("\t")
+    assert len(paths.split(";")) == 3 and len(paths.split(";")[0].split(" ")) == 6      # P paths, T steps
+    assert [int(v) + 1 for v in paths.split(";")[0].split(" ")[0].split(",")] == data[0, 0, 0].tolist()   # file is 0-based
+    l2, d2 = io.read_int_file(str(p))
+    np.testing.assert_array_equal(d2, data)
+    np.testing.assert_array_equal(l2, labels)
+    assert d2.min() >= 1                                      # int2torch.lua -addOne 1
+
+
+def test_batcher_matches_reference_semantics(tmp_path):
+    """model/batcher/test/testBatcher.lua: getBatch non-nil, classId, same number of batches before/after reset."""
+    labels, data = _bucket(22, 2)
+    b = io.Batcher(labels, data, batch_size=4, shuffle=False, class_id=1)
+    n = 0
+    while True:
+        got = b.getBatch()
+        if got is None:
+            break
+        lab, dat, count, cls = got
+        assert cls == 1 and dat.shape[0] == count == len(lab)
+        n += 1
+    assert n == 6
+    b.reset()
+    n2 = sum(1 for _ in iter(b.getBatch, None))
+    assert n2 == 6
+    # shuffle keeps (label, data) rows together
+    bs = io.Batcher(labels, data, batch_size=22, shuffle=True)
+    lab, dat, _, _ = bs.getBatch()
+    key = {tuple(d.reshape(-1)): l for l, d in zip(labels, data)}
+    assert all(key[tuple(d.reshape(-1))] == l for l, d in zip(lab, dat))
+
+
+def test_batcher_file_list_and_csr(tmp_path):
+    names = []
+    for P in (1, 2, 5):
+        labels, data = _bucket(9, P, seed=P)
+        name = "train.txt.%d.int" % P
+        io.write_int_file(str(tmp_path / name), labels, data)
+        names.append(name)
+    (tmp_path / "train.list").write_text("\n".join(names) + "\n")
+    fl = io.BatcherFileList(str(tmp_path), batch_size=4, shuffle=False, list_file="train.list")
+    batches = list(iter(fl.getBatch, None))
+    assert len(batches) == 9                                  # 3 files x ceil(9/4)
+    fl.reset()
+    assert len(list(iter(fl.getBatch, None))) == 9            # testBatcherFilelist.lua: stable across reset
+    ids, seg, labels = io.to_csr([(b[0], b[1]) for b in batches])
+    assert ids.shape[0] == seg[-1] == 9 * (1 + 2 + 5) and len(labels) == len(seg) - 1 == 27
+    assert (np.diff(seg) > 0).all()
+
+
+def test_partition_never_splits_a_segment_and_balances_paths():
+    seg = synth.make_segments(10000, seed=4)
+    for world in (1, 2, 3, 8):
+        parts = dist.partition_segments(seg, world)
+        assert parts[0][0] == 0 and parts[-1][1] == len(seg) - 1
+        assert all(parts[i][1] == parts[i + 1][0] for i in range(world - 1))
+        counts = [int(seg[b] - seg[a]) for a, b in parts]
+        assert sum(counts) == 10000 and max(counts) - min(counts) <= 28 * 2
+    ids = synth.make_paths(10000, V_e=50, seed=4)
+    l_ids, l_seg, _, (a, b) = dist.shard(ids, seg, None, 1, 4)
+    assert l_seg[0] == 0 and l_seg[-1] == len(l_ids) and len(l_seg) == b - a + 1
+    np.testing.assert_array_equal(l_ids, ids[seg[a]:seg[b]])
