@@ -1,0 +1,41 @@
+"""Turns ncu outputs in gpurun_out/ into the committed summaries under profiles/.
+usage: python tools/profile_summary.py <tag> <launches.csv> [<full.ncu-rep>]"""
+import csv
+import os
+import subprocess
+import sys
+from collections import defaultdict
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+tag, launches = sys.argv[1], sys.argv[2]
+rep = sys.argv[3] if len(sys.argv) > 3 else None
+out = open(os.path.join(ROOT, "profiles", "%s_summary.md" % tag), "w")
+rows = [r for r in csv.reader(open(launches)) if len(r) > 5]
+hdr = rows[0]
+ki, mi, vi = hdr.index("Kernel Name"), hdr.index("Metric Name"), hdr.index("Metric Value")
+agg = defaultdict(list)
+for r in rows[1:]:
+    if r[mi] == "gpu__time_duration.sum":
+        agg[r[ki].split("(")[0][:48]].append(float(r[vi].replace(",", "")))
+tot = sum(sum(v) for v in agg.values())
+out.write("# %s -- ncu launch list (`--metrics gpu__time_duration.sum --clock-control none`), python bench.py\n\n" % tag)
+out.write("Per-launch times under ncu are cold-cache and serialised: compare SHARES, not absolutes.\n\n")
+out.write("| kernel | launches | avg us | share |\n|---|---|---|---|\n")
+for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
+    out.write("| %s | %d | %.1f | %.1f %% |\n" % (k, len(v), sum(v) / len(v) / 1e3, 100 * sum(v) / tot))
+if rep:
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rr = list(csv.reader(raw.splitlines()))
+    h = rr[0]
+    want = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+            "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+            "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "launch__registers_per_thread", "sm__warps_active.avg.pct_of_peak_sustained_active",
+            "launch__grid_size", "launch__block_size", "smsp__cycles_active.avg", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+            "lts__t_bytes.sum", "l1tex__t_bytes.sum", "smsp__inst_executed.sum", "sm__cycles_elapsed.max"]
+    out.write("\n## `ncu --set full` capture (one launch per kernel)\n\n| metric | unit | " + " | ".join(r[h.index("Kernel Name")].split("(")[0][:24] for r in rr[2:]) + " |\n")
+    out.write("|---|---|" + "---|" * len(rr[2:]) + "\n")
+    for i, name in enumerate(h):
+        if name in want and name != "Kernel Name":
+            out.write("| %s | %s | %s |\n" % (name, rr[1][i], " | ".join(r[i] for r in rr[2:])))
+out.close()
+print(open(os.path.join(ROOT, "profiles", "%s_summary.md" % tag)).read())
