@@ -16,6 +16,7 @@
 // Operand layouts are the canonical K-major no-swizzle UMMA layout [k/8][row][8 elements] (ptx.cuh), which the
 // packing kernels below produce in global memory so that a slab is one contiguous TMA bulk copy.
 #include <cuda_bf16.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -25,12 +26,20 @@ namespace kprn {
 
 using bf16 = __nv_bfloat16;
 
+// wait on an mbarrier and, when debugging, charge the waited cycles to counter `slot`
+#define TWAIT(slot, bar, par)                                              \
+    do {                                                                  \
+        if (a.dbg) { long long _t0 = clock64(); ptx::mbar_wait((bar), (par)); dbg_acc[slot] += clock64() - _t0; } \
+        else ptx::mbar_wait((bar), (par));                                \
+    } while (0)
+
 constexpr int TILE_M = 128;           // paths per CTA tile (UMMA M)
 constexpr int B_SLAB_ELEMS = 8 * 128 * 8;   // weight slab: 64 k x 128 gate columns (16 KB), both kernels
 constexpr int PROJ_RING = 5;
 constexpr int RECUR_RING = 6;
 constexpr int MAX_NS = 6;             // k-slices of the proj A tile: KE/64 entity slices + NOH one-hot slices
-constexpr int NUM_THREADS = 384;      // warps: 0 TMA producer, 1 MMA issuer, 2-3 gather/alloc, 4-11 epilogue
+constexpr int NUM_THREADS = 384;      // proj: warps 0 TMA producer, 1 MMA issuer, 2-3 gather/alloc, 4-11 epilogue
+constexpr int RECUR_THREADS = 640;    // recur: warps 0 TMA producer, 1 MMA issuer, 2 alloc, 3 h loader, 4-19 epilogue (4 groups)
 
 struct TcState {
     uint64_t packed_version = 0;
@@ -38,7 +47,8 @@ struct TcState {
     bf16* E_hi = nullptr; bf16* E_lo = nullptr;
     bf16* WxE = nullptr; bf16* Wh = nullptr;
     float* Ptr = nullptr;
-    DBuf xw, hT, hscratch;
+    DBuf xw, hT, hscratch, dbg;
+    bool debug = false;
     int num_sms = 148;
     bool attrs_set = false;
 };
@@ -165,6 +175,7 @@ struct ProjArgs {
     const int32_t* ids; int64_t N; int T; int64_t V_e; int V_t; int V_r;
     const bf16* E_hi; const bf16* E_lo; const bf16* W; float* XW;
     int KE, KSe, NOH, NS, NCH, G4; int64_t num_tiles; int passes;   // passes: 3 = bf16x3, 1 = hi*hi only
+    unsigned long long* dbg;   // optional wait-cycle counters (KPRN_TC_DEBUG=1): see tc_debug_dump
 };
 
 __global__ void __launch_bounds__(NUM_THREADS, 1) proj_kernel(ProjArgs a) {
@@ -194,6 +205,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) proj_kernel(ProjArgs a) {
     ptx::tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
+    long long dbg_acc[16] = {0};
+    const long long dbg_t0 = clock64();
     const int64_t my_tiles = (a.num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;   // tiles blockIdx.x + i*gridDim.x
     const uint32_t idesc = ptx::make_idesc_f16(1, TILE_M, 128);
     const int parts = a.passes == 3 ? 2 : 1;
@@ -206,7 +219,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) proj_kernel(ProjArgs a) {
                 for (int nt = 0; nt < a.NCH; ++nt)
                     for (int s = 0; s < a.NS; ++s)
                         for (int part = 0; part < parts; ++part) {
-                            ptx::mbar_wait(BAR(R + stage), phase ^ 1);
+                            TWAIT(0, BAR(R + stage), phase ^ 1);
                             ptx::mbar_arrive_expect_tx(BAR(stage), B_SLAB_ELEMS * 2);
                             const bf16* src = a.W + ((int64_t)(nt * a.NS + s) * 2 + part) * B_SLAB_ELEMS;
                             ptx::tma_bulk_g2s(ptx::smem_u32(sRing + stage * B_SLAB_ELEMS * 2), src, B_SLAB_ELEMS * 2, BAR(stage));
@@ -226,14 +239,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) proj_kernel(ProjArgs a) {
             for (int64_t it = 0; it < my_tiles; ++it) {
                 for (int nt = 0; nt < a.NCH; ++nt, ++au) {
                     const int buf = au & 3;
-                    ptx::mbar_wait(BAR(B_ACCE + buf), ((au >> 2) & 1) ^ 1);
+                    TWAIT(1, BAR(B_ACCE + buf), ((au >> 2) & 1) ^ 1);
                     ptx::tc_fence_after();
                     const uint32_t d = tmem + buf * 128;
                     for (int s = 0; s < a.NS; ++s) {
-                        if (nt == 0) { ptx::mbar_wait(BAR(B_AFULL + s), it & 1); ptx::tc_fence_after(); }
+                        if (nt == 0) { TWAIT(2, BAR(B_AFULL + s), it & 1); ptx::tc_fence_after(); }
                         const bool onehot = s >= a.KSe;
                         const uint32_t ah = aHi0 + s * SLICE_STEP, al = aLo0 + s * SLICE_STEP;
-                        ptx::mbar_wait(BAR(stage), phase);
+                        TWAIT(3, BAR(stage), phase);
                         ptx::tc_fence_after();
                         uint32_t bl = ring0 + stage * SLAB_STEP;
                         if (issue) {
@@ -249,7 +262,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) proj_kernel(ProjArgs a) {
                         }
                         if (++stage == R) { stage = 0; phase ^= 1; }
                         if (a.passes == 3) {
-                            ptx::mbar_wait(BAR(stage), phase);
+                            TWAIT(3, BAR(stage), phase);
                             ptx::tc_fence_after();
                             bl = ring0 + stage * SLAB_STEP;
                             if (issue) {
@@ -268,18 +281,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) proj_kernel(ProjArgs a) {
         }
     } else if (warp < 4) {
         // ===== gather warps: pre-split entity rows -> canonical A layout via 16-byte LDGSTS; one-hot (type,rel) slice =====
+        // Lane mapping: 8 lanes cover one 128-byte line of one row (k-chunks 0..7 of the slice), 4 rows per instruction,
+        // so an instruction touches 4 lines instead of 16 (LDGSTS cost scales with the lines touched).  All k-slices of
+        // a tile are issued back to back (one commit group each) as their buffers are released and completed in order
+        // with wait_group<n>; the ids of the next tile are loaded while the copies are in flight.
         const int gw = warp - 2;
-        const int rsub = lane >> 1, cpar = lane & 1;
+        const int rsub = lane >> 3, kc = lane & 7;
         const uint32_t dHi = ptx::smem_u32(sA_hi), dLo = ptx::smem_u32(sA_lo);
-        for (int64_t it = 0; it < my_tiles; ++it) {
+        int64_t eid[16];
+        int combo[16];
+        auto load_ids = [&](int64_t it) {
             const int64_t m = blockIdx.x + it * gridDim.x;
             const int64_t pt = m / a.T;
             const int t = (int)(m % a.T);
-            int64_t eid[4];
-            int combo[4];
 #pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                const int r = (gw + 2 * b) * 16 + rsub;
+            for (int b = 0; b < 16; ++b) {
+                const int r = (2 * b + gw) * 4 + rsub;
                 int64_t n = pt * TILE_M + r;
                 if (n >= a.N) n = a.N - 1;
                 const int32_t* idp = a.ids + (n * a.T + t) * 3;
@@ -290,46 +307,46 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) proj_kernel(ProjArgs a) {
                 rb = rb < 0 ? 0 : (rb >= a.V_r ? a.V_r - 1 : rb);
                 combo[b] = ta * a.V_r + rb;
             }
+        };
+        if (my_tiles > 0) load_ids(0);
+        for (int64_t it = 0; it < my_tiles; ++it) {
             for (int s = 0; s < a.NS; ++s) {
-                ptx::mbar_wait(BAR(B_AFREE + s), (it & 1) ^ 1);
+                TWAIT(4, BAR(B_AFREE + s), (it & 1) ^ 1);
+                const uint32_t off = (s * 8 + kc) * 2048;
                 if (s < a.KSe) {
 #pragma unroll
-                    for (int b = 0; b < 4; ++b) {
-                        const int r = (gw + 2 * b) * 16 + rsub;
-                        const bf16* sh = a.E_hi + eid[b] * a.KE + s * 64;
-                        const bf16* sl = a.E_lo + eid[b] * a.KE + s * 64;
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const int kc = cpar + 2 * i;
-                            ptx::cp_async16(dHi + (s * 8 + kc) * 2048 + r * 16, sh + kc * 8);
-                            ptx::cp_async16(dLo + (s * 8 + kc) * 2048 + r * 16, sl + kc * 8);
-                        }
+                    for (int b = 0; b < 16; ++b) {
+                        const int r = (2 * b + gw) * 4 + rsub;
+                        ptx::cp_async16(dHi + off + r * 16, a.E_hi + eid[b] * a.KE + s * 64 + kc * 8);
+                        ptx::cp_async16(dLo + off + r * 16, a.E_lo + eid[b] * a.KE + s * 64 + kc * 8);
                     }
                 } else {
                     const int o = s - a.KSe;
 #pragma unroll
-                    for (int b = 0; b < 4; ++b) {
-                        const int r = (gw + 2 * b) * 16 + rsub;
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const int kc = cpar + 2 * i;
-                            uint32_t w[4] = {0u, 0u, 0u, 0u};
-                            if ((combo[b] >> 3) == o * 8 + kc) w[(combo[b] & 7) >> 1] = 0x3F80u << (16 * (combo[b] & 1));   // bf16 1.0
-                            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dHi + (s * 8 + kc) * 2048 + r * 16),
-                                         "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
-                        }
+                    for (int b = 0; b < 16; ++b) {
+                        const int r = (2 * b + gw) * 4 + rsub;
+                        uint32_t w[4] = {0u, 0u, 0u, 0u};
+                        if ((combo[b] >> 3) == o * 8 + kc) w[(combo[b] & 7) >> 1] = 0x3F80u << (16 * (combo[b] & 1));   // bf16 1.0
+                        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dHi + off + r * 16),
+                                     "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
                     }
                 }
                 ptx::cp_async_commit();
-                if (s > 0) {
-                    ptx::cp_async_wait_group<1>();
-                    ptx::fence_proxy_async_smem();
-                    ptx::mbar_arrive(BAR(B_AFULL + s - 1));
-                }
             }
-            ptx::cp_async_wait_group<0>();
-            ptx::fence_proxy_async_smem();
-            ptx::mbar_arrive(BAR(B_AFULL + a.NS - 1));
+            if (it + 1 < my_tiles) load_ids(it + 1);      // overlaps the copies in flight
+            // complete the slices in order: group s is done when at most NS-1-s younger groups are pending
+            for (int s = 0; s < a.NS; ++s) {
+                switch (a.NS - 1 - s) {
+                    case 5: ptx::cp_async_wait_group<5>(); break;
+                    case 4: ptx::cp_async_wait_group<4>(); break;
+                    case 3: ptx::cp_async_wait_group<3>(); break;
+                    case 2: ptx::cp_async_wait_group<2>(); break;
+                    case 1: ptx::cp_async_wait_group<1>(); break;
+                    default: ptx::cp_async_wait_group<0>(); break;
+                }
+                ptx::fence_proxy_async_smem();
+                ptx::mbar_arrive(BAR(B_AFULL + s));
+            }
         }
     } else {
         // ===== epilogue: TMEM -> registers -> XW (pure copy; bias and (type,rel) terms came through the MMA) =====
@@ -343,7 +360,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) proj_kernel(ProjArgs a) {
             const int buf = au & 3;
             const int64_t m = blockIdx.x + it * gridDim.x;
             float* xw = a.XW + ((m * (a.G4 / 4) + nt * 32) * TILE_M + r) * 4;
-            ptx::mbar_wait(BAR(B_ACCF + buf), (au >> 2) & 1);
+            if (nt == 0 && it + 1 < my_tiles) {
+                // pull the entity rows of the NEXT tile into L2 (one row per thread) so that the gather warps' LDGSTS
+                // see L2 latency instead of HBM latency: the A tile is single-buffered, its refill is on the critical path
+                const int64_t m2 = m + gridDim.x;
+                int64_t n2 = (m2 / a.T) * TILE_M + r;
+                if (n2 >= a.N) n2 = a.N - 1;
+                int64_t id2 = (int64_t)a.ids[(n2 * a.T + (int)(m2 % a.T)) * 3 + 1] - 1;
+                id2 = id2 < 0 ? 0 : (id2 >= a.V_e ? a.V_e - 1 : id2);
+                const char* ph = reinterpret_cast<const char*>(a.E_hi + id2 * a.KE);
+                const char* pl = reinterpret_cast<const char*>(a.E_lo + id2 * a.KE);
+                for (int b = 0; b < a.KE * 2; b += 128) {
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(ph + b));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(pl + b));
+                }
+            }
+            TWAIT(5, BAR(B_ACCF + buf), (au >> 2) & 1);
             ptx::tc_fence_after();
             const uint32_t tbase = tmem + ((uint32_t)(q4 * 32) << 16) + buf * 128;
 #pragma unroll
@@ -357,6 +389,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) proj_kernel(ProjArgs a) {
             }
             ptx::tc_fence_before();
             ptx::mbar_arrive(BAR(B_ACCE + buf));
+        }
+    }
+    if (a.dbg && lane == 0) {
+        // one representative lane per role: warps 0..3 and the first warp of each epilogue warpgroup
+        if (warp < 4 || warp == 4 || warp == 8) {
+            for (int i = 0; i < 15; ++i) if (dbg_acc[i]) atomicAdd(a.dbg + i, (unsigned long long)dbg_acc[i]);
+            if (warp == 1) atomicAdd(a.dbg + 15, (unsigned long long)(clock64() - dbg_t0));
         }
     }
     ptx::tc_fence_before();
@@ -376,6 +415,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) proj_kernel(ProjArgs a) {
 
 struct RecurArgs {
     const float* XW; const bf16* W; float* hT; bf16* hscratch; int64_t N; int T; int H; int G4; int64_t num_tiles; int passes;
+    unsigned long long* dbg;
 };
 
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
@@ -395,7 +435,7 @@ __device__ __forceinline__ void pack_split8(const float* v, uint4& hi, uint4& lo
 }
 
 template <int HP>
-__global__ void __launch_bounds__(NUM_THREADS, 1) recur_kernel(RecurArgs a) {
+__global__ void __launch_bounds__(RECUR_THREADS, 1) recur_kernel(RecurArgs a) {
     constexpr int NCH = HP / 32;        // 128-column chunks per step
     constexpr int KS = HP / 64;         // 64-wide k slices of h
     constexpr int R = RECUR_RING;
@@ -417,9 +457,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) recur_kernel(RecurArgs a) {
     if (threadIdx.x == 0) {
         for (int i = 0; i < R; ++i) { ptx::mbar_init(BAR(i), 1); ptx::mbar_init(BAR(R + i), 1); }
         ptx::mbar_init(BAR(2 * R), 1); ptx::mbar_init(BAR(2 * R + 1), 1);
-        ptx::mbar_init(BAR(2 * R + 2), 128); ptx::mbar_init(BAR(2 * R + 3), 128);
+        ptx::mbar_init(BAR(2 * R + 2), 256); ptx::mbar_init(BAR(2 * R + 3), 256);     // two epilogue groups share an accumulator
         ptx::mbar_init(BAR(2 * R + 4), 1);
-        for (int s = 0; s < KS; ++s) { ptx::mbar_init(BAR(B_HREADY + s), 1); ptx::mbar_init(BAR(B_HWRIT + s), 256); }
+        for (int s = 0; s < KS; ++s) { ptx::mbar_init(BAR(B_HREADY + s), 1); ptx::mbar_init(BAR(B_HWRIT + s), 512); }
         ptx::fence_mbar_init();
     }
     if (warp == 2) { ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 512); ptx::tmem_relinquish(); }
@@ -428,6 +468,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) recur_kernel(RecurArgs a) {
     ptx::tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
+    long long dbg_acc[16] = {0};
+    const long long dbg_t0 = clock64();
     const int64_t my_tiles = (a.num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
     const int T = a.T;
     const uint32_t idesc = ptx::make_idesc_f16(1, TILE_M, 128);
@@ -443,7 +485,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) recur_kernel(RecurArgs a) {
                 for (int j = 0; j < NCH; ++j)
                     for (int s = 0; s < KS; ++s)
                         for (int part = 0; part < slabs_per_k; ++part) {
-                            ptx::mbar_wait(BAR(R + stage), phase ^ 1);
+                            TWAIT(8, BAR(R + stage), phase ^ 1);
                             ptx::mbar_arrive_expect_tx(BAR(stage), B_SLAB_ELEMS * 2);
                             const bf16* src = a.W + ((int64_t)(j * KS + s) * 2 + part) * B_SLAB_ELEMS;
                             ptx::tma_bulk_g2s(ptx::smem_u32(sRing + stage * B_SLAB_ELEMS * 2), src, B_SLAB_ELEMS * 2, BAR(stage));
@@ -467,17 +509,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) recur_kernel(RecurArgs a) {
                 for (int j = 0; j < NCH; ++j) {
                     const int g = j & 1;
                     uint32_t& ug = g ? ug1 : ug0;
-                    ptx::mbar_wait(BAR(2 * R + 2 + g), (ug & 1) ^ 1);
+                    TWAIT(9, BAR(2 * R + 2 + g), (ug & 1) ^ 1);
                     ptx::tc_fence_after();
                     const uint32_t d = tmem + g * 128;
 #pragma unroll 1
                     for (int s = 0; s < KS; ++s) {
                         if (j == 0) {          // h_{t-1} slice s has landed in shared memory
-                            ptx::mbar_wait(BAR(B_HREADY + s), (cnt - 1) & 1);
+                            TWAIT(10, BAR(B_HREADY + s), (cnt - 1) & 1);
                             ptx::tc_fence_after();
                         }
                         const uint32_t ah = hHi0 + s * SLICE_STEP, al = hLo0 + s * SLICE_STEP;
-                        ptx::mbar_wait(BAR(stage), phase);
+                        TWAIT(11, BAR(stage), phase);
                         ptx::tc_fence_after();
                         uint32_t bl = ring0 + stage * SLAB_STEP;
                         if (issue) {
@@ -493,7 +535,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) recur_kernel(RecurArgs a) {
                         }
                         if (++stage == R) { stage = 0; phase ^= 1; }
                         if (a.passes == 3) {
-                            ptx::mbar_wait(BAR(stage), phase);
+                            TWAIT(11, BAR(stage), phase);
                             ptx::tc_fence_after();
                             bl = ring0 + stage * SLAB_STEP;
                             if (issue) {
@@ -519,9 +561,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) recur_kernel(RecurArgs a) {
                 for (int t = 0; t < T - 1; ++t) {
                     ++idx;
                     // all MMAs that read the previous contents of sH must have retired: that is MMA step idx-1
-                    if (idx >= 2) ptx::mbar_wait(BAR(2 * R + 4), (idx - 2) & 1);
+                    if (idx >= 2) TWAIT(12, BAR(2 * R + 4), (idx - 2) & 1);
                     for (int s = 0; s < KS; ++s) {
-                        ptx::mbar_wait(BAR(B_HWRIT + s), (idx - 1) & 1);
+                        TWAIT(13, BAR(B_HWRIT + s), (idx - 1) & 1);
                         ptx::mbar_arrive_expect_tx(BAR(B_HREADY + s), 2 * SLICE_BYTES);
                         ptx::tma_bulk_g2s(ptx::smem_u32(sH_hi) + s * SLICE_BYTES, scratch + s * SLICE_BYTES, SLICE_BYTES, BAR(B_HREADY + s));
                         ptx::tma_bulk_g2s(ptx::smem_u32(sH_lo) + s * SLICE_BYTES, scratch + H_BYTES + s * SLICE_BYTES, SLICE_BYTES, BAR(B_HREADY + s));
@@ -530,8 +572,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) recur_kernel(RecurArgs a) {
             }
         }
     } else if (warp >= 4) {
-        // ===== epilogue warpgroups =====
-        const int wg = (warp - 4) >> 2;
+        // ===== epilogue: 4 groups of 4 warps.  group = (half << 1) | wg : wg = chunk parity / accumulator,
+        // half = which two of the chunk's four 8-unit sub-blocks this group owns =====
+        const int group = (warp - 4) >> 2;
+        const int wg = group & 1, half = group >> 1;
         const int q4 = warp & 3;
         const int r = q4 * 32 + lane;
         const uint32_t lane_base = (uint32_t)(q4 * 32) << 16;
@@ -548,7 +592,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) recur_kernel(RecurArgs a) {
                     const int j = 2 * lc + wg;
                     const float* xj = xw_t + (int64_t)j * 32 * TILE_M * 4;
                     // XW of sub-block sb, gate q: column blocks q*8 + 2*sb, +1   (each block = 128 rows x 4 floats)
-                    float xc[32];
+                    float xc[32], xn[32];
 #define KPRN_LOAD_XW(dst, sb)                                                                              \
     _Pragma("unroll") for (int q = 0; q < 4; ++q) {                                                       \
         const float4 x0 = *reinterpret_cast<const float4*>(xj + (int64_t)(q * 8 + 2 * (sb)) * TILE_M * 4);     \
@@ -556,17 +600,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) recur_kernel(RecurArgs a) {
         dst[q * 8 + 0] = x0.x; dst[q * 8 + 1] = x0.y; dst[q * 8 + 2] = x0.z; dst[q * 8 + 3] = x0.w;           \
         dst[q * 8 + 4] = x1.x; dst[q * 8 + 5] = x1.y; dst[q * 8 + 6] = x1.z; dst[q * 8 + 7] = x1.w;           \
     }
-                    KPRN_LOAD_XW(xc, 0)
+                    KPRN_LOAD_XW(xc, 2 * half)
                     if (t > 0) {
-                        ptx::mbar_wait(BAR(2 * R + wg), ug & 1);
+                        TWAIT(14, BAR(2 * R + wg), ug & 1);
                         ptx::tc_fence_after();
                     }
                     const uint32_t acc = tmem + lane_base + wg * 128;
                     const uint32_t cst = tmem + lane_base + 256 + j * 32;
 #pragma unroll
-                    for (int sb = 0; sb < 4; ++sb) {
-                        float xn[32];
-                        if (sb < 3) { KPRN_LOAD_XW(xn, sb + 1) }
+                    for (int sbi = 0; sbi < 2; ++sbi) {
+                        const int sb = 2 * half + sbi;
                         float cp[8];
                         if (t > 0) {
                             float ai[8], ag[8], af[8], ao[8];
@@ -582,11 +625,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) recur_kernel(RecurArgs a) {
 #pragma unroll
                             for (int e = 0; e < 8; ++e) cp[e] = 0.f;
                         }
+                        if (sbi == 0) { KPRN_LOAD_XW(xn, 2 * half + 1) }     // in flight during the cell math below
                         float cn[8], hv[8];
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) {          // FastLSTM cell
-                            const float i_ = fast_sigmoid(xc[e]), g_ = fast_tanh(xc[8 + e]);
-                            const float f_ = fast_sigmoid(xc[16 + e]), o_ = fast_sigmoid(xc[24 + e]);
+                        for (int e = 0; e < 8; ++e) {
+                            // FastLSTM cell; two activations share one reciprocal (8 MUFU per cell instead of 10)
+                            const float ei = __expf(-fmaxf(xc[e], -30.f)), ef = __expf(-fmaxf(xc[16 + e], -30.f));
+                            const float eo = __expf(-fmaxf(xc[24 + e], -30.f)), eg = __expf(2.f * fminf(xc[8 + e], 15.f));
+                            const float rif = __fdividef(1.f, (1.f + ei) * (1.f + ef));
+                            const float rog = __fdividef(1.f, (1.f + eo) * (1.f + eg));
+                            const float i_ = (1.f + ef) * rif, f_ = (1.f + ei) * rif;
+                            const float o_ = (1.f + eg) * rog, g_ = 1.f - 2.f * (1.f + eo) * rog;
                             cn[e] = fmaf(i_, g_, f_ * cp[e]);
                             hv[e] = o_ * fast_tanh(cn[e]);
                         }
@@ -604,7 +653,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) recur_kernel(RecurArgs a) {
                             for (int e = 0; e < 8; ++e)
                                 if (j * 32 + sb * 8 + e < a.H) dst[e] = hv[e];
                         }
-                        if (sb < 3) {
+                        if (sbi == 0) {
 #pragma unroll
                             for (int e = 0; e < 32; ++e) xc[e] = xn[e];
                         }
@@ -623,6 +672,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) recur_kernel(RecurArgs a) {
                     }
                 }
             }
+        }
+    }
+    if (a.dbg && lane == 0) {
+        // one representative lane per role: warps 0..3 and the first warp of each epilogue warpgroup
+        if (warp < 4 || warp == 4 || warp == 8) {
+            for (int i = 0; i < 15; ++i) if (dbg_acc[i]) atomicAdd(a.dbg + i, (unsigned long long)dbg_acc[i]);
+            if (warp == 1) atomicAdd(a.dbg + 15, (unsigned long long)(clock64() - dbg_t0));
         }
     }
     ptx::tc_fence_before();
@@ -677,6 +733,7 @@ int tc_forward(kprn_ctx* ctx, const int32_t* d_ids, const int32_t* d_seg, int64_
         cudaDeviceProp prop;
         KPRN_CUDA(cudaGetDeviceProperties(&prop, ctx->device));
         s->num_sms = prop.multiProcessorCount;
+        { const char* d = getenv("KPRN_TC_DEBUG"); s->debug = d && d[0] == '1'; }
         if (prop.major != 10) { set_error("tensor-core path needs sm_100 (found sm_%d%d)", prop.major, prop.minor); return KPRN_ECUDA; }
     }
     TcState* s = ctx->tc;
@@ -693,11 +750,17 @@ int tc_forward(kprn_ctx* ctx, const int32_t* d_ids, const int32_t* d_seg, int64_
     KPRN_TRY(ensure(s->hT, sizeof(float) * (size_t)N * c.H));
     KPRN_TRY(ensure(ctx->path_logits, sizeof(float) * N * c.L));
     const int passes = c.precision == KPRN_PREC_TC_FAST ? 1 : 3;
+    unsigned long long* dbg = nullptr;
+    if (s->debug) {
+        KPRN_TRY(ensure(s->dbg, 2 * 16 * sizeof(unsigned long long)));
+        dbg = s->dbg.as<unsigned long long>();
+        KPRN_CUDA(cudaMemsetAsync(dbg, 0, 2 * 16 * sizeof(unsigned long long), ctx->stream));
+    }
     {
         ProjArgs a;
         a.ids = d_ids; a.N = N; a.T = c.T; a.V_e = c.V_e; a.V_t = (int)c.V_t; a.V_r = (int)c.V_r;
         a.E_hi = s->E_hi; a.E_lo = s->E_lo; a.W = s->WxE; a.XW = s->xw.as<float>();
-        a.KE = s->KE; a.KSe = s->KSe; a.NOH = s->NOH; a.NS = s->NS; a.NCH = s->NCH; a.G4 = s->G4; a.num_tiles = ptiles * c.T; a.passes = passes;
+        a.KE = s->KE; a.KSe = s->KSe; a.NOH = s->NOH; a.NS = s->NS; a.NCH = s->NCH; a.G4 = s->G4; a.num_tiles = ptiles * c.T; a.passes = passes; a.dbg = dbg;
         int64_t grid = a.num_tiles < s->num_sms ? a.num_tiles : s->num_sms;
         cudaEvent_t e0;
         KPRN_TRY(prof_begin(ctx, &e0));
@@ -710,16 +773,28 @@ int tc_forward(kprn_ctx* ctx, const int32_t* d_ids, const int32_t* d_seg, int64_
         int64_t grid_r = ptiles < s->num_sms ? ptiles : s->num_sms;
         KPRN_TRY(ensure(s->hscratch, (size_t)grid_r * 2 * TILE_M * s->Hp * 2));
         a.XW = s->xw.as<float>(); a.W = s->Wh; a.hT = s->hT.as<float>(); a.hscratch = s->hscratch.as<bf16>(); a.N = N; a.T = c.T; a.H = c.H; a.G4 = s->G4;
-        a.num_tiles = ptiles; a.passes = passes;
+        a.num_tiles = ptiles; a.passes = passes; a.dbg = dbg ? dbg + 16 : nullptr;
 
         int64_t grid = ptiles < s->num_sms ? ptiles : s->num_sms;
         cudaEvent_t e0;
         KPRN_TRY(prof_begin(ctx, &e0));
-        if (s->Hp == 64) recur_kernel<64><<<(unsigned)grid, NUM_THREADS, recur_smem(64), ctx->stream>>>(a);
-        else if (s->Hp == 128) recur_kernel<128><<<(unsigned)grid, NUM_THREADS, recur_smem(128), ctx->stream>>>(a);
-        else recur_kernel<256><<<(unsigned)grid, NUM_THREADS, recur_smem(256), ctx->stream>>>(a);
+        if (s->Hp == 64) recur_kernel<64><<<(unsigned)grid, RECUR_THREADS, recur_smem(64), ctx->stream>>>(a);
+        else if (s->Hp == 128) recur_kernel<128><<<(unsigned)grid, RECUR_THREADS, recur_smem(128), ctx->stream>>>(a);
+        else recur_kernel<256><<<(unsigned)grid, RECUR_THREADS, recur_smem(256), ctx->stream>>>(a);
         KPRN_LAUNCH_CHECK(ctx);
         KPRN_TRY(prof_end(ctx, e0, 2));
+    }
+    if (s->debug) {
+        unsigned long long h[32];
+        KPRN_CUDA(cudaMemcpyAsync(h, dbg, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+        KPRN_CUDA(cudaStreamSynchronize(ctx->stream));
+        const double np_ = (double)(ptiles * c.T < s->num_sms ? ptiles * c.T : s->num_sms), nr_ = (double)(ptiles < s->num_sms ? ptiles : s->num_sms);
+        fprintf(stderr, "[kprn tc debug] proj: kernel cycles/CTA %.0f | waits/CTA: producer.slab_empty %.0f, mma.acc_empty %.0f, mma.a_full %.0f, "
+                        "mma.slab_full %.0f, gather.a_free %.0f, epilogue(wg0+wg1).acc_full %.0f\n",
+                h[15] / np_, h[0] / np_, h[1] / np_, h[2] / np_, h[3] / np_, h[4] / np_ / 2, h[5] / np_);
+        fprintf(stderr, "[kprn tc debug] recur: kernel cycles/CTA %.0f | waits/CTA: producer.slab_empty %.0f, mma.acc_empty %.0f, mma.h_ready %.0f, "
+                        "mma.slab_full %.0f, hloader.mma_done %.0f, hloader.h_written %.0f, epilogue(wg0+wg1).acc_full %.0f\n",
+                h[31] / nr_, h[24] / nr_, h[25] / nr_, h[26] / nr_, h[27] / nr_, h[28] / nr_, h[29] / nr_, h[30] / nr_);
     }
     // A5: head on the last hidden state (fp32 CUDA cores; 0.2 % of the flops)
     if (ctx->cls_only) {
