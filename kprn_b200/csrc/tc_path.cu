@@ -39,6 +39,11 @@ constexpr int PROJ_RING = 5;
 constexpr int RECUR_RING = 6;
 constexpr int MAX_NS = 6;             // k-slices of the proj A tile: KE/64 entity slices + NOH one-hot slices
 constexpr int NUM_THREADS = 384;      // proj: warps 0 TMA producer, 1 MMA issuer, 2-3 gather/alloc, 4-11 epilogue
+#ifndef KPRN_PROJ2_GW
+#define KPRN_PROJ2_GW 4
+#endif
+constexpr int PROJ2_GW = KPRN_PROJ2_GW;                 // gather warps of proj2: 2, 4 or 8
+constexpr int PROJ2_THREADS = 384 + 32 * (PROJ2_GW - 2);  // warps 2,3 + (PROJ2_GW-2) extra gather warps after the epilogue
 constexpr int RECUR_THREADS = 640;    // recur: warps 0 TMA producer, 1 MMA issuer, 2 alloc, 3 h loader, 4-19 epilogue (4 groups)
 
 struct TcState {
@@ -49,6 +54,7 @@ struct TcState {
     float* Ptr = nullptr;
     DBuf xw, hT, hscratch, dbg;
     bool debug = false;
+    bool use_pairs = true;     // cta_group::2 projection kernel (KPRN_TC_PAIRS=0 falls back to the 1-CTA kernel)
     int num_sms = 148;
     bool attrs_set = false;
 };
@@ -404,6 +410,250 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) proj_kernel(ProjArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// kernel "proj2": the same projection on CTA PAIRS (tcgen05 cta_group::2, cluster of 2).  The pair multiplies two
+// 128-row tiles (one per CTA) by the same 256 gate columns per MMA: each CTA stages only its 128-column half of every
+// weight slab, so shared-memory traffic per CTA (the binding resource of the 1-CTA N=128 kernel: every SS MMA reads 4 KB
+// of A and 4 KB of B) drops to 4 KB of A + 4 KB of B per 128 tensor cycles, and the weight stream per SM halves.
+// The leader (cluster rank 0) issues the MMAs; completion is multicast to the barriers of both CTAs; the peer forwards
+// "my half of the slab / my A slice / my accumulator drain" to the leader's barriers with remote mbarrier arrives.
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PROJ2_THREADS, 1) proj2_kernel(ProjArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int R = PROJ_RING;
+    const uint32_t rank = ptx::cluster_ctarank();
+    const bool leader = rank == 0;
+    const int ah_chunks = a.KE / 8 + 8 * a.NOH;
+    uint8_t* sA_hi = smem;
+    uint8_t* sA_lo = smem + (size_t)ah_chunks * 2048;
+    uint8_t* sRing = sA_lo + (size_t)(a.KE / 8) * 2048;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sRing + R * B_SLAB_ELEMS * 2);
+    const uint32_t bar0 = ptx::smem_u32(bars);
+    auto BAR = [&](int i) { return bar0 + 8u * i; };
+    // [0,R) slab_full  [R,2R) slab_empty  [2R,3R) peer_full (leader)  then a_full[6] a_free[6] acc_full[2] acc_empty[2]
+    constexpr int B_PEER = 2 * R, B_AFULL = 3 * R, B_AFREE = 3 * R + MAX_NS, B_ACCF = 3 * R + 2 * MAX_NS, B_ACCE = B_ACCF + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_ACCE + 2);
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < R; ++i) { ptx::mbar_init(BAR(i), 1); ptx::mbar_init(BAR(R + i), 1); ptx::mbar_init(BAR(B_PEER + i), 1); }
+        for (int i = 0; i < MAX_NS; ++i) { ptx::mbar_init(BAR(B_AFULL + i), 2 * PROJ2_GW); ptx::mbar_init(BAR(B_AFREE + i), 1); }   // 8 gather warps x 2 CTAs
+        for (int i = 0; i < 2; ++i) { ptx::mbar_init(BAR(B_ACCF + i), 1); ptx::mbar_init(BAR(B_ACCE + i), 8); }           // 4 epilogue warps x 2 CTAs
+        ptx::fence_mbar_init();
+    }
+    if (warp == 2) { ptx::tmem_alloc2(ptx::smem_u32(tmem_slot), 512); ptx::tmem_relinquish2(); }
+    ptx::tc_fence_before();
+    ptx::cluster_sync();                      // barriers of both CTAs are initialised before any remote arrive
+    ptx::tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    long long dbg_acc[16] = {0};
+    const long long dbg_t0 = clock64();
+    const int64_t npairs = gridDim.x / 2, pair = blockIdx.x / 2;
+    const int64_t n_tp = (a.num_tiles + 1) / 2;                                  // tile pairs
+    const int64_t my_tiles = pair < n_tp ? (n_tp - pair + npairs - 1) / npairs : 0;
+    auto tile_of = [&](int64_t it) { int64_t m = 2 * (pair + it * npairs) + rank; return m < a.num_tiles ? m : a.num_tiles - 1; };
+    const int NP = a.NCH / 2;                                                    // 256-column pairs of chunks per tile
+    const uint32_t idesc = ptx::make_idesc_f16(1, 256, 256);
+    const int parts = a.passes == 3 ? 2 : 1;
+
+    if (warp == 0) {
+        // ===== TMA producer: this CTA's 128-column half (chunk 2*np + rank) of every slab =====
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int64_t it = 0; it < my_tiles; ++it)
+                for (int np = 0; np < NP; ++np)
+                    for (int s = 0; s < a.NS; ++s)
+                        for (int part = 0; part < parts; ++part) {
+                            TWAIT(0, BAR(R + stage), phase ^ 1);
+                            ptx::mbar_arrive_expect_tx(BAR(stage), B_SLAB_ELEMS * 2);
+                            const bf16* src = a.W + ((int64_t)((2 * np + rank) * a.NS + s) * 2 + part) * B_SLAB_ELEMS;
+                            ptx::tma_bulk_g2s(ptx::smem_u32(sRing + stage * B_SLAB_ELEMS * 2), src, B_SLAB_ELEMS * 2, BAR(stage));
+                            if (++stage == R) { stage = 0; phase ^= 1; }
+                        }
+        }
+    } else if (warp == 1) {
+        if (leader) {
+            // ===== MMA issuer (leader CTA): uniform control flow on the whole warp, one elected lane issues =====
+            const bool issue = ptx::elect_one();
+            uint32_t stage = 0, phase = 0;
+            int64_t au = 0;
+            const uint32_t aHi0 = ptx::desc_lo(ptx::smem_u32(sA_hi), 2048), aLo0 = ptx::desc_lo(ptx::smem_u32(sA_lo), 2048);
+            const uint32_t ring0 = ptx::desc_lo(ptx::smem_u32(sRing), 2048);
+            constexpr uint32_t DHI = ptx::desc_hi(128);
+            constexpr uint32_t SLAB_STEP = (B_SLAB_ELEMS * 2) >> 4, K16_STEP = (2 * 2048) >> 4, SLICE_STEP = (8 * 2048) >> 4;
+            for (int64_t it = 0; it < my_tiles; ++it) {
+                for (int np = 0; np < NP; ++np, ++au) {
+                    const int buf = au & 1;
+                    if (a.dbg) { long long t0 = clock64(); ptx::mbar_wait_cluster(BAR(B_ACCE + buf), ((au >> 1) & 1) ^ 1); dbg_acc[1] += clock64() - t0; }
+                    else ptx::mbar_wait_cluster(BAR(B_ACCE + buf), ((au >> 1) & 1) ^ 1);
+                    ptx::tc_fence_after();
+                    const uint32_t d = tmem + buf * 256;
+                    for (int s = 0; s < a.NS; ++s) {
+                        if (np == 0) {
+                            if (a.dbg) { long long t0 = clock64(); ptx::mbar_wait_cluster(BAR(B_AFULL + s), it & 1); dbg_acc[2] += clock64() - t0; }
+                            else ptx::mbar_wait_cluster(BAR(B_AFULL + s), it & 1);
+                            ptx::tc_fence_after();
+                        }
+                        const bool onehot = s >= a.KSe;
+                        const uint32_t ah = aHi0 + s * SLICE_STEP, al = aLo0 + s * SLICE_STEP;
+                        for (int part = 0; part < parts; ++part) {
+                            if (a.dbg) { long long t0 = clock64(); ptx::mbar_wait(BAR(stage), phase); ptx::mbar_wait_cluster(BAR(B_PEER + stage), phase); dbg_acc[3] += clock64() - t0; }
+                            else { ptx::mbar_wait(BAR(stage), phase); ptx::mbar_wait_cluster(BAR(B_PEER + stage), phase); }
+                            ptx::tc_fence_after();
+                            const uint32_t bl = ring0 + stage * SLAB_STEP;
+                            if (issue) {
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)
+                                    ptx::umma2_f16(d, ptx::desc_join(DHI, ah + k * K16_STEP), ptx::desc_join(DHI, bl + k * K16_STEP), idesc,
+                                                   (part | s | k) != 0);
+                                if (part == 0 && a.passes == 3 && !onehot) {
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k)
+                                        ptx::umma2_f16(d, ptx::desc_join(DHI, al + k * K16_STEP), ptx::desc_join(DHI, bl + k * K16_STEP), idesc, 1);
+                                }
+                                ptx::umma2_commit(BAR(R + stage), 3);
+                            }
+                            if (++stage == R) { stage = 0; phase ^= 1; }
+                        }
+                        if (issue && np == NP - 1) ptx::umma2_commit(BAR(B_AFREE + s), 3);
+                    }
+                    if (issue) ptx::umma2_commit(BAR(B_ACCF + buf), 3);
+                }
+            }
+        } else {
+            // ===== peer forwarder: tells the leader when this CTA's half of a slab has landed =====
+            if (lane == 0) {
+                uint32_t stage = 0, phase = 0;
+                const uint32_t remote0 = ptx::mapa(BAR(B_PEER), 0);
+                for (int64_t it = 0; it < my_tiles; ++it)
+                    for (int np = 0; np < NP; ++np)
+                        for (int s = 0; s < a.NS; ++s)
+                            for (int part = 0; part < parts; ++part) {
+                                ptx::mbar_wait(BAR(stage), phase);
+                                ptx::mbar_arrive_cluster(remote0 + 8u * stage);
+                                if (++stage == R) { stage = 0; phase ^= 1; }
+                            }
+            }
+        }
+    } else if (warp < 4 || warp >= 12) {   // gather warps: 2, 3, 12 .. 12+PROJ2_GW-3
+        // ===== 8 gather warps (2,3,12..17), one 16-row block each; both CTAs gather their own tile and report completion
+        // to the leader's a_full.  Many warps, few copies each: LDGSTS throughput is bounded by the copies in flight per warp =====
+        const int gw = warp < 4 ? warp - 2 : warp - 10;          // 0..PROJ2_GW-1
+        constexpr int GB = 8 / PROJ2_GW;                          // 16-row blocks per gather warp
+        const int rsub = lane >> 1, cpar = lane & 1;
+        const uint32_t dHi = ptx::smem_u32(sA_hi), dLo = ptx::smem_u32(sA_lo);
+        const uint32_t afull_leader = ptx::mapa(BAR(B_AFULL), 0);
+        int64_t eid[GB];
+        int combo[GB];
+        auto load_ids = [&](int64_t it) {
+            const int64_t m = tile_of(it);
+            const int64_t pt = m / a.T;
+            const int t = (int)(m % a.T);
+#pragma unroll
+            for (int b = 0; b < GB; ++b) {
+                const int r = (gw + PROJ2_GW * b) * 16 + rsub;
+                int64_t n = pt * TILE_M + r;
+                if (n >= a.N) n = a.N - 1;
+                const int32_t* idp = a.ids + (n * a.T + t) * 3;
+                int64_t id = (int64_t)idp[1] - 1;
+                eid[b] = id < 0 ? 0 : (id >= a.V_e ? a.V_e - 1 : id);
+                int ta = idp[0] - 1, rb = idp[2] - 1;
+                ta = ta < 0 ? 0 : (ta >= a.V_t ? a.V_t - 1 : ta);
+                rb = rb < 0 ? 0 : (rb >= a.V_r ? a.V_r - 1 : rb);
+                combo[b] = ta * a.V_r + rb;
+            }
+        };
+        if (my_tiles > 0) load_ids(0);
+        for (int64_t it = 0; it < my_tiles; ++it) {
+            for (int s = 0; s < a.NS; ++s) {
+                TWAIT(4, BAR(B_AFREE + s), (it & 1) ^ 1);
+                if (s < a.KSe) {
+#pragma unroll
+                    for (int b = 0; b < GB; ++b) {
+                        const int r = (gw + PROJ2_GW * b) * 16 + rsub;
+                        const bf16* sh = a.E_hi + eid[b] * a.KE + s * 64;
+                        const bf16* sl = a.E_lo + eid[b] * a.KE + s * 64;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int kc = cpar + 2 * i;
+                            ptx::cp_async16(dHi + (s * 8 + kc) * 2048 + r * 16, sh + kc * 8);
+                            ptx::cp_async16(dLo + (s * 8 + kc) * 2048 + r * 16, sl + kc * 8);
+                        }
+                    }
+                } else {
+                    const int o = s - a.KSe;
+#pragma unroll
+                    for (int b = 0; b < GB; ++b) {
+                        const int r = (gw + PROJ2_GW * b) * 16 + rsub;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int kc = cpar + 2 * i;
+                            uint32_t w[4] = {0u, 0u, 0u, 0u};
+                            if ((combo[b] >> 3) == o * 8 + kc) w[(combo[b] & 7) >> 1] = 0x3F80u << (16 * (combo[b] & 1));   // bf16 1.0
+                            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dHi + (s * 8 + kc) * 2048 + r * 16),
+                                         "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+                        }
+                    }
+                }
+                ptx::cp_async_commit();
+            }
+            if (it + 1 < my_tiles) load_ids(it + 1);
+            for (int s = 0; s < a.NS; ++s) {
+                switch (a.NS - 1 - s) {
+                    case 5: ptx::cp_async_wait_group<5>(); break;
+                    case 4: ptx::cp_async_wait_group<4>(); break;
+                    case 3: ptx::cp_async_wait_group<3>(); break;
+                    case 2: ptx::cp_async_wait_group<2>(); break;
+                    case 1: ptx::cp_async_wait_group<1>(); break;
+                    default: ptx::cp_async_wait_group<0>(); break;
+                }
+                ptx::fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive_cluster(afull_leader + 8u * s);
+            }
+        }
+    } else {
+        // ===== epilogue: each CTA drains its own 128 rows x 256 columns; the leader is told when both are done =====
+        const int wg = (warp - 4) >> 2;
+        const int q4 = warp & 3;
+        const int r = q4 * 32 + lane;
+        const uint32_t acce_leader = ptx::mapa(BAR(B_ACCE), 0);
+        const int64_t total_uses = my_tiles * NP;
+        for (int64_t au = wg; au < total_uses; au += 2) {
+            const int64_t it = au / NP;
+            const int np = (int)(au % NP);
+            const int buf = au & 1;
+            const int64_t m = tile_of(it);
+            float* xw = a.XW + ((m * (a.G4 / 4) + np * 64) * TILE_M + r) * 4;
+            TWAIT(5, BAR(B_ACCF + buf), (au >> 1) & 1);
+            ptx::tc_fence_after();
+            const uint32_t tbase = tmem + ((uint32_t)(q4 * 32) << 16) + buf * 256;
+#pragma unroll
+            for (int blk = 0; blk < 8; ++blk) {
+                float v[32];
+                ptx::tmem_ld32(tbase + blk * 32, v);
+                ptx::tc_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    *reinterpret_cast<float4*>(xw + (int64_t)(blk * 8 + i) * TILE_M * 4) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive_cluster(acce_leader + 8u * buf);
+        }
+    }
+    if (a.dbg && lane == 0 && leader) {
+        if (warp < 4 || warp == 4 || warp == 8) {
+            for (int i = 0; i < 15; ++i) if (dbg_acc[i]) atomicAdd(a.dbg + i, (unsigned long long)dbg_acc[i]);
+            if (warp == 1) atomicAdd(a.dbg + 15, (unsigned long long)(clock64() - dbg_t0));
+        }
+    }
+    ptx::tc_fence_before();
+    ptx::cluster_sync();
+    if (warp == 2) ptx::tmem_dealloc2(tmem, 512);
+}
+
+// ---------------------------------------------------------------------------------------------
 // kernel "recur": per 128-path tile, T LSTM steps.  TMEM: columns [0,256) two 128-column accumulators
 // (a chunk = 32 hidden units x 4 gates), columns [256,256+HP) the cell state c (fp32, lane = path).
 // Roles: warp 0 TMA producer (Wh slabs), warp 1 MMA issuer, warp 2 TMEM allocator, warp 3 h loader,
@@ -734,11 +984,13 @@ int tc_forward(kprn_ctx* ctx, const int32_t* d_ids, const int32_t* d_seg, int64_
         KPRN_CUDA(cudaGetDeviceProperties(&prop, ctx->device));
         s->num_sms = prop.multiProcessorCount;
         { const char* d = getenv("KPRN_TC_DEBUG"); s->debug = d && d[0] == '1'; }
+        { const char* d = getenv("KPRN_TC_PAIRS"); s->use_pairs = !(d && d[0] == '0'); }
         if (prop.major != 10) { set_error("tensor-core path needs sm_100 (found sm_%d%d)", prop.major, prop.minor); return KPRN_ECUDA; }
     }
     TcState* s = ctx->tc;
     if (!s->attrs_set) {
         KPRN_CUDA(cudaFuncSetAttribute(proj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)proj_smem(s->KE, s->NOH)));
+        KPRN_CUDA(cudaFuncSetAttribute(proj2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)proj_smem(s->KE, s->NOH)));
         KPRN_CUDA(cudaFuncSetAttribute(recur_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)recur_smem(64)));
         KPRN_CUDA(cudaFuncSetAttribute(recur_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)recur_smem(128)));
         KPRN_CUDA(cudaFuncSetAttribute(recur_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)recur_smem(256)));
@@ -764,7 +1016,13 @@ int tc_forward(kprn_ctx* ctx, const int32_t* d_ids, const int32_t* d_seg, int64_
         int64_t grid = a.num_tiles < s->num_sms ? a.num_tiles : s->num_sms;
         cudaEvent_t e0;
         KPRN_TRY(prof_begin(ctx, &e0));
-        proj_kernel<<<(unsigned)grid, NUM_THREADS, proj_smem(s->KE, s->NOH), ctx->stream>>>(a);
+        if (s->use_pairs && a.num_tiles >= 2) {
+            int64_t pairs = (a.num_tiles + 1) / 2;
+            int64_t g2 = 2 * (pairs < s->num_sms / 2 ? pairs : s->num_sms / 2);
+            proj2_kernel<<<(unsigned)g2, PROJ2_THREADS, proj_smem(s->KE, s->NOH), ctx->stream>>>(a);
+        } else {
+            proj_kernel<<<(unsigned)grid, NUM_THREADS, proj_smem(s->KE, s->NOH), ctx->stream>>>(a);
+        }
         KPRN_LAUNCH_CHECK(ctx);
         KPRN_TRY(prof_end(ctx, e0, 1));
     }
