@@ -116,6 +116,12 @@ int kprn_forward_f64ids(kprn_ctx* ctx, const double* ids_f64, int64_t B, int64_t
 /* device-pointer variant: everything already resident in HBM, fully asynchronous on the ctx stream */
 int kprn_forward_device(kprn_ctx* ctx, const int32_t* d_ids, const int32_t* d_seg_offsets, int64_t N, int64_t S,
                         int32_t train, float* d_out_scores, float* d_out_logits);
+/* Page-locked host buffers for the caller's batch tensors (optional).  kprn_forward* detect pinned host pointers and DMA
+ * from them directly; pageable pointers are staged through an internal pinned buffer first (one extra host memcpy).
+ * Replaces BatcherFileList:preallocateTensorToGPU / populateGPUTensor (SP/model/batcher/BatcherFileList.lua:53-96). */
+int kprn_pinned_alloc(int64_t bytes, void** host_ptr);
+int kprn_pinned_free(void* host_ptr);
+
 /* per-path head outputs s[N,L] of the last forward (MapReduce's "mapped", MapReduce.lua:33) -- tests/diagnostics */
 int kprn_get_path_logits(kprn_ctx* ctx, float* host, int64_t n_floats);
 

@@ -431,6 +431,24 @@ int kprn_forward_device(kprn_ctx* ctx, const int32_t* d_ids, const int32_t* d_se
     return forward_device_impl(ctx, d_ids, d_seg, N, S, train != 0, d_out_logits != nullptr, d_out_scores, d_out_logits);
 }
 
+static bool is_pinned(const void* p) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return attr.type == cudaMemoryTypeHost;
+}
+
+// host -> device copy on the ctx stream; pageable sources go through the ctx's pinned staging buffer at `stage_off`
+static int h2d(kprn_ctx* ctx, void* dst, const void* src, size_t bytes, size_t stage_off) {
+    if (is_pinned(src)) {
+        KPRN_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        return KPRN_OK;
+    }
+    KPRN_TRY(ensure_stage(ctx, stage_off + bytes));
+    memcpy((char*)ctx->h_stage + stage_off, src, bytes);
+    KPRN_CUDA(cudaMemcpyAsync(dst, (char*)ctx->h_stage + stage_off, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return KPRN_OK;
+}
+
 static int forward_host_common(kprn_ctx* ctx, int64_t N, int64_t S, int32_t train, float* out_scores, float* out_logits) {
     // ids / seg are already on the device in ctx->ids_buf / ctx->seg_buf
     const kprn_config& c = ctx->cfg;
@@ -459,13 +477,11 @@ int kprn_forward(kprn_ctx* ctx, const int32_t* ids, const int32_t* seg_offsets, 
     size_t ids_bytes = sizeof(int32_t) * (size_t)N * c.T * 3, seg_bytes = sizeof(int32_t) * (size_t)(S + 1);
     KPRN_TRY(ensure(ctx->ids_buf, ids_bytes));
     KPRN_TRY(ensure(ctx->seg_buf, seg_bytes));
-    // caller memory is pageable in general: stage through pinned memory so the copy is a real async DMA
-    KPRN_TRY(ensure_stage(ctx, ids_bytes + seg_bytes));
-    memcpy(ctx->h_stage, ids, ids_bytes);
-    KPRN_CUDA(cudaMemcpyAsync(ctx->ids_buf.p, ctx->h_stage, ids_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    // pinned caller memory is DMA'd directly; pageable memory is staged through pinned memory first
+    if (!is_pinned(ids) || (seg_offsets && !is_pinned(seg_offsets))) KPRN_TRY(ensure_stage(ctx, ids_bytes + seg_bytes));
+    KPRN_TRY(h2d(ctx, ctx->ids_buf.p, ids, ids_bytes, 0));
     if (seg_offsets) {
-        memcpy((char*)ctx->h_stage + ids_bytes, seg_offsets, seg_bytes);
-        KPRN_CUDA(cudaMemcpyAsync(ctx->seg_buf.p, (char*)ctx->h_stage + ids_bytes, seg_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        KPRN_TRY(h2d(ctx, ctx->seg_buf.p, seg_offsets, seg_bytes, ids_bytes));
     } else {
         dense_seg_kernel<<<(unsigned)cdiv(S + 1, 256), 256, 0, ctx->stream>>>(ctx->seg_buf.as<int32_t>(), S, paths_per_seg);
         KPRN_LAUNCH_CHECK(ctx);
@@ -490,6 +506,18 @@ int kprn_forward_f64ids(kprn_ctx* ctx, const double* ids_f64, int64_t B, int64_t
     dense_seg_kernel<<<(unsigned)cdiv(B + 1, 256), 256, 0, ctx->stream>>>(ctx->seg_buf.as<int32_t>(), B, (int32_t)P);
     KPRN_LAUNCH_CHECK(ctx);
     return forward_host_common(ctx, N, B, train, out_scores, out_logits);
+}
+
+int kprn_pinned_alloc(int64_t bytes, void** host_ptr) {
+    if (!host_ptr || bytes <= 0) { set_error("pinned_alloc: bad arguments"); return KPRN_EINVAL; }
+    cudaError_t e = cudaMallocHost(host_ptr, (size_t)bytes);
+    if (e != cudaSuccess) { set_error("cudaMallocHost(%lld) failed: %s", (long long)bytes, cudaGetErrorString(e)); return KPRN_ENOMEM; }
+    return KPRN_OK;
+}
+
+int kprn_pinned_free(void* host_ptr) {
+    if (host_ptr) cudaFreeHost(host_ptr);
+    return KPRN_OK;
 }
 
 int kprn_get_path_logits(kprn_ctx* ctx, float* host, int64_t n_floats) {

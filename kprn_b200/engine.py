@@ -59,6 +59,8 @@ ABI = {
     "kprn_forward": [C.c_void_p, _I32P, _I32P, C.c_int64, C.c_int64, C.c_int32, C.c_int32, _F32P, _F32P],
     "kprn_forward_f64ids": [C.c_void_p, _F64P, C.c_int64, C.c_int64, C.c_int32, _F32P, _F32P],
     "kprn_forward_device": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p],
+    "kprn_pinned_alloc": [C.c_int64, C.POINTER(C.c_void_p)],
+    "kprn_pinned_free": [C.c_void_p],
     "kprn_get_path_logits": [C.c_void_p, _F32P, C.c_int64],
     "kprn_loss_bce": [C.c_void_p, _F32P, C.c_int64, _F32P],
     "kprn_loss_bpr": [C.c_void_p, _I32P, _I32P, C.c_int64, C.c_int32, _F32P],
@@ -108,6 +110,20 @@ def _f32p(a):
 
 def _i32p(a):
     return None if a is None else a.ctypes.data_as(_I32P)
+
+
+def pinned_empty(shape, dtype):
+    """numpy array backed by page-locked host memory from kprn_pinned_alloc (freed when the array is collected)."""
+    lib = load_library()
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape))
+    p = C.c_void_p()
+    _chk(lib.kprn_pinned_alloc(max(n * dtype.itemsize, 1), C.byref(p)))
+    buf = (C.c_char * (n * dtype.itemsize)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=n).reshape(shape)
+    import weakref
+    weakref.finalize(buf, lib.kprn_pinned_free, C.c_void_p(p.value))
+    return arr
 
 
 class Engine:

@@ -46,6 +46,8 @@ int kprn_forward_f64ids(kprn_ctx* ctx, const double* ids_f64, int64_t B, int64_t
                         float* out_scores, float* out_logits);
 int kprn_forward_device(kprn_ctx* ctx, const int32_t* d_ids, const int32_t* d_seg_offsets, int64_t N, int64_t S,
                         int32_t train, float* d_out_scores, float* d_out_logits);
+int kprn_pinned_alloc(int64_t bytes, void** host_ptr);
+int kprn_pinned_free(void* host_ptr);
 int kprn_get_path_logits(kprn_ctx* ctx, float* host, int64_t n_floats);
 int kprn_loss_bce(kprn_ctx* ctx, const float* labels, int64_t S, float* loss);
 int kprn_loss_bpr(kprn_ctx* ctx, const int32_t* pos_seg, const int32_t* neg_seg, int64_t n_pairs,

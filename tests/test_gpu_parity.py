@@ -157,3 +157,16 @@ def test_scores_only_fast_path_equals_full(precision):
     assert_rel(s_fast, ref["scores"], what="scores-only")
     assert_rel(s_fast, s_full, rtol=1e-6, what="scores-only vs full")
     e.close()
+
+
+def test_pinned_host_buffers_give_identical_results():
+    from kprn_b200 import engine
+    o, params, ids, seg, labels = make_case(N=300, seed=22)
+    e = engine_for(o)
+    e.set_params(params)
+    s_pageable = e.forward(ids, seg)
+    pi = engine.pinned_empty(ids.shape, np.int32); pi[...] = ids
+    ps = engine.pinned_empty(seg.shape, np.int32); ps[...] = seg
+    s_pinned = e.forward(pi, ps)
+    np.testing.assert_array_equal(s_pageable, s_pinned)
+    e.close()
