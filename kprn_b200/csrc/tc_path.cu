@@ -60,12 +60,14 @@ struct TcState {
 };
 
 static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+// hidden size padded to an instantiated recur_kernel<HP> (padded units have zero weights and stay exactly 0)
+static inline int pad_hidden(int H) { return H <= 64 ? 64 : (H <= 128 ? 128 : 256); }
 
 bool tc_supported(const kprn_ctx* ctx) {
     const kprn_config& c = ctx->cfg;
     if (c.cell != KPRN_CELL_LSTM) return false;
-    int Hp = round_up(c.H, 64), KE = round_up(c.d_e, 64);
-    if (Hp > 256 || KE > 256) return false;
+    int KE = round_up(c.d_e, 64);
+    if (c.H > 256 || KE > 256) return false;
     int noh = (int)((c.V_t * c.V_r + 63) / 64);
     if (noh > 2 || KE / 64 + noh > MAX_NS) return false;   // (type,relation) combos ride the MMA as a one-hot k-slice
     return true;
@@ -977,7 +979,7 @@ int tc_forward(kprn_ctx* ctx, const int32_t* d_ids, const int32_t* d_seg, int64_
     if (!ctx->tc) {
         ctx->tc = new TcState();
         TcState* s = ctx->tc;
-        s->Hp = round_up(c.H, 64); s->KE = round_up(c.d_e, 64);
+        s->Hp = pad_hidden(c.H); s->KE = round_up(c.d_e, 64);
         s->NCH = s->Hp / 32; s->KSh = s->Hp / 64; s->KSe = s->KE / 64; s->G4 = 4 * s->Hp;
         s->NOH = (int)((c.V_t * c.V_r + 63) / 64); s->NS = s->KSe + s->NOH;
         cudaDeviceProp prop;

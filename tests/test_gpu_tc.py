@@ -17,6 +17,10 @@ TC_CASES = [
     dict(N=40000, seed=7, d_t=8, d_e=64, d_r=8, H=64, V_e=50000),                  # > 148 tiles: persistent loop
     dict(N=500, seed=8, d_t=8, d_e=64, d_r=8, H=64, V_e=500, pool=1),
     dict(N=500, seed=9, d_t=8, d_e=64, d_r=8, H=64, V_e=500, head_layers=2, L=1),
+    dict(N=260, seed=11, T=1, d_t=8, d_e=64, d_r=8, H=64, V_e=500),                 # single step: no recurrent MMA at all
+    dict(N=260, seed=12, T=2, d_t=8, d_e=128, d_r=8, H=64, V_e=500),                # d_e > H
+    dict(N=260, seed=13, d_t=8, d_e=64, d_r=8, H=192, V_e=500),                     # H padded 192 -> 256? no: 192 = 3*64, odd chunk pairs
+    dict(N=700, seed=14, d_t=6, d_e=72, d_r=10, H=96, V_e=900, V_t=9, V_r=12),      # 108 (type,rel) combos -> two one-hot slices, ragged dims
 ]
 
 

@@ -24,8 +24,8 @@ def assert_rel(actual, expected, rtol=RTOL, what=""):
 
 
 def make_case(N, seed, T=6, d_t=8, d_e=16, d_r=8, H=16, L=46, V_e=300, seg_mode="realistic", fixed_p=4,
-              length_mode="stress", **kw):
-    o = Oracle(T=T, d_t=d_t, d_e=d_e, d_r=d_r, H=H, L=L, V_e=V_e, **kw)
+              length_mode="stress", V_t=6, V_r=9, **kw):
+    o = Oracle(T=T, d_t=d_t, d_e=d_e, d_r=d_r, H=H, L=L, V_e=V_e, V_t=V_t, V_r=V_r, **kw)
     c = o.cfg
     ids = synth.make_paths(N, T=T, V_e=V_e, seed=seed, length_mode=length_mode, V_t=c.V_t, V_r=c.V_r)
     seg = synth.make_segments(N, seed=seed, mode=seg_mode, fixed_p=fixed_p)
