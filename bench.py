@@ -167,7 +167,7 @@ def workload_config(d, n_paths, gpus):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture (profiles/), bytes
-TRAFFIC = {"proj": 1.770e9, "recur": 1.869e9}   # profiles/r01_v2_summary.md
+TRAFFIC = {"proj": 1.772e9, "recur": 1.875e9}   # profiles/r01_v3_summary.md (proj2_kernel, recur_kernel<256>)
 
 
 def main():
