@@ -42,6 +42,9 @@ extern "C" {
 #define KPRN_PREC_FP32 0     /* CUDA-core FFMA, fp32 everywhere */
 #define KPRN_PREC_TC_SPLIT 1 /* tcgen05 kind::f16, 3-pass hi/lo split (parity mode on tensor cores) */
 #define KPRN_PREC_TC_FAST 2  /* tcgen05 kind::f16, single pass (NOT parity-certified) */
+#define KPRN_PREC_TC_ALL 3   /* like TC_SPLIT, and the training products (forward with caches, BPTT, weight gradients) also run
+                                on tcgen05 with the bf16x3 split: scores/loss within 1e-4, gradients within 5e-4 of fp64
+                                (TC_SPLIT keeps training on fp32 CUDA cores: gradients within 1e-4) */
 /* tables for kprn_zero_row */
 #define KPRN_TABLE_TYPE 0
 #define KPRN_TABLE_ENTITY 1

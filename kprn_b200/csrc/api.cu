@@ -262,7 +262,7 @@ int kprn_create(const kprn_config* cfg, kprn_ctx** out) {
     if (c.T < 1 || c.T > 64 || c.d_t < 1 || c.d_e < 1 || c.d_r < 1 || c.H < 1 || c.L < 1 || c.V_t < 1 || c.V_e < 1 ||
         c.V_r < 1 || c.class_id < 1 || c.class_id > c.L || (c.cell != KPRN_CELL_LSTM && c.cell != KPRN_CELL_RNN) ||
         (c.head_layers != 1 && c.head_layers != 2) || c.pool < 0 || c.pool > 2 || (c.pool == KPRN_POOL_TOPK && c.topk < 1) ||
-        c.precision < 0 || c.precision > 2) {
+        c.precision < 0 || c.precision > 3) {
         set_error("invalid kprn_config");
         return KPRN_EINVAL;
     }

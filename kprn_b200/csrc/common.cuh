@@ -104,6 +104,10 @@ int head_forward_cls(kprn_ctx* ctx, const float* d_hT, int64_t ldh, int64_t n0, 
 int sgemm(kprn_ctx* ctx, int64_t M, int64_t N, int64_t K, const float* A, int64_t sAm, int64_t sAk,
           const float* B, int64_t sBk, int64_t sBn, float* C, int64_t ldc, bool accumulate, int splitk = 1);
 
+// generic-stride GEMM on tensor cores (tc_gemm.cu); *handled == false -> caller falls back to the FFMA kernel
+int tc_gemm(kprn_ctx* ctx, int64_t M, int64_t N, int64_t K, const float* A, int64_t sAm, int64_t sAk, const float* B,
+            int64_t sBk, int64_t sBn, float* C, int64_t ldc, bool accumulate, int splitk, bool* handled);
+
 // ---- tensor-core path (tc_path.cu) ----
 bool tc_supported(const kprn_ctx* ctx);
 int tc_forward(kprn_ctx* ctx, const int32_t* d_ids, const int32_t* d_seg, int64_t N, int64_t S, bool train);

@@ -12,6 +12,11 @@ namespace kprn {
 int sgemm(kprn_ctx* ctx, int64_t M, int64_t N, int64_t K, const float* A, int64_t sAm, int64_t sAk,
           const float* B, int64_t sBk, int64_t sBn, float* C, int64_t ldc, bool accumulate, int splitk) {
     if (M <= 0 || N <= 0 || K <= 0) return KPRN_OK;
+    {   // tensor-core precision modes: large products run on tcgen05 (bf16x3 split), the rest on the FFMA kernel below
+        bool handled = false;
+        KPRN_TRY(tc_gemm(ctx, M, N, K, A, sAm, sAk, B, sBk, sBn, C, ldc, accumulate, splitk, &handled));
+        if (handled) return KPRN_OK;
+    }
     if (splitk < 1) splitk = 1;
     int64_t kchunk = cdiv(cdiv(K, splitk), SG_BK) * SG_BK;
     splitk = (int)cdiv(K, kchunk);

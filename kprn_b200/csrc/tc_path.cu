@@ -1003,7 +1003,7 @@ int tc_forward(kprn_ctx* ctx, const int32_t* d_ids, const int32_t* d_seg, int64_
     KPRN_TRY(ensure(s->xw, sizeof(float) * (size_t)ptiles * c.T * s->G4 * TILE_M));
     KPRN_TRY(ensure(s->hT, sizeof(float) * (size_t)N * c.H));
     KPRN_TRY(ensure(ctx->path_logits, sizeof(float) * N * c.L));
-    const int passes = c.precision == KPRN_PREC_TC_FAST ? 1 : 3;
+    const int passes = c.precision == KPRN_PREC_TC_FAST ? 1 : 3;   // TC_SPLIT and TC_ALL: bf16x3
     unsigned long long* dbg = nullptr;
     if (s->debug) {
         KPRN_TRY(ensure(s->dbg, 2 * 16 * sizeof(unsigned long long)));

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libkprn_b200.so")
 
 CELL_LSTM, CELL_RNN = 0, 1
 POOL_LSE, POOL_MAX, POOL_TOPK = 0, 1, 2
-PREC_FP32, PREC_TC_SPLIT, PREC_TC_FAST = 0, 1, 2
+PREC_FP32, PREC_TC_SPLIT, PREC_TC_FAST, PREC_TC_ALL = 0, 1, 2, 3
 TABLE_TYPE, TABLE_ENTITY, TABLE_RELATION = 0, 1, 2
 
 PARAM_NAMES = ["E_t", "E_e", "E_r", "Wx", "bx", "Wh", "bh", "W1", "b1", "Wo", "bo"]
