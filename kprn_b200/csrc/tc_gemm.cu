@@ -38,58 +38,79 @@ __device__ __forceinline__ void split_store8(const float* v, uint32_t dst_hi, ui
     uint32_t wh[4], wl[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const bf16 a = __float2bfloat16_rn(v[2 * i]), b = __float2bfloat16_rn(v[2 * i + 1]);
-        const bf16 c = __float2bfloat16_rn(v[2 * i] - __bfloat162float(a)), d = __float2bfloat16_rn(v[2 * i + 1] - __bfloat162float(b));
-        wh[i] = (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
-        wl[i] = (uint32_t)__bfloat16_as_ushort(c) | ((uint32_t)__bfloat16_as_ushort(d) << 16);
+        // packed conversions: cvt.rn.bf16x2.f32 for the hi pair, exact fp32 residuals, cvt.rn.bf16x2.f32 for the lo pair
+        const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h2);
+        const float r0 = v[2 * i] - __uint_as_float(hb << 16), r1 = v[2 * i + 1] - __uint_as_float(hb & 0xFFFF0000u);
+        const __nv_bfloat162 l2 = __floats2bfloat162_rn(r0, r1);
+        wh[i] = hb;
+        wl[i] = *reinterpret_cast<const uint32_t*>(&l2);
     }
     asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst_hi), "r"(wh[0]), "r"(wh[1]), "r"(wh[2]), "r"(wh[3]) : "memory");
     asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst_lo), "r"(wl[0]), "r"(wl[1]), "r"(wl[2]), "r"(wl[3]) : "memory");
 }
 
 // Fill one operand tile (ROWS x 64 k) of a stage.  elem(row, k) = P[row*sR + k*sK]; rows >= R or k >= kend read as 0.
+// Every thread first issues ALL of its global loads for the tile (independent, so their latencies overlap), then
+// converts and stores: the tile fill is then bounded by issue slots, not by one HBM round trip per task.
 template <int ROWS>
 __device__ __forceinline__ void fill_operand(const float* __restrict__ P, int64_t sR, int64_t sK, int64_t row0, int64_t R,
                                              int64_t k0, int64_t kend, uint32_t s_hi, uint32_t s_lo, int ptid) {
     constexpr uint32_t KC_STRIDE = ROWS * 16;     // bytes between k-chunks
     if (sK == 1) {
         // K-contiguous source: a thread owns (row, kc) = 8 consecutive k of one row (32 B); lanes take consecutive rows
+        constexpr int TASKS = ROWS * 8 / G_PRODUCERS;
         const bool vec = ((sR & 3) == 0) && ((reinterpret_cast<uintptr_t>(P) & 15) == 0) && ((k0 & 3) == 0);
-        for (int task = ptid; task < ROWS * 8; task += G_PRODUCERS) {
+        float v[TASKS][8];
+#pragma unroll
+        for (int i = 0; i < TASKS; ++i) {
+            const int task = ptid + i * G_PRODUCERS;
             const int row = task % ROWS, kc = task / ROWS;
             const int64_t gr = row0 + row, gk = k0 + kc * 8;
-            float v[8];
             if (gr < R && gk + 8 <= kend && vec) {
                 const float4 x0 = *reinterpret_cast<const float4*>(P + gr * sR + gk);
                 const float4 x1 = *reinterpret_cast<const float4*>(P + gr * sR + gk + 4);
-                v[0] = x0.x; v[1] = x0.y; v[2] = x0.z; v[3] = x0.w; v[4] = x1.x; v[5] = x1.y; v[6] = x1.z; v[7] = x1.w;
+                v[i][0] = x0.x; v[i][1] = x0.y; v[i][2] = x0.z; v[i][3] = x0.w; v[i][4] = x1.x; v[i][5] = x1.y; v[i][6] = x1.z; v[i][7] = x1.w;
             } else {
 #pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] = (gr < R && gk + e < kend) ? P[gr * sR + gk + e] : 0.f;
+                for (int e = 0; e < 8; ++e) v[i][e] = (gr < R && gk + e < kend) ? P[gr * sR + gk + e] : 0.f;
             }
-            split_store8(v, s_hi + kc * KC_STRIDE + row * 16, s_lo + kc * KC_STRIDE + row * 16);
+        }
+#pragma unroll
+        for (int i = 0; i < TASKS; ++i) {
+            const int task = ptid + i * G_PRODUCERS;
+            const int row = task % ROWS, kc = task / ROWS;
+            split_store8(v[i], s_hi + kc * KC_STRIDE + row * 16, s_lo + kc * KC_STRIDE + row * 16);
         }
     } else {
         // row-contiguous source (sR == 1 in practice): a thread owns (4 rows, kc): 8 float4 loads, one per k;
         // lanes take consecutive row quads (coalesced 512 B per k), shared stores are 64 B per lane, conflict-free
+        constexpr int TASKS = (ROWS / 4) * 8 / G_PRODUCERS;
         const bool vec = (sR == 1) && ((sK & 3) == 0) && ((reinterpret_cast<uintptr_t>(P) & 15) == 0) && ((row0 & 3) == 0);
-        for (int task = ptid; task < (ROWS / 4) * 8; task += G_PRODUCERS) {
+        float v[TASKS][4][8];
+#pragma unroll
+        for (int t = 0; t < TASKS; ++t) {
+            const int task = ptid + t * G_PRODUCERS;
             const int rq = task % (ROWS / 4), kc = task / (ROWS / 4);
             const int64_t gr = row0 + rq * 4, gk = k0 + kc * 8;
-            float v[4][8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
                 if (vec && gr + 4 <= R && gk + e < kend) {
                     const float4 x = *reinterpret_cast<const float4*>(P + (gk + e) * sK + gr);
-                    v[0][e] = x.x; v[1][e] = x.y; v[2][e] = x.z; v[3][e] = x.w;
+                    v[t][0][e] = x.x; v[t][1][e] = x.y; v[t][2][e] = x.z; v[t][3][e] = x.w;
                 } else {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) v[i][e] = (gr + i < R && gk + e < kend) ? P[(gr + i) * sR + (gk + e) * sK] : 0.f;
+                    for (int i = 0; i < 4; ++i) v[t][i][e] = (gr + i < R && gk + e < kend) ? P[(gr + i) * sR + (gk + e) * sK] : 0.f;
                 }
             }
+        }
+#pragma unroll
+        for (int t = 0; t < TASKS; ++t) {
+            const int task = ptid + t * G_PRODUCERS;
+            const int rq = task % (ROWS / 4), kc = task / (ROWS / 4);
 #pragma unroll
             for (int i = 0; i < 4; ++i)
-                split_store8(v[i], s_hi + kc * KC_STRIDE + (rq * 4 + i) * 16, s_lo + kc * KC_STRIDE + (rq * 4 + i) * 16);
+                split_store8(v[t][i], s_hi + kc * KC_STRIDE + (rq * 4 + i) * 16, s_lo + kc * KC_STRIDE + (rq * 4 + i) * 16);
         }
     }
 }
@@ -162,12 +183,15 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(GemmArgs a) {
             ptx::fence_proxy_async_smem();
             ptx::mbar_arrive(BAR(st));
         }
-        // ===== epilogue: TMEM -> C =====
-        ptx::mbar_wait(BAR(2 * G_STAGES), 0);
+        // ===== epilogue: TMEM -> shared (per-warp transpose tile, reusing the operand stages) -> C, coalesced:
+        // a warp owns 32 rows x 128 columns; lane = row when reading TMEM, lane = column when writing C, so every
+        // global access is 128 contiguous bytes instead of 32 scattered sectors =====
+        ptx::mbar_wait(BAR(2 * G_STAGES), 0);        // all MMAs retired: the stage buffers are free
         ptx::tc_fence_after();
         const int q4 = warp & 3;                      // TMEM lane quarter
         const int ch = (warp - 1) >> 2;               // column half
-        const int64_t gm = m0 + q4 * 32 + lane;
+        constexpr int TS = 129;                       // padded row stride (floats): conflict-free both ways
+        float* tile = reinterpret_cast<float*>(smem) + (size_t)(warp - 1) * 32 * TS;
         const uint32_t tbase = tmem + ((uint32_t)(q4 * 32) << 16) + ch * 128;
 #pragma unroll 1
         for (int blk = 0; blk < 4; ++blk) {
@@ -177,15 +201,36 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(GemmArgs a) {
 #pragma unroll
                 for (int e = 0; e < 32; ++e) v[e] = 0.f;
             }
-            if (gm < a.M) {
-                float* crow = a.C + gm * a.ldc;
 #pragma unroll
-                for (int e = 0; e < 32; ++e) {
-                    const int64_t gn = n0 + ch * 128 + blk * 32 + e;
-                    if (gn < a.N) {
-                        if (a.use_atomic) atomicAdd(crow + gn, v[e]);
-                        else if (a.accumulate) crow[gn] += v[e];
-                        else crow[gn] = v[e];
+            for (int e = 0; e < 32; ++e) tile[lane * TS + blk * 32 + e] = v[e];
+        }
+        __syncwarp();
+        const int64_t gn0 = n0 + ch * 128;
+#pragma unroll 1
+        for (int r0 = 0; r0 < 32; r0 += 8) {          // 8 rows x 4 accesses in flight per lane
+            float val[8][4], old[8][4];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int64_t gm = m0 + q4 * 32 + r0 + i;
+#pragma unroll
+                for (int c4 = 0; c4 < 4; ++c4) {
+                    const int col = c4 * 32 + lane;
+                    val[i][c4] = tile[(r0 + i) * TS + col];
+                    old[i][c4] = 0.f;
+                    if (a.accumulate && !a.use_atomic && gm < a.M && gn0 + col < a.N) old[i][c4] = a.C[gm * a.ldc + gn0 + col];
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int64_t gm = m0 + q4 * 32 + r0 + i;
+                if (gm >= a.M) continue;
+                float* crow = a.C + gm * a.ldc + gn0;
+#pragma unroll
+                for (int c4 = 0; c4 < 4; ++c4) {
+                    const int col = c4 * 32 + lane;
+                    if (gn0 + col < a.N) {
+                        if (a.use_atomic) atomicAdd(crow + col, val[i][c4]);
+                        else crow[col] = val[i][c4] + old[i][c4];
                     }
                 }
             }

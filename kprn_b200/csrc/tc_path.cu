@@ -677,10 +677,13 @@ __device__ __forceinline__ void pack_split8(const float* v, uint4& hi, uint4& lo
     uint32_t wh[4], wl[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const bf16 a = __float2bfloat16_rn(v[2 * i]), b = __float2bfloat16_rn(v[2 * i + 1]);
-        const bf16 c = __float2bfloat16_rn(v[2 * i] - __bfloat162float(a)), d = __float2bfloat16_rn(v[2 * i + 1] - __bfloat162float(b));
-        wh[i] = (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
-        wl[i] = (uint32_t)__bfloat16_as_ushort(c) | ((uint32_t)__bfloat16_as_ushort(d) << 16);
+        // packed cvt.rn.bf16x2.f32 for the hi pair, exact fp32 residuals, packed conversion for the lo pair
+        const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h2);
+        const float r0 = v[2 * i] - __uint_as_float(hb << 16), r1 = v[2 * i + 1] - __uint_as_float(hb & 0xFFFF0000u);
+        const __nv_bfloat162 l2 = __floats2bfloat162_rn(r0, r1);
+        wh[i] = hb;
+        wl[i] = *reinterpret_cast<const uint32_t*>(&l2);
     }
     hi = make_uint4(wh[0], wh[1], wh[2], wh[3]);
     lo = make_uint4(wl[0], wl[1], wl[2], wl[3]);
