@@ -77,3 +77,32 @@ def test_partition_never_splits_a_segment_and_balances_paths():
     l_ids, l_seg, _, (a, b) = dist.shard(ids, seg, None, 1, 4)
     assert l_seg[0] == 0 and l_seg[-1] == len(l_ids) and len(l_seg) == b - a + 1
     np.testing.assert_array_equal(l_ids, ids[seg[a]:seg[b]])
+
+
+def test_formatter_port_reproduces_reference_script_outputs(tmp_path):
+    """tests/golden/formatter_ref.json holds `.int` files written by the reference's own data/movie_data_format.py
+    (run by tools/make_golden.py on the first lines of the shipped samples); the port must reproduce them byte for byte."""
+    import json
+    import os
+    z = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "formatter_ref.json")))
+    for name, text in z["vocab"].items():
+        (tmp_path / name).write_text(text)
+    v = io.Vocab.load(str(tmp_path))
+    all_lines = z["inputs"]["positive"] + z["inputs"]["negative"] + z["inputs"]["test"]
+    T = io.max_path_length(all_lines, 6)
+    assert T == 6
+    train = {}
+    for name, label in (("positive", "1"), ("negative", "-1")):          # both append to train.txt.<P>.int, in this order
+        for P, rows in io.format_translated(z["inputs"][name], v, T, fixed_label=label).items():
+            train.setdefault(P, []).extend(rows)
+    test = io.format_translated(z["inputs"]["test"], v, T)
+    got = {"train/train.txt.%d.int" % P: rows for P, rows in train.items()}
+    got.update({"test/test.txt.%d.int" % P: rows for P, rows in test.items()})
+    assert sorted(got) == sorted(z["outputs"])
+    for k in got:
+        assert got[k] == z["outputs"][k], k
+    # and the reader turns a bucket into the tensors int2torch.lua would: [B,P,T,3], ids shifted by +1
+    p = tmp_path / "train.txt.2.int"
+    p.write_text("\n".join(got["train/train.txt.2.int"]) + "\n")
+    labels, data = io.read_int_file(str(p))
+    assert data.shape[1:] == (2, 6, 3) and data.min() >= 1 and set(np.unique(labels)) <= {0.0, 1.0}

@@ -10,6 +10,7 @@
 3. resort_ref.json -- a slice of the reference's shipped combine / sorted fixtures (eval/config1/*) to pin resort().
 """
 import importlib.util
+import zlib
 import json
 import os
 import sys
@@ -83,8 +84,58 @@ def make_eval_goldens():
               open(os.path.join(OUT, "resort_ref.json"), "w"))
 
 
+def make_formatter_goldens(n_lines=250):
+    """Runs the REFERENCE formatter (data/movie_data_format.py, Python-2 source: `xrange` and integer `/` are patched to
+    their Python-3 spellings, nothing else) on the first lines of the shipped samples in a scratch directory and stores
+    inputs + the `.int` files it writes."""
+    import shutil
+    import subprocess
+    import tempfile
+    tmp = tempfile.mkdtemp(prefix="kprn_fmt_")
+    os.makedirs(os.path.join(tmp, "input")); os.makedirs(os.path.join(tmp, "vocab"))
+    inputs = {}
+    for name in ("positive", "negative", "test"):
+        src = os.path.join(REF, "data", "input", "%s_matrix_sample.tsv.translated" % name)
+        lines = [ln.rstrip("\n") for ln in open(src)][:n_lines]
+        inputs[name] = lines
+        open(os.path.join(tmp, "input", "%s_matrix.tsv.translated" % name), "w").write("\n".join(lines) + "\n")
+    # vocabularies: the shipped ones; the entity vocab is a 10 000-row sample without the special rows, so they are appended
+    ent = [ln.rstrip("\n") for ln in open(os.path.join(REF, "data", "vocab", "all_entity_id_sample.txt"))]
+    seen = {ln.split("\t")[0] for ln in ent}
+    extra = []
+    for lines in inputs.values():          # give every third entity of the inputs an id, the rest stay #UNK_ENTITY
+        for ln in lines:
+            for tok in ln.split("\t")[2].replace("###", "-").split("-"):
+                if tok and tok[0] in "sup" and tok not in seen and (zlib.crc32(tok.encode()) % 3 == 0 or len(extra) < 5):
+                    seen.add(tok); extra.append(tok)
+    extra = sorted(extra)
+    ent += ["%s\t%d" % (t, 10000 + i) for i, t in enumerate(extra)]
+    ent += ["#UNK_ENTITY\t%d" % (10000 + len(extra)), "#PAD_TOKEN\t%d" % (10001 + len(extra))]
+    open(os.path.join(tmp, "vocab", "all_entity_id.txt"), "w").write("\n".join(ent) + "\n")
+    e2t = [ln.rstrip("\n") for ln in open(os.path.join(REF, "data", "vocab", "entity_to_type_sample.txt"))]
+    e2t += ["%s\t%s" % (t, {"s": "song", "u": "user", "p": "person"}[t[0]]) for t in extra[::2]]
+    open(os.path.join(tmp, "vocab", "entity_to_type.txt"), "w").write("\n".join(e2t) + "\n")
+    for f in ("entity_type_id.txt", "all_relation_id.txt", "domain-label"):
+        shutil.copy(os.path.join(REF, "data", "vocab", f), os.path.join(tmp, "vocab", f))
+    src = open(os.path.join(REF, "data", "movie_data_format.py")).read()
+    src = src.replace("xrange", "range").replace("path_len / 2 + 2", "path_len // 2 + 2")
+    open(os.path.join(tmp, "ref_formatter_py3.py"), "w").write(src)
+    subprocess.check_call([sys.executable, "ref_formatter_py3.py", "-i", "input", "-d", "output", "-o", "0", "-g", "0", "-e", "0",
+                           "-m", "6", "-t", "1"], cwd=tmp, stdout=subprocess.DEVNULL)
+    outputs = {}
+    for sub in ("train", "test"):
+        for f in sorted(os.listdir(os.path.join(tmp, "output", sub))):
+            outputs[sub + "/" + f] = [ln.rstrip("\n") for ln in open(os.path.join(tmp, "output", sub, f))]
+    vocab = {f: open(os.path.join(tmp, "vocab", f)).read() for f in ("all_entity_id.txt", "entity_to_type.txt", "entity_type_id.txt",
+                                                                       "all_relation_id.txt", "domain-label")}
+    json.dump({"inputs": inputs, "vocab": vocab, "outputs": outputs}, open(os.path.join(OUT, "formatter_ref.json"), "w"))
+    shutil.rmtree(tmp)
+    print("formatter goldens:", {k: len(v) for k, v in outputs.items()})
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    make_formatter_goldens()
     for name, kw in CASES.items():
         make_oracle_case(name, **kw)
     make_eval_goldens()
