@@ -712,9 +712,9 @@ __global__ void __launch_bounds__(RECUR_THREADS, 1) recur_kernel(RecurArgs a) {
     if (threadIdx.x == 0) {
         for (int i = 0; i < R; ++i) { ptx::mbar_init(BAR(i), 1); ptx::mbar_init(BAR(R + i), 1); }
         ptx::mbar_init(BAR(2 * R), 1); ptx::mbar_init(BAR(2 * R + 1), 1);
-        ptx::mbar_init(BAR(2 * R + 2), 256); ptx::mbar_init(BAR(2 * R + 3), 256);     // two epilogue groups share an accumulator
+        ptx::mbar_init(BAR(2 * R + 2), 512); ptx::mbar_init(BAR(2 * R + 3), 512);     // all 16 epilogue warps drain each accumulator
         ptx::mbar_init(BAR(2 * R + 4), 1);
-        for (int s = 0; s < KS; ++s) { ptx::mbar_init(BAR(B_HREADY + s), 1); ptx::mbar_init(BAR(B_HWRIT + s), 512); }
+        for (int s = 0; s < KS; ++s) { ptx::mbar_init(BAR(B_HREADY + s), 1); ptx::mbar_init(BAR(B_HWRIT + s), 1024); }   // 2 chunks x 512 epilogue threads per k-slice
         ptx::fence_mbar_init();
     }
     if (warp == 2) { ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 512); ptx::tmem_relinquish(); }
@@ -827,107 +827,108 @@ __global__ void __launch_bounds__(RECUR_THREADS, 1) recur_kernel(RecurArgs a) {
             }
         }
     } else if (warp >= 4) {
-        // ===== epilogue: 4 groups of 4 warps.  group = (half << 1) | wg : wg = chunk parity / accumulator,
-        // half = which two of the chunk's four 8-unit sub-blocks this group owns =====
-        const int group = (warp - 4) >> 2;
-        const int wg = group & 1, half = group >> 1;
+        // ===== epilogue: 4 groups of 4 warps; group g owns sub-block g (8 hidden units x 4 gates) of EVERY chunk, so all
+        // 16 warps drain one accumulator together: the latency of a chunk's cell math (what the MMA issuer waits for when
+        // it recycles an accumulator, and what delays h_t at the step boundary) is a quarter of a single group's =====
+        const int sb = (warp - 4) >> 2;               // this group's sub-block
         const int q4 = warp & 3;
         const int r = q4 * 32 + lane;
         const uint32_t lane_base = (uint32_t)(q4 * 32) << 16;
         const int64_t tile_xw = (int64_t)(a.G4 / 4) * TILE_M * 4;  // floats per tile-step
-        uint32_t ug = 0;
+        uint32_t ug0 = 0, ug1 = 0;
+        // XW of (chunk j, this sub-block), gate q: column blocks j*32 + q*8 + 2*sb, +1   (a block = 128 rows x 4 floats)
+#define KPRN_LOAD_XW(dst, base, j)                                                                                  \
+    _Pragma("unroll") for (int q = 0; q < 4; ++q) {                                                               \
+        const float4 x0 = *reinterpret_cast<const float4*>((base) + (int64_t)((j) * 32 + q * 8 + 2 * sb) * TILE_M * 4);     \
+        const float4 x1 = *reinterpret_cast<const float4*>((base) + (int64_t)((j) * 32 + q * 8 + 2 * sb + 1) * TILE_M * 4); \
+        dst[q * 8 + 0] = x0.x; dst[q * 8 + 1] = x0.y; dst[q * 8 + 2] = x0.z; dst[q * 8 + 3] = x0.w;                   \
+        dst[q * 8 + 4] = x1.x; dst[q * 8 + 5] = x1.y; dst[q * 8 + 6] = x1.z; dst[q * 8 + 7] = x1.w;                   \
+    }
         for (int64_t it = 0; it < my_tiles; ++it) {
             const int64_t pt = blockIdx.x + it * gridDim.x;
             const int64_t n = pt * TILE_M + r;
             for (int t = 0; t < T; ++t) {
                 const float* xw_t = a.XW + (pt * T + t) * tile_xw + r * 4;
                 const bool last = (t == T - 1);
-#pragma unroll 1
-                for (int lc = 0; lc < NCH / 2; ++lc) {
-                    const int j = 2 * lc + wg;
-                    const float* xj = xw_t + (int64_t)j * 32 * TILE_M * 4;
-                    // XW of sub-block sb, gate q: column blocks q*8 + 2*sb, +1   (each block = 128 rows x 4 floats)
-                    float xc[32], xn[32];
-#define KPRN_LOAD_XW(dst, sb)                                                                              \
-    _Pragma("unroll") for (int q = 0; q < 4; ++q) {                                                       \
-        const float4 x0 = *reinterpret_cast<const float4*>(xj + (int64_t)(q * 8 + 2 * (sb)) * TILE_M * 4);     \
-        const float4 x1 = *reinterpret_cast<const float4*>(xj + (int64_t)(q * 8 + 2 * (sb) + 1) * TILE_M * 4); \
-        dst[q * 8 + 0] = x0.x; dst[q * 8 + 1] = x0.y; dst[q * 8 + 2] = x0.z; dst[q * 8 + 3] = x0.w;           \
-        dst[q * 8 + 4] = x1.x; dst[q * 8 + 5] = x1.y; dst[q * 8 + 6] = x1.z; dst[q * 8 + 7] = x1.w;           \
-    }
-                    KPRN_LOAD_XW(xc, 2 * half)
+                float xa[32], xb[32];                 // XW of the current / next chunk, ping-pong (no register copies)
+                KPRN_LOAD_XW(xa, xw_t, 0)
+                auto chunk = [&](const int j, float (&xc)[32], float (&xn)[32]) {
+                    const int g = j & 1;
+                    uint32_t& ug = g ? ug1 : ug0;
+                    if (!last && j > 0) {
+                        // publish chunk j-1's h writes: generic-proxy global writes -> async-proxy (TMA) reader
+                        asm volatile("fence.proxy.async.global;" ::: "memory");
+                        ptx::mbar_arrive(BAR(B_HWRIT + ((j - 1) >> 1)));
+                    }
                     if (t > 0) {
-                        TWAIT(14, BAR(2 * R + wg), ug & 1);
+                        TWAIT(14, BAR(2 * R + g), ug & 1);
                         ptx::tc_fence_after();
                     }
-                    const uint32_t acc = tmem + lane_base + wg * 128;
+                    const uint32_t acc = tmem + lane_base + g * 128;
                     const uint32_t cst = tmem + lane_base + 256 + j * 32;
-#pragma unroll
-                    for (int sbi = 0; sbi < 2; ++sbi) {
-                        const int sb = 2 * half + sbi;
-                        float cp[8];
-                        if (t > 0) {
-                            float ai[8], ag[8], af[8], ao[8];
-                            ptx::tmem_ld8(acc + 0 * 32 + sb * 8, ai);
-                            ptx::tmem_ld8(acc + 1 * 32 + sb * 8, ag);
-                            ptx::tmem_ld8(acc + 2 * 32 + sb * 8, af);
-                            ptx::tmem_ld8(acc + 3 * 32 + sb * 8, ao);
-                            ptx::tmem_ld8(cst + sb * 8, cp);
-                            ptx::tc_wait_ld();
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) { xc[e] += ai[e]; xc[8 + e] += ag[e]; xc[16 + e] += af[e]; xc[24 + e] += ao[e]; }
-                        } else {
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) cp[e] = 0.f;
-                        }
-                        if (sbi == 0) { KPRN_LOAD_XW(xn, 2 * half + 1) }     // in flight during the cell math below
-                        float cn[8], hv[8];
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            // FastLSTM cell; two activations share one reciprocal (8 MUFU per cell instead of 10)
-                            const float ei = __expf(-fmaxf(xc[e], -30.f)), ef = __expf(-fmaxf(xc[16 + e], -30.f));
-                            const float eo = __expf(-fmaxf(xc[24 + e], -30.f)), eg = __expf(2.f * fminf(xc[8 + e], 15.f));
-                            const float rif = __fdividef(1.f, (1.f + ei) * (1.f + ef));
-                            const float rog = __fdividef(1.f, (1.f + eo) * (1.f + eg));
-                            const float i_ = (1.f + ef) * rif, f_ = (1.f + ei) * rif;
-                            const float o_ = (1.f + eg) * rog, g_ = 1.f - 2.f * (1.f + eo) * rog;
-                            cn[e] = fmaf(i_, g_, f_ * cp[e]);
-                            hv[e] = o_ * fast_tanh(cn[e]);
-                        }
-                        ptx::tmem_st8(cst + sb * 8, cn);
-                        if (!last) {
-                            uint4 hi, lo;
-                            pack_split8(hv, hi, lo);
-                            const int kc = 4 * j + sb;
-                            *reinterpret_cast<uint4*>(scratch + kc * 2048 + r * 16) = hi;
-                            *reinterpret_cast<uint4*>(scratch + H_BYTES + kc * 2048 + r * 16) = lo;
-                        } else if (n < a.N) {
-                            // SelectTable(-1): last hidden state, standard [N,H] layout for the head
-                            float* dst = a.hT + n * a.H + j * 32 + sb * 8;
-#pragma unroll
-                            for (int e = 0; e < 8; ++e)
-                                if (j * 32 + sb * 8 + e < a.H) dst[e] = hv[e];
-                        }
-                        if (sbi == 0) {
-#pragma unroll
-                            for (int e = 0; e < 32; ++e) xc[e] = xn[e];
-                        }
-                    }
-#undef KPRN_LOAD_XW
-                    ptx::tc_wait_st();
+                    float cp[8];
                     if (t > 0) {
+                        float ai[8], ag[8], af[8], ao[8];
+                        ptx::tmem_ld8(acc + 0 * 32 + sb * 8, ai);
+                        ptx::tmem_ld8(acc + 1 * 32 + sb * 8, ag);
+                        ptx::tmem_ld8(acc + 2 * 32 + sb * 8, af);
+                        ptx::tmem_ld8(acc + 3 * 32 + sb * 8, ao);
+                        ptx::tmem_ld8(cst + sb * 8, cp);
+                        ptx::tc_wait_ld();
+                        // the accumulator has been read: hand it back to the MMA issuer before the cell math
                         ptx::tc_fence_before();
-                        ptx::mbar_arrive(BAR(2 * R + 2 + wg));
+                        ptx::mbar_arrive(BAR(2 * R + 2 + g));
                         ++ug;
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) { xc[e] += ai[e]; xc[8 + e] += ag[e]; xc[16 + e] += af[e]; xc[24 + e] += ao[e]; }
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) cp[e] = 0.f;
                     }
+                    if (j + 1 < NCH) { KPRN_LOAD_XW(xn, xw_t, j + 1) }     // next chunk's XW, in flight during the cell math
+                    float cn[8], hv[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        // FastLSTM cell; two activations share one reciprocal (8 MUFU per cell instead of 10)
+                        const float ei = __expf(-fmaxf(xc[e], -30.f)), ef = __expf(-fmaxf(xc[16 + e], -30.f));
+                        const float eo = __expf(-fmaxf(xc[24 + e], -30.f)), eg = __expf(2.f * fminf(xc[8 + e], 15.f));
+                        const float rif = __fdividef(1.f, (1.f + ei) * (1.f + ef));
+                        const float rog = __fdividef(1.f, (1.f + eo) * (1.f + eg));
+                        const float i_ = (1.f + ef) * rif, f_ = (1.f + ei) * rif;
+                        const float o_ = (1.f + eg) * rog, g_ = 1.f - 2.f * (1.f + eo) * rog;
+                        cn[e] = fmaf(i_, g_, f_ * cp[e]);
+                        hv[e] = o_ * fast_tanh(cn[e]);
+                    }
+                    ptx::tmem_st8(cst + sb * 8, cn);
                     if (!last) {
-                        // generic-proxy global writes -> async-proxy (TMA) reader
-                        asm volatile("fence.proxy.async.global;" ::: "memory");
-                        ptx::mbar_arrive(BAR(B_HWRIT + (j >> 1)));
+                        uint4 hi, lo;
+                        pack_split8(hv, hi, lo);
+                        const int kc = 4 * j + sb;
+                        *reinterpret_cast<uint4*>(scratch + kc * 2048 + r * 16) = hi;
+                        *reinterpret_cast<uint4*>(scratch + H_BYTES + kc * 2048 + r * 16) = lo;
+                        // publication of these writes (proxy fence + arrive) is deferred by one chunk: by then the
+                        // stores have drained and the fence costs nothing (see the top of the loop / after the loop)
+                    } else if (n < a.N) {
+                        // SelectTable(-1): last hidden state, standard [N,H] layout for the head
+                        float* dst = a.hT + n * a.H + j * 32 + sb * 8;
+#pragma unroll
+                        for (int e = 0; e < 8; ++e)
+                            if (j * 32 + sb * 8 + e < a.H) dst[e] = hv[e];
                     }
+                                };
+#pragma unroll 1
+                for (int j = 0; j < NCH; j += 2) {
+                    chunk(j, xa, xb);
+                    chunk(j + 1, xb, xa);
                 }
+                if (!last) {
+                    asm volatile("fence.proxy.async.global;" ::: "memory");
+                    ptx::mbar_arrive(BAR(B_HWRIT + ((NCH - 1) >> 1)));
+                }
+                ptx::tc_wait_st();        // c_t is read back (tcgen05.ld) by this thread in the next step
             }
         }
+#undef KPRN_LOAD_XW
     }
     if (a.dbg && lane == 0) {
         // one representative lane per role: warps 0..3 and the first warp of each epilogue warpgroup
