@@ -332,7 +332,7 @@ def main():
                 "note": "achieved = algorithmic flops / CUDA-event launch time; the tensor cores execute %dx the hoisted flops "
                         "(bf16 hi/lo split) so frac <= ~0.45 in this mode even at 100%% tensor-pipe utilisation" % mult}
         if dom:
-            roof.update({"kernel": dom + ("_kernel" if dom != "gate_phase" else ""), "achieved": kern[dom]["achieved_tflops"],
+            roof.update({"kernel": {"proj": "proj2_kernel (x-projection, cta_group::2)", "recur": "recur_kernel<256> (recurrence)"}.get(dom, dom), "achieved": kern[dom]["achieved_tflops"],
                          "frac": kern[dom]["achieved_tflops"] / peak, "launch_ms": kern[dom]["launch_ms"],
                          "share_of_step": kern[dom]["launch_ms"] / ms_per_step})
         if "gate_phase" in kern:
