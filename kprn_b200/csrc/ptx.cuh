@@ -191,5 +191,20 @@ __device__ __forceinline__ void umma2_commit(uint32_t bar, uint16_t mask) {
                  ::"r"(bar), "h"(mask) : "memory");
 }
 
+
+// TMA tile::gather4: four rows (row indices r0..r3) x one box of columns starting at element `col` of a 2-D tensor map
+// -> 4 consecutive box rows in shared memory (hardware swizzle as encoded in the map), bytes counted on an mbarrier
+__device__ __forceinline__ void tma_gather4(uint32_t dst_smem, const void* tmap, int32_t col, int32_t r0, int32_t r1, int32_t r2,
+                                            int32_t r3, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+                 ::"r"(dst_smem), "l"(tmap), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void prefetch_tensormap(const void* tmap) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
+// K-major SWIZZLE_128B operand (rows of 128 B = 64 bf16, 8-row atoms of 1024 B): descriptor words
+__host__ __device__ constexpr uint32_t desc_hi_sw128() { return ((1024u >> 4) & 0x3FFF) | (1u << 14) | (2u << 29); }
+__device__ __forceinline__ uint32_t desc_lo_sw128(uint32_t smem_addr) { return ((smem_addr >> 4) & 0x3FFF) | (1u << 16); }
+
 }  // namespace ptx
 }  // namespace kprn

@@ -15,6 +15,7 @@
 //
 // Operand layouts are the canonical K-major no-swizzle UMMA layout [k/8][row][8 elements] (ptx.cuh), which the
 // packing kernels below produce in global memory so that a slab is one contiguous TMA bulk copy.
+#include <cuda.h>
 #include <cuda_bf16.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -54,6 +55,9 @@ struct TcState {
     float* Ptr = nullptr;
     DBuf xw, hT, hscratch, dbg;
     bool debug = false;
+    bool use_gather4 = true;   // TMA tile::gather4 for the entity rows (KPRN_TC_GATHER4=0 -> LDGSTS gather of proj2)
+    bool have_tmaps = false;
+    CUtensorMap tm_hi, tm_lo;
     bool use_pairs = true;     // cta_group::2 projection kernel (KPRN_TC_PAIRS=0 falls back to the 1-CTA kernel)
     int num_sms = 148;
     bool attrs_set = false;
@@ -656,6 +660,244 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PROJ2_THREADS, 1) pr
 }
 
 // ---------------------------------------------------------------------------------------------
+// kernel "proj3": proj2 with the entity rows gathered by the TMA unit (cp.async.bulk.tensor.2d tile::gather4 over a
+// tensor map of the pre-split bf16 table, 4 rows x 128 B per instruction, hardware 128-byte swizzle) instead of LDGSTS.
+// The entity k-slices of the A tile therefore use the K-major SWIZZLE_128B UMMA layout (rows of 128 B, 8-row atoms of
+// 1 KB); the one-hot slice keeps the no-swizzle layout.  Warp 2 issues the gathers (lane l owns rows 4l..4l+3), warp 3
+// forwards "my A slice has landed" to the leader CTA.
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+proj3_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo, ProjArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int R = PROJ_RING;
+    const uint32_t rank = ptx::cluster_ctarank();
+    const bool leader = rank == 0;
+    const int ah_chunks = a.KE / 8 + 8 * a.NOH;
+    uint8_t* sA_hi = smem;                                   // entity slices: [s][128 rows][128 B] swizzled; then one-hot slices
+    uint8_t* sA_lo = smem + (size_t)ah_chunks * 2048;
+    uint8_t* sRing = sA_lo + (size_t)(a.KE / 8) * 2048;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sRing + R * B_SLAB_ELEMS * 2);
+    const uint32_t bar0 = ptx::smem_u32(bars);
+    auto BAR = [&](int i) { return bar0 + 8u * i; };
+    // [0,R) slab_full [R,2R) slab_empty [2R,3R) peer_full(leader) a_full[6](leader) a_free[6] acc_full[2] acc_empty[2](leader) a_land[6]
+    constexpr int B_PEER = 2 * R, B_AFULL = 3 * R, B_AFREE = 3 * R + MAX_NS, B_ACCF = 3 * R + 2 * MAX_NS, B_ACCE = B_ACCF + 2,
+                  B_ALAND = B_ACCE + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_ALAND + MAX_NS);
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < R; ++i) { ptx::mbar_init(BAR(i), 1); ptx::mbar_init(BAR(R + i), 1); ptx::mbar_init(BAR(B_PEER + i), 1); }
+        for (int i = 0; i < MAX_NS; ++i) { ptx::mbar_init(BAR(B_AFULL + i), 2); ptx::mbar_init(BAR(B_AFREE + i), 1); ptx::mbar_init(BAR(B_ALAND + i), 1); }
+        for (int i = 0; i < 2; ++i) { ptx::mbar_init(BAR(B_ACCF + i), 1); ptx::mbar_init(BAR(B_ACCE + i), 8); }
+        ptx::fence_mbar_init();
+        ptx::prefetch_tensormap(&tm_hi);
+        ptx::prefetch_tensormap(&tm_lo);
+    }
+    if (warp == 2) { ptx::tmem_alloc2(ptx::smem_u32(tmem_slot), 512); ptx::tmem_relinquish2(); }
+    ptx::tc_fence_before();
+    ptx::cluster_sync();
+    ptx::tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    long long dbg_acc[16] = {0};
+    const long long dbg_t0 = clock64();
+    const int64_t npairs = gridDim.x / 2, pair = blockIdx.x / 2;
+    const int64_t n_tp = (a.num_tiles + 1) / 2;
+    const int64_t my_tiles = pair < n_tp ? (n_tp - pair + npairs - 1) / npairs : 0;
+    auto tile_of = [&](int64_t it) { int64_t m = 2 * (pair + it * npairs) + rank; return m < a.num_tiles ? m : a.num_tiles - 1; };
+    const int NP = a.NCH / 2;
+    const uint32_t idesc = ptx::make_idesc_f16(1, 256, 256);
+    const int parts = a.passes == 3 ? 2 : 1;
+
+    if (warp == 0) {
+        // ===== TMA producer: this CTA's 128-column half (chunk 2*np + rank) of every weight slab =====
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int64_t it = 0; it < my_tiles; ++it)
+                for (int np = 0; np < NP; ++np)
+                    for (int s = 0; s < a.NS; ++s)
+                        for (int part = 0; part < parts; ++part) {
+                            TWAIT(0, BAR(R + stage), phase ^ 1);
+                            ptx::mbar_arrive_expect_tx(BAR(stage), B_SLAB_ELEMS * 2);
+                            const bf16* src = a.W + ((int64_t)((2 * np + rank) * a.NS + s) * 2 + part) * B_SLAB_ELEMS;
+                            ptx::tma_bulk_g2s(ptx::smem_u32(sRing + stage * B_SLAB_ELEMS * 2), src, B_SLAB_ELEMS * 2, BAR(stage));
+                            if (++stage == R) { stage = 0; phase ^= 1; }
+                        }
+        }
+    } else if (warp == 1) {
+        if (leader) {
+            // ===== MMA issuer (leader CTA) =====
+            const bool issue = ptx::elect_one();
+            uint32_t stage = 0, phase = 0;
+            int64_t au = 0;
+            const uint32_t aHiSw = ptx::desc_lo_sw128(ptx::smem_u32(sA_hi)), aLoSw = ptx::desc_lo_sw128(ptx::smem_u32(sA_lo));
+            const uint32_t aHi0 = ptx::desc_lo(ptx::smem_u32(sA_hi), 2048);
+            const uint32_t ring0 = ptx::desc_lo(ptx::smem_u32(sRing), 2048);
+            constexpr uint32_t DHI = ptx::desc_hi(128), DHI_SW = ptx::desc_hi_sw128();
+            constexpr uint32_t SLAB_STEP = (B_SLAB_ELEMS * 2) >> 4, K16_STEP = (2 * 2048) >> 4, SLICE_STEP = (8 * 2048) >> 4;
+            for (int64_t it = 0; it < my_tiles; ++it) {
+                for (int np = 0; np < NP; ++np, ++au) {
+                    const int buf = au & 1;
+                    if (a.dbg) { long long t0 = clock64(); ptx::mbar_wait_cluster(BAR(B_ACCE + buf), ((au >> 1) & 1) ^ 1); dbg_acc[1] += clock64() - t0; }
+                    else ptx::mbar_wait_cluster(BAR(B_ACCE + buf), ((au >> 1) & 1) ^ 1);
+                    ptx::tc_fence_after();
+                    const uint32_t d = tmem + buf * 256;
+                    for (int s = 0; s < a.NS; ++s) {
+                        if (np == 0) {
+                            if (a.dbg) { long long t0 = clock64(); ptx::mbar_wait_cluster(BAR(B_AFULL + s), it & 1); dbg_acc[2] += clock64() - t0; }
+                            else ptx::mbar_wait_cluster(BAR(B_AFULL + s), it & 1);
+                            ptx::tc_fence_after();
+                        }
+                        const bool onehot = s >= a.KSe;
+                        // entity slices: SWIZZLE_128B descriptors (k16 step = 32 B); one-hot slice: no-swizzle descriptors
+                        const uint32_t ah = onehot ? aHi0 + s * SLICE_STEP : aHiSw + s * SLICE_STEP;
+                        const uint32_t al = aLoSw + s * SLICE_STEP;
+                        const uint32_t a_hi_word = onehot ? DHI : DHI_SW;
+                        const uint32_t a_k16 = onehot ? K16_STEP : 2u;
+                        for (int part = 0; part < parts; ++part) {
+                            if (a.dbg) { long long t0 = clock64(); ptx::mbar_wait(BAR(stage), phase); ptx::mbar_wait_cluster(BAR(B_PEER + stage), phase); dbg_acc[3] += clock64() - t0; }
+                            else { ptx::mbar_wait(BAR(stage), phase); ptx::mbar_wait_cluster(BAR(B_PEER + stage), phase); }
+                            ptx::tc_fence_after();
+                            const uint32_t bl = ring0 + stage * SLAB_STEP;
+                            if (issue) {
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)
+                                    ptx::umma2_f16(d, ptx::desc_join(a_hi_word, ah + k * a_k16), ptx::desc_join(DHI, bl + k * K16_STEP), idesc,
+                                                   (part | s | k) != 0);
+                                if (part == 0 && a.passes == 3 && !onehot) {
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k)
+                                        ptx::umma2_f16(d, ptx::desc_join(DHI_SW, al + k * 2u), ptx::desc_join(DHI, bl + k * K16_STEP), idesc, 1);
+                                }
+                                ptx::umma2_commit(BAR(R + stage), 3);
+                            }
+                            if (++stage == R) { stage = 0; phase ^= 1; }
+                        }
+                        if (issue && np == NP - 1) ptx::umma2_commit(BAR(B_AFREE + s), 3);
+                    }
+                    if (issue) ptx::umma2_commit(BAR(B_ACCF + buf), 3);
+                }
+            }
+        } else {
+            // ===== peer forwarder: tells the leader when this CTA's half of a slab has landed =====
+            if (lane == 0) {
+                uint32_t stage = 0, phase = 0;
+                const uint32_t remote0 = ptx::mapa(BAR(B_PEER), 0);
+                for (int64_t it = 0; it < my_tiles; ++it)
+                    for (int np = 0; np < NP; ++np)
+                        for (int s = 0; s < a.NS; ++s)
+                            for (int part = 0; part < parts; ++part) {
+                                ptx::mbar_wait(BAR(stage), phase);
+                                ptx::mbar_arrive_cluster(remote0 + 8u * stage);
+                                if (++stage == R) { stage = 0; phase ^= 1; }
+                            }
+            }
+        }
+    } else if (warp == 2) {
+        // ===== TMA gather warp: lane l owns rows 4l..4l+3 of this CTA's tile =====
+        const uint32_t dHi = ptx::smem_u32(sA_hi), dLo = ptx::smem_u32(sA_lo);
+        const uint32_t afull_leader = ptx::mapa(BAR(B_AFULL), 0);
+        int32_t eid[4];
+        int combo[4];
+        auto load_ids = [&](int64_t it) {
+            const int64_t m = tile_of(it);
+            const int64_t pt = m / a.T;
+            const int t = (int)(m % a.T);
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                int64_t n = pt * TILE_M + lane * 4 + b;
+                if (n >= a.N) n = a.N - 1;
+                const int32_t* idp = a.ids + (n * a.T + t) * 3;
+                int64_t id = (int64_t)idp[1] - 1;
+                eid[b] = (int32_t)(id < 0 ? 0 : (id >= a.V_e ? a.V_e - 1 : id));
+                int ta = idp[0] - 1, rb = idp[2] - 1;
+                ta = ta < 0 ? 0 : (ta >= a.V_t ? a.V_t - 1 : ta);
+                rb = rb < 0 ? 0 : (rb >= a.V_r ? a.V_r - 1 : rb);
+                combo[b] = ta * a.V_r + rb;
+            }
+        };
+        if (my_tiles > 0) load_ids(0);
+        for (int64_t it = 0; it < my_tiles; ++it) {
+            for (int s = 0; s < a.NS; ++s) {
+                TWAIT(4, BAR(B_AFREE + s), (it & 1) ^ 1);
+                if (s < a.KSe) {
+                    if (lane == 0) ptx::mbar_arrive_expect_tx(BAR(B_ALAND + s), 2 * TILE_M * 128);
+                    __syncwarp();
+                    const uint32_t off = s * 16384 + lane * 512;
+                    ptx::tma_gather4(dHi + off, &tm_hi, s * 64, eid[0], eid[1], eid[2], eid[3], BAR(B_ALAND + s));
+                    ptx::tma_gather4(dLo + off, &tm_lo, s * 64, eid[0], eid[1], eid[2], eid[3], BAR(B_ALAND + s));
+                } else {
+                    const int o = s - a.KSe;
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        const int r = lane * 4 + b;
+#pragma unroll
+                        for (int kc = 0; kc < 8; ++kc) {
+                            uint32_t w[4] = {0u, 0u, 0u, 0u};
+                            if ((combo[b] >> 3) == o * 8 + kc) w[(combo[b] & 7) >> 1] = 0x3F80u << (16 * (combo[b] & 1));   // bf16 1.0
+                            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dHi + (s * 8 + kc) * 2048 + r * 16),
+                                         "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+                        }
+                    }
+                    ptx::fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive_cluster(afull_leader + 8u * s);
+                }
+            }
+            if (it + 1 < my_tiles) load_ids(it + 1);
+        }
+    } else if (warp == 3) {
+        // ===== A forwarder: entity slice s of this CTA's tile has landed -> leader's a_full[s] =====
+        if (lane == 0) {
+            const uint32_t afull_leader = ptx::mapa(BAR(B_AFULL), 0);
+            for (int64_t it = 0; it < my_tiles; ++it)
+                for (int s = 0; s < a.KSe; ++s) {
+                    ptx::mbar_wait(BAR(B_ALAND + s), it & 1);
+                    ptx::mbar_arrive_cluster(afull_leader + 8u * s);
+                }
+        }
+    } else {
+        // ===== epilogue: each CTA drains its own 128 rows x 256 columns; the leader is told when both are done =====
+        const int wg = (warp - 4) >> 2;
+        const int q4 = warp & 3;
+        const int r = q4 * 32 + lane;
+        const uint32_t acce_leader = ptx::mapa(BAR(B_ACCE), 0);
+        const int64_t total_uses = my_tiles * NP;
+        for (int64_t au = wg; au < total_uses; au += 2) {
+            const int64_t it = au / NP;
+            const int np = (int)(au % NP);
+            const int buf = au & 1;
+            const int64_t m = tile_of(it);
+            float* xw = a.XW + ((m * (a.G4 / 4) + np * 64) * TILE_M + r) * 4;
+            TWAIT(5, BAR(B_ACCF + buf), (au >> 1) & 1);
+            ptx::tc_fence_after();
+            const uint32_t tbase = tmem + ((uint32_t)(q4 * 32) << 16) + buf * 256;
+#pragma unroll
+            for (int blk = 0; blk < 8; ++blk) {
+                float v[32];
+                ptx::tmem_ld32(tbase + blk * 32, v);
+                ptx::tc_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    *reinterpret_cast<float4*>(xw + (int64_t)(blk * 8 + i) * TILE_M * 4) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive_cluster(acce_leader + 8u * buf);
+        }
+    }
+    if (a.dbg && lane == 0 && leader) {
+        if (warp < 4 || warp == 4 || warp == 8) {
+            for (int i = 0; i < 15; ++i) if (dbg_acc[i]) atomicAdd(a.dbg + i, (unsigned long long)dbg_acc[i]);
+            if (warp == 1) atomicAdd(a.dbg + 15, (unsigned long long)(clock64() - dbg_t0));
+        }
+    }
+    ptx::tc_fence_before();
+    ptx::cluster_sync();
+    if (warp == 2) ptx::tmem_dealloc2(tmem, 512);
+}
+
+// ---------------------------------------------------------------------------------------------
 // kernel "recur": per 128-path tile, T LSTM steps.  TMEM: columns [0,256) two 128-column accumulators
 // (a chunk = 32 hidden units x 4 gates), columns [256,256+HP) the cell state c (fp32, lane = path).
 // Roles: warp 0 TMA producer (Wh slabs), warp 1 MMA issuer, warp 2 TMEM allocator, warp 3 h loader,
@@ -945,6 +1187,29 @@ __global__ void __launch_bounds__(RECUR_THREADS, 1) recur_kernel(RecurArgs a) {
 // ---------------------------------------------------------------------------------------------
 // host side
 
+// 2-D tensor maps over the pre-split entity tables [V_e rows][KE cols] bf16: box = 64 columns x 1 row (tile::gather4
+// fetches 4 such rows per instruction), 128-byte swizzle.  The driver entry point is resolved through the runtime.
+static bool make_entity_tensor_maps(TcState* s, int64_t V_e) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) { cudaGetLastError(); return false; }
+    EncodeFn enc = reinterpret_cast<EncodeFn>(fn);
+    const cuuint64_t gdim[2] = {(cuuint64_t)s->KE, (cuuint64_t)V_e};
+    const cuuint64_t gstride[1] = {(cuuint64_t)s->KE * 2};
+    const cuuint32_t box[2] = {64, 1};
+    const cuuint32_t estr[2] = {1, 1};
+    for (int i = 0; i < 2; ++i) {
+        CUresult r = enc(i ? &s->tm_lo : &s->tm_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, i ? (void*)s->E_lo : (void*)s->E_hi, gdim, gstride,
+                         box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return false;
+    }
+    return true;
+}
+
 static int tc_pack(kprn_ctx* ctx) {
     TcState* s = ctx->tc;
     const kprn_config& c = ctx->cfg;
@@ -957,6 +1222,7 @@ static int tc_pack(kprn_ctx* ctx) {
         KPRN_CUDA(cudaMalloc(&s->WxE, sizeof(bf16) * (size_t)s->NCH * s->NS * 2 * B_SLAB_ELEMS));
         KPRN_CUDA(cudaMalloc(&s->Wh, sizeof(bf16) * (size_t)s->NCH * s->KSh * 2 * B_SLAB_ELEMS));
         KPRN_CUDA(cudaMalloc(&s->Ptr, sizeof(float) * (size_t)c.V_t * c.V_r * s->G4));
+        s->have_tmaps = make_entity_tensor_maps(s, c.V_e);
     }
     int64_t ne = c.V_e * (int64_t)s->KE;
     split_entity_kernel<<<(unsigned)cdiv(ne, 256), 256, 0, ctx->stream>>>(ctx->d_params + l.E_e, c.V_e, c.d_e, s->KE, s->E_hi, s->E_lo);
@@ -974,7 +1240,7 @@ static int tc_pack(kprn_ctx* ctx) {
     return KPRN_OK;
 }
 
-static size_t proj_smem(int KE, int NOH) { return (size_t)(KE / 8 + 8 * NOH) * 2048 + (size_t)(KE / 8) * 2048 + PROJ_RING * B_SLAB_ELEMS * 2 + 384; }
+static size_t proj_smem(int KE, int NOH) { return (size_t)(KE / 8 + 8 * NOH) * 2048 + (size_t)(KE / 8) * 2048 + PROJ_RING * B_SLAB_ELEMS * 2 + 512; }
 static size_t recur_smem(int Hp) { return (size_t)2 * TILE_M * Hp * 2 + RECUR_RING * B_SLAB_ELEMS * 2 + 384; }
 
 int tc_forward(kprn_ctx* ctx, const int32_t* d_ids, const int32_t* d_seg, int64_t N, int64_t S, bool train) {
@@ -991,12 +1257,14 @@ int tc_forward(kprn_ctx* ctx, const int32_t* d_ids, const int32_t* d_seg, int64_
         s->num_sms = prop.multiProcessorCount;
         { const char* d = getenv("KPRN_TC_DEBUG"); s->debug = d && d[0] == '1'; }
         { const char* d = getenv("KPRN_TC_PAIRS"); s->use_pairs = !(d && d[0] == '0'); }
+        { const char* d = getenv("KPRN_TC_GATHER4"); s->use_gather4 = !(d && d[0] == '0'); }
         if (prop.major != 10) { set_error("tensor-core path needs sm_100 (found sm_%d%d)", prop.major, prop.minor); return KPRN_ECUDA; }
     }
     TcState* s = ctx->tc;
     if (!s->attrs_set) {
         KPRN_CUDA(cudaFuncSetAttribute(proj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)proj_smem(s->KE, s->NOH)));
         KPRN_CUDA(cudaFuncSetAttribute(proj2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)proj_smem(s->KE, s->NOH)));
+        KPRN_CUDA(cudaFuncSetAttribute(proj3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)proj_smem(s->KE, s->NOH)));
         KPRN_CUDA(cudaFuncSetAttribute(recur_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)recur_smem(64)));
         KPRN_CUDA(cudaFuncSetAttribute(recur_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)recur_smem(128)));
         KPRN_CUDA(cudaFuncSetAttribute(recur_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)recur_smem(256)));
@@ -1025,7 +1293,8 @@ int tc_forward(kprn_ctx* ctx, const int32_t* d_ids, const int32_t* d_seg, int64_
         if (s->use_pairs && a.num_tiles >= 2) {
             int64_t pairs = (a.num_tiles + 1) / 2;
             int64_t g2 = 2 * (pairs < s->num_sms / 2 ? pairs : s->num_sms / 2);
-            proj2_kernel<<<(unsigned)g2, PROJ2_THREADS, proj_smem(s->KE, s->NOH), ctx->stream>>>(a);
+            if (s->use_gather4 && s->have_tmaps) proj3_kernel<<<(unsigned)g2, NUM_THREADS, proj_smem(s->KE, s->NOH), ctx->stream>>>(s->tm_hi, s->tm_lo, a);
+            else proj2_kernel<<<(unsigned)g2, PROJ2_THREADS, proj_smem(s->KE, s->NOH), ctx->stream>>>(a);
         } else {
             proj_kernel<<<(unsigned)grid, NUM_THREADS, proj_smem(s->KE, s->NOH), ctx->stream>>>(a);
         }
