@@ -104,6 +104,14 @@ __device__ __forceinline__ int perm_to_row(int gp, int H, int& u) {
     return q * H + u;
 }
 
+// The recurrent kernel evaluates the gates as sigmoid(x) = 1/(1+2^(-x log2 e)) and tanh(x) = 1 - 2/(1+2^(2x log2 e)) with
+// ex2.approx; the factor (-log2 e for i,f,o and +2 log2 e for g) is folded into the packed weights, the hoisted table and
+// hence XW and the accumulators, so the cell math needs no multiply in front of the four gate exponentials.
+__device__ __forceinline__ float gate_scale(int gp) {
+    const int q = (gp >> 5) & 3;
+    return q == 1 ? 2.8853900817779268f : -1.4426950408889634f;
+}
+
 // proj B operand, slabs [chunk nt][slice s][hi|lo][kc 8][n 128][8]:
 //   s <  KSe : Wx[:, d_t : d_t+d_e]  (entity columns of the input projection)
 //   s >= KSe : P_tr^T, the hoisted (type,relation) table, multiplied by a one-hot k-slice of the A tile
@@ -127,6 +135,7 @@ __global__ void pack_wxe_kernel(const float* __restrict__ Wx, const float* __res
         int combo = (s - KSe) * 64 + kc * 8 + e;
         v = combo < ncombo ? Ptr[(int64_t)combo * G4 + gp] : 0.f;
     }
+    v *= gate_scale(gp);
     bf16 h, l;
     split_bf16(v, h, l);
     int64_t base = slab * 2 * B_SLAB_ELEMS + ((kc * 128 + n) << 3) + e;
@@ -146,7 +155,7 @@ __global__ void pack_wh_kernel(const float* __restrict__ Wh, int H, int NCH, int
     int s = (int)(slab % KSh), j = (int)(slab / KSh);
     int gp = j * 128 + n, k = s * 64 + kc * 8 + e, u;
     int row = perm_to_row(gp, H, u);
-    float v = (u < H && k < H) ? Wh[(int64_t)row * H + k] : 0.f;
+    float v = (u < H && k < H) ? Wh[(int64_t)row * H + k] * gate_scale(gp) : 0.f;
     bf16 h, l;
     split_bf16(v, h, l);
     int64_t base = slab * 2 * B_SLAB_ELEMS + ((kc * 128 + n) << 3) + e;
@@ -912,6 +921,8 @@ struct RecurArgs {
     unsigned long long* dbg;
 };
 
+__device__ __forceinline__ float ex2f(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcpf(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 __device__ __forceinline__ float fast_tanh(float x) { return 1.f - __fdividef(2.f, __expf(2.f * x) + 1.f); }
 
@@ -1131,15 +1142,17 @@ __global__ void __launch_bounds__(RECUR_THREADS, 1) recur_kernel(RecurArgs a) {
                     float cn[8], hv[8];
 #pragma unroll
                     for (int e = 0; e < 8; ++e) {
-                        // FastLSTM cell; two activations share one reciprocal (8 MUFU per cell instead of 10)
-                        const float ei = __expf(-fmaxf(xc[e], -30.f)), ef = __expf(-fmaxf(xc[16 + e], -30.f));
-                        const float eo = __expf(-fmaxf(xc[24 + e], -30.f)), eg = __expf(2.f * fminf(xc[8 + e], 15.f));
-                        const float rif = __fdividef(1.f, (1.f + ei) * (1.f + ef));
-                        const float rog = __fdividef(1.f, (1.f + eo) * (1.f + eg));
-                        const float i_ = (1.f + ef) * rif, f_ = (1.f + ei) * rif;
-                        const float o_ = (1.f + eg) * rog, g_ = 1.f - 2.f * (1.f + eo) * rog;
+                        // FastLSTM cell.  The pre-activations arrive pre-scaled (gate_scale): xc = -x log2e (i,f,o), +2x log2e (g),
+                        // so each gate costs one ex2; two activations share one reciprocal (8 MUFU per cell instead of 10).
+                        const float ei = ex2f(fminf(xc[e], 43.2809f)), ef = ex2f(fminf(xc[16 + e], 43.2809f));
+                        const float eo = ex2f(fminf(xc[24 + e], 43.2809f)), eg = ex2f(fminf(xc[8 + e], 43.2809f));
+                        const float pi = 1.f + ei, pf = 1.f + ef, po = 1.f + eo, pg = 1.f + eg;
+                        const float rif = rcpf(pi * pf), rog = rcpf(po * pg);
+                        const float i_ = pf * rif, f_ = pi * rif, o_ = pg * rog;
+                        const float g_ = fmaf(-2.f * po, rog, 1.f);
                         cn[e] = fmaf(i_, g_, f_ * cp[e]);
-                        hv[e] = o_ * fast_tanh(cn[e]);
+                        const float th = fmaf(-2.f, rcpf(ex2f(cn[e] * 2.8853900817779268f) + 1.f), 1.f);
+                        hv[e] = o_ * th;
                     }
                     ptx::tmem_st8(cst + sb * 8, cn);
                     if (!last) {
