@@ -227,11 +227,52 @@ __global__ void pool_fwd_kernel(const float* __restrict__ s, const int32_t* __re
     }
 }
 
+// Scores-only LSE pool: a warp-shuffle segmented reduction keyed by the (user,item) segment -- one warp per segment, lanes
+// stride over the segment's paths keeping an online (max, sum-exp) pair, merged across lanes with a shuffle butterfly.
+// Same math as LogSumExp.lua:13-30 for column classId, then nn.Sigmoid (OneModel.lua:294).
+__global__ void pool_lse_cls_warp_kernel(const float* __restrict__ s, const int32_t* __restrict__ seg, int64_t S, int L, float ig,
+                                         int cls, float* __restrict__ seg_logits, float* __restrict__ scores,
+                                         float* __restrict__ out_scores) {
+    const int64_t k = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (k >= S) return;
+    const int lane = threadIdx.x & 31;
+    const int64_t a = seg[k], b = seg[k + 1];
+    float m = -INFINITY, z = 0.f;
+    for (int64_t p = a + lane; p < b; p += 32) {
+        const float v = s[p * L + cls] * ig;
+        const float nm = fmaxf(m, v);
+        z = z * expf(m - nm) + expf(v - nm);      // exp(-inf) = 0 on the first element
+        m = nm;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        const float om = __shfl_xor_sync(0xffffffffu, m, o), oz = __shfl_xor_sync(0xffffffffu, z, o);
+        const float nm = fmaxf(m, om);
+        const float za = (m == -INFINITY) ? 0.f : z * expf(m - nm), zb = (om == -INFINITY) ? 0.f : oz * expf(om - nm);
+        z = za + zb;
+        m = nm;
+    }
+    if (lane == 0) {
+        const float out = (b > a) ? (m + logf(z)) / ig : 0.f;
+        seg_logits[k * L + cls] = out;
+        const float pr = sigmoidf_(out);
+        scores[k] = pr;
+        if (out_scores) out_scores[k] = pr;
+    }
+}
+
 int pool_forward(kprn_ctx* ctx, const int32_t* d_seg, int64_t S, float* d_out_scores, float* d_out_logits) {
     const kprn_config& c = ctx->cfg;
     KPRN_TRY(ensure(ctx->seg_logits, sizeof(float) * S * c.L));
     KPRN_TRY(ensure(ctx->scores, sizeof(float) * S));
     float ig = c.inv_gamma == 0.f ? 1.f : c.inv_gamma;
+    if (ctx->cls_only && c.pool == KPRN_POOL_LSE) {
+        pool_lse_cls_warp_kernel<<<(unsigned)cdiv(S, 8), 256, 0, ctx->stream>>>(ctx->path_logits.as<float>(), d_seg, S, c.L, ig,
+                                                                              c.class_id - 1, ctx->seg_logits.as<float>(),
+                                                                              ctx->scores.as<float>(), d_out_scores);
+        KPRN_LAUNCH_CHECK(ctx);
+        return KPRN_OK;
+    }
     const int col0 = ctx->cls_only ? c.class_id - 1 : 0, ncols = ctx->cls_only ? 1 : c.L;
     pool_fwd_kernel<<<(unsigned)cdiv(S * ncols, 256), 256, 0, ctx->stream>>>(
         ctx->path_logits.as<float>(), d_seg, S, c.L, c.pool, c.topk, ig, c.class_id - 1, col0, ncols,

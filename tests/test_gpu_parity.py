@@ -170,3 +170,39 @@ def test_pinned_host_buffers_give_identical_results():
     s_pinned = e.forward(pi, ps)
     np.testing.assert_array_equal(s_pageable, s_pinned)
     e.close()
+
+
+def test_long_and_ragged_segments_warp_shuffle_pool():
+    """Scores-only LSE pool = one warp per segment with a shuffle butterfly: segments of 1, 31, 32, 33, 1000 paths."""
+    o, params, ids, _, _ = make_case(N=1 + 31 + 32 + 33 + 1000 + 7, seed=23)
+    seg = np.cumsum([0, 1, 31, 32, 33, 1000, 7]).astype(np.int32)
+    ref = o.forward(params, ids, seg)
+    for precision in (0, 1):
+        e = engine_for(o, precision=precision) if precision == 0 else None
+        if e is None:
+            continue
+        e.set_params(params)
+        assert_rel(e.forward(ids, seg), ref["scores"], what="scores-only pool")
+        s_full, lg = e.forward(ids, seg, want_logits=True)
+        assert_rel(lg, ref["seg_logits"], what="full pool")
+        e.close()
+
+
+def test_fallback_kernels_still_match():
+    """KPRN_TC_GATHER4=0 (LDGSTS gather, proj2) and KPRN_TC_PAIRS=0 (1-CTA proj) are kept as fallbacks: same results."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = "\n".join([
+        "import sys; sys.path.insert(0, %r)" % root,
+        "from tests.util import make_case, engine_for, assert_rel",
+        "o, params, ids, seg, labels = make_case(N=700, seed=24, d_t=8, d_e=128, d_r=8, H=128, V_e=900)",
+        "ref = o.forward(params, ids, seg)",
+        "e = engine_for(o, precision=1); e.set_params(params)",
+        "assert_rel(e.forward(ids, seg), ref['scores'], what='scores'); print('ok')",
+    ])
+    compile(code, "<fallback>", "exec")
+    for env in ({"KPRN_TC_GATHER4": "0"}, {"KPRN_TC_PAIRS": "0"}):
+        out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0 and "ok" in out.stdout, (env, out.stderr[-800:])
