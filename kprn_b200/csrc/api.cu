@@ -232,15 +232,15 @@ static int forward_device_impl(kprn_ctx* ctx, const int32_t* d_ids, const int32_
     // scores-only fast path: nothing downstream of nn.Select(2,classId) needs the other L-1 columns
     ctx->cls_only = !train && !want_logits && c.head_layers == 1;
     bool use_tc = c.precision != KPRN_PREC_FP32 && tc_supported(ctx);
-    if (c.precision != KPRN_PREC_FP32 && !use_tc) {
-        set_error("precision mode %d (tensor cores) does not support this configuration", c.precision);
-        return KPRN_EINVAL;
-    }
+    // shapes the fused kernels do not cover (H or d_e > 256, Elman cell, large type x relation product): the generic
+    // engine runs, with its large products on tcgen05 (bf16x3) for scoring; TC_SPLIT training stays on fp32 FFMA
+    ctx->gemm_on_tc = c.precision != KPRN_PREC_FP32 && !use_tc && !train;
     cudaEvent_t e0;
     KPRN_TRY(prof_begin(ctx, &e0));
     if (use_tc) KPRN_TRY(tc_forward(ctx, d_ids, d_seg, N, S, train));
     else KPRN_TRY(simple_forward(ctx, d_ids, d_seg, N, S, train));
     KPRN_TRY(prof_end(ctx, e0, 0));
+    ctx->gemm_on_tc = false;
     KPRN_TRY(pool_forward(ctx, d_seg, S, d_out_scores, d_out_logits));
     ctx->have_fwd = true;
     ctx->have_train_cache = train;

@@ -206,5 +206,16 @@ __device__ __forceinline__ void prefetch_tensormap(const void* tmap) {
 __host__ __device__ constexpr uint32_t desc_hi_sw128() { return ((1024u >> 4) & 0x3FFF) | (1u << 14) | (2u << 29); }
 __device__ __forceinline__ uint32_t desc_lo_sw128(uint32_t smem_addr) { return ((smem_addr >> 4) & 0x3FFF) | (1u << 16); }
 
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// ---- packed fp32 pairs (sm_100: add/mul/fma .f32x2 on 64-bit registers = SASS FADD2 / FMUL2 / FFMA2) ----
+__device__ __forceinline__ uint64_t pack2(float a, float b) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void unpack2(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ float lo2(uint64_t v) { float a, b; unpack2(v, a, b); return a; }
+__device__ __forceinline__ float hi2(uint64_t v) { float a, b; unpack2(v, a, b); return b; }
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) { uint64_t r; asm("add.rn.ftz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) { uint64_t r; asm("mul.rn.ftz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) { uint64_t r; asm("fma.rn.ftz.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
 }  // namespace ptx
 }  // namespace kprn

@@ -247,7 +247,7 @@ static bool g_attr_set = false;
 int tc_gemm(kprn_ctx* ctx, int64_t M, int64_t N, int64_t K, const float* A, int64_t sAm, int64_t sAk, const float* B,
             int64_t sBk, int64_t sBn, float* C, int64_t ldc, bool accumulate, int splitk, bool* handled) {
     *handled = false;
-    if (ctx->cfg.precision != KPRN_PREC_TC_ALL && ctx->cfg.precision != KPRN_PREC_TC_FAST) return KPRN_OK;
+    if (ctx->cfg.precision != KPRN_PREC_TC_ALL && ctx->cfg.precision != KPRN_PREC_TC_FAST && !ctx->gemm_on_tc) return KPRN_OK;
     if (M * N * K < (1ll << 24)) return KPRN_OK;                      // small products stay on the FFMA kernel
     if (!(sAk == 1 || sAm == 1) || !(sBk == 1 || sBn == 1)) return KPRN_OK;
     const size_t smem = G_STAGES * G_STAGE_BYTES + 256;

@@ -37,7 +37,9 @@ using bf16 = __nv_bfloat16;
 constexpr int TILE_M = 128;           // paths per CTA tile (UMMA M)
 constexpr int B_SLAB_ELEMS = 8 * 128 * 8;   // weight slab: 64 k x 128 gate columns (16 KB), both kernels
 constexpr int PROJ_RING = 5;
-constexpr int RECUR_RING = 6;
+constexpr int RECUR_RING = 6;          // 16 KB weight slabs in flight (1-CTA recurrence)
+constexpr int RECUR_RING_PAIR = 8;     // 8 KB half-slabs in flight per CTA (CTA-pair recurrence)
+constexpr int RECUR_BAR_BYTES = 384;   // barrier block at the end of the recurrence's shared memory
 constexpr int MAX_NS = 6;             // k-slices of the proj A tile: KE/64 entity slices + NOH one-hot slices
 constexpr int NUM_THREADS = 384;      // proj: warps 0 TMA producer, 1 MMA issuer, 2-3 gather/alloc, 4-11 epilogue
 #ifndef KPRN_PROJ2_GW
@@ -45,7 +47,7 @@ constexpr int NUM_THREADS = 384;      // proj: warps 0 TMA producer, 1 MMA issue
 #endif
 constexpr int PROJ2_GW = KPRN_PROJ2_GW;                 // gather warps of proj2: 2, 4 or 8
 constexpr int PROJ2_THREADS = 384 + 32 * (PROJ2_GW - 2);  // warps 2,3 + (PROJ2_GW-2) extra gather warps after the epilogue
-constexpr int RECUR_THREADS = 640;    // recur: warps 0 TMA producer, 1 MMA issuer, 2 alloc, 3 h loader, 4-19 epilogue (4 groups)
+constexpr int RECUR_THREADS = 608;    // recur: warps 0 TMA producer, 1 MMA issuer, 2 TMEM alloc + h loader, 3-18 epilogue (4 groups); 19 warps -> 104 registers per thread
 
 struct TcState {
     uint64_t packed_version = 0;
@@ -59,6 +61,7 @@ struct TcState {
     bool have_tmaps = false;
     CUtensorMap tm_hi, tm_lo;
     bool use_pairs = true;     // cta_group::2 projection kernel (KPRN_TC_PAIRS=0 falls back to the 1-CTA kernel)
+    bool recur_pairs = true;   // cta_group::2 recurrence (KPRN_TC_RECUR_PAIRS=0 falls back to the 1-CTA form)
     int num_sms = 148;
     bool attrs_set = false;
 };
@@ -144,7 +147,8 @@ __global__ void pack_wxe_kernel(const float* __restrict__ Wx, const float* __res
 }
 
 // recur B operand: Wh -> slabs [chunk][kslice][hi|lo][kc 8][n 128][8]
-__global__ void pack_wh_kernel(const float* __restrict__ Wh, int H, int NCH, int KSh, bf16* __restrict__ out) {
+// pair = 1: each slab is stored as two 64-column halves [half][kc 8][n 64][8] (one contiguous 8 KB piece per CTA of a pair)
+__global__ void pack_wh_kernel(const float* __restrict__ Wh, int H, int NCH, int KSh, int pair, bf16* __restrict__ out) {
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t total = (int64_t)NCH * KSh * B_SLAB_ELEMS;
     if (idx >= total) return;
@@ -158,7 +162,8 @@ __global__ void pack_wh_kernel(const float* __restrict__ Wh, int H, int NCH, int
     float v = (u < H && k < H) ? Wh[(int64_t)row * H + k] * gate_scale(gp) : 0.f;
     bf16 h, l;
     split_bf16(v, h, l);
-    int64_t base = slab * 2 * B_SLAB_ELEMS + ((kc * 128 + n) << 3) + e;
+    int64_t within = pair ? (int64_t)(n >> 6) * (B_SLAB_ELEMS / 2) + ((kc * 64 + (n & 63)) << 3) + e : ((kc * 128 + n) << 3) + e;
+    int64_t base = slab * 2 * B_SLAB_ELEMS + within;
     out[base] = h;
     out[base + B_SLAB_ELEMS] = l;
 }
@@ -909,8 +914,8 @@ proj3_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ 
 // ---------------------------------------------------------------------------------------------
 // kernel "recur": per 128-path tile, T LSTM steps.  TMEM: columns [0,256) two 128-column accumulators
 // (a chunk = 32 hidden units x 4 gates), columns [256,256+HP) the cell state c (fp32, lane = path).
-// Roles: warp 0 TMA producer (Wh slabs), warp 1 MMA issuer, warp 2 TMEM allocator, warp 3 h loader,
-// warps 4-11 epilogue (wg 0 even chunks / accumulator 0, wg 1 odd chunks / accumulator 1).
+// Roles: warp 0 TMA producer (Wh slabs), warp 1 MMA issuer, warp 2 TMEM allocator + h loader, warps 3-18 epilogue:
+// four groups of four warps (one per TMEM lane quarter); group g owns sub-block g (8 hidden units x 4 gates) of every chunk.
 // h_t round trip: the epilogue writes h_t (bf16 hi/lo, already in the UMMA operand layout) to a per-CTA scratch that
 // stays in L2; once every MMA of step t has retired, the h loader pulls it into shared memory slice by slice with TMA
 // bulk copies, so the next step's MMAs start on slice 0 while the last chunks are still in the epilogue.  Keeping h_t
@@ -942,50 +947,80 @@ __device__ __forceinline__ void pack_split8(const float* v, uint4& hi, uint4& lo
     lo = make_uint4(wl[0], wl[1], wl[2], wl[3]);
 }
 
-template <int HP>
+// recur_kernel<HP, PAIR>.  PAIR = true: launched as clusters of two CTAs (cta_group::2).  Each CTA still owns one 128-path
+// tile (its own h in shared memory, c and accumulators in its own TMEM, its own epilogue), but one MMA multiplies both
+// tiles (M = 256) by the same 128 gate columns, and each CTA stages only ITS 64-column half of every weight slab: the
+// L2 -> SM weight stream -- more than half of this kernel's L2 traffic, which runs at ~85 % of the chip's measured L2
+// throughput in the 1-CTA form -- is halved.  The leader CTA's warp 1 issues the MMAs; the peer's warp 1 forwards
+// "my half-slab landed" / "my h slice landed" to the leader; both epilogues hand accumulators back to the leader;
+// MMA completion is multicast to both CTAs (tcgen05.commit ... multicast::cluster).
+template <int HP, bool PAIR>
 __global__ void __launch_bounds__(RECUR_THREADS, 1) recur_kernel(RecurArgs a) {
     constexpr int NCH = HP / 32;        // 128-column chunks per step
     constexpr int KS = HP / 64;         // 64-wide k slices of h
-    constexpr int R = RECUR_RING;
+    constexpr int R = PAIR ? RECUR_RING_PAIR : RECUR_RING;
+    constexpr uint32_t B_ROWS = PAIR ? 64 : 128;                    // gate columns of a slab staged by this CTA
+    constexpr uint32_t STAGE_ELEMS = 8 * B_ROWS * 8;                // [kc 8][n B_ROWS][8]
     constexpr uint32_t H_BYTES = TILE_M * HP * 2;   // one of hi / lo
     constexpr uint32_t SLICE_BYTES = 8 * 2048;      // one k-slice (64 units) of hi or lo
+    constexpr int EPI_WARPS = 16;
     extern __shared__ __align__(1024) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = PAIR ? ptx::cluster_ctarank() : 0u;
+    const bool leader = rank == 0;
     uint8_t* sH_hi = smem;
     uint8_t* sH_lo = smem + H_BYTES;
     uint8_t* sRing = smem + 2 * H_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sRing + R * B_SLAB_ELEMS * 2);
-    // bars: [0,R) slab_full  [R,2R) slab_empty  2R+{0,1} acc_full  2R+{2,3} acc_empty  2R+4 mma_step_done
-    //       2R+5+[0,KS) h_ready (TMA tx)  2R+5+KS+[0,KS) h_written
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sRing + R * STAGE_ELEMS * 2);
+    // bars: [0,R) slab_full  [R,2R) slab_empty  acc_full[2]  acc_empty[2] (leader's: both CTAs' epilogue warps)  mma_step_done
+    //       h_ready[KS] (TMA tx)  h_written[KS]  and on the leader: peer_slab_full[R]  peer_h_ready[KS]
     const uint32_t bar0 = ptx::smem_u32(bars);
     auto BAR = [&](int i) { return bar0 + 8u * i; };
-    constexpr int B_HREADY = 2 * R + 5, B_HWRIT = 2 * R + 5 + KS;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_HWRIT + KS);
+    constexpr int B_ACCF = 2 * R, B_ACCE = 2 * R + 2, B_STEP = 2 * R + 4, B_HREADY = 2 * R + 5, B_HWRIT = B_HREADY + KS,
+                  B_PSLAB = B_HWRIT + KS, B_PH = B_PSLAB + R, NBARS = B_PH + KS;
+    static_assert(NBARS * 8 + 4 <= RECUR_BAR_BYTES, "barrier block too small");
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NBARS);
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < R; ++i) { ptx::mbar_init(BAR(i), 1); ptx::mbar_init(BAR(R + i), 1); }
-        ptx::mbar_init(BAR(2 * R), 1); ptx::mbar_init(BAR(2 * R + 1), 1);
-        ptx::mbar_init(BAR(2 * R + 2), 512); ptx::mbar_init(BAR(2 * R + 3), 512);     // all 16 epilogue warps drain each accumulator
-        ptx::mbar_init(BAR(2 * R + 4), 1);
-        for (int s = 0; s < KS; ++s) { ptx::mbar_init(BAR(B_HREADY + s), 1); ptx::mbar_init(BAR(B_HWRIT + s), 1024); }   // 2 chunks x 512 epilogue threads per k-slice
+        for (int i = 0; i < R; ++i) { ptx::mbar_init(BAR(i), 1); ptx::mbar_init(BAR(R + i), 1); ptx::mbar_init(BAR(B_PSLAB + i), 1); }
+        ptx::mbar_init(BAR(B_ACCF), 1); ptx::mbar_init(BAR(B_ACCF + 1), 1);
+        ptx::mbar_init(BAR(B_ACCE), (PAIR ? 2 : 1) * EPI_WARPS); ptx::mbar_init(BAR(B_ACCE + 1), (PAIR ? 2 : 1) * EPI_WARPS);
+        ptx::mbar_init(BAR(B_STEP), 1);
+        for (int s = 0; s < KS; ++s) {
+            ptx::mbar_init(BAR(B_HREADY + s), 1);
+            ptx::mbar_init(BAR(B_HWRIT + s), 2 * EPI_WARPS * 32);     // 2 chunks x 512 epilogue threads per k-slice
+            ptx::mbar_init(BAR(B_PH + s), 1);
+        }
         ptx::fence_mbar_init();
     }
-    if (warp == 2) { ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 512); ptx::tmem_relinquish(); }
+    if (warp == 2) {
+        if (PAIR) { ptx::tmem_alloc2(ptx::smem_u32(tmem_slot), 512); ptx::tmem_relinquish2(); }
+        else { ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 512); ptx::tmem_relinquish(); }
+    }
     ptx::tc_fence_before();
-    __syncthreads();
+    if (PAIR) ptx::cluster_sync(); else __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
     long long dbg_acc[16] = {0};
     const long long dbg_t0 = clock64();
-    const int64_t my_tiles = (a.num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+    // tiles: 1-CTA form: blockIdx.x, +gridDim.x, ...; pair form: pair p takes tiles 2(p + i*npairs) + rank (an odd tail tile is
+    // computed by both CTAs of the last pair: identical values, identical stores)
+    const int64_t npairs = gridDim.x / 2, pair = blockIdx.x / 2, n_tp = (a.num_tiles + 1) / 2;
+    const int64_t my_tiles = PAIR ? (pair < n_tp ? (n_tp - pair + npairs - 1) / npairs : 0)
+                                  : (a.num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+    auto tile_of = [&](int64_t it) -> int64_t {
+        if (!PAIR) return blockIdx.x + it * gridDim.x;
+        const int64_t m = 2 * (pair + it * npairs) + rank;
+        return m < a.num_tiles ? m : a.num_tiles - 1;
+    };
     const int T = a.T;
-    const uint32_t idesc = ptx::make_idesc_f16(1, TILE_M, 128);
+    const uint32_t idesc = ptx::make_idesc_f16(1, PAIR ? 2 * TILE_M : TILE_M, 128);
     const int slabs_per_k = a.passes == 3 ? 2 : 1;
     uint8_t* scratch = reinterpret_cast<uint8_t*>(a.hscratch) + (size_t)blockIdx.x * 2 * H_BYTES;   // [hi | lo] image of sH
 
     if (warp == 0) {
-        // ===== TMA producer: Wh slabs; the sequence is identical for every MMA step (t >= 1) =====
+        // ===== TMA producer: Wh slabs (this CTA's columns); the sequence is identical for every MMA step (t >= 1) =====
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
             const int64_t steps = my_tiles * (T - 1);
@@ -994,74 +1029,105 @@ __global__ void __launch_bounds__(RECUR_THREADS, 1) recur_kernel(RecurArgs a) {
                     for (int s = 0; s < KS; ++s)
                         for (int part = 0; part < slabs_per_k; ++part) {
                             TWAIT(8, BAR(R + stage), phase ^ 1);
-                            ptx::mbar_arrive_expect_tx(BAR(stage), B_SLAB_ELEMS * 2);
-                            const bf16* src = a.W + ((int64_t)(j * KS + s) * 2 + part) * B_SLAB_ELEMS;
-                            ptx::tma_bulk_g2s(ptx::smem_u32(sRing + stage * B_SLAB_ELEMS * 2), src, B_SLAB_ELEMS * 2, BAR(stage));
+                            ptx::mbar_arrive_expect_tx(BAR(stage), STAGE_ELEMS * 2);
+                            const bf16* src = a.W + ((int64_t)(j * KS + s) * 2 + part) * B_SLAB_ELEMS + (PAIR ? rank * STAGE_ELEMS : 0u);
+                            ptx::tma_bulk_g2s(ptx::smem_u32(sRing + stage * STAGE_ELEMS * 2), src, STAGE_ELEMS * 2, BAR(stage));
                             if (++stage == R) { stage = 0; phase ^= 1; }
                         }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer: uniform control flow on the whole warp, one elected lane issues =====
-        const bool issue = ptx::elect_one();
-        uint32_t stage = 0, phase = 0;
-        uint32_t ug0 = 0, ug1 = 0;
-        const uint32_t hHi0 = ptx::desc_lo(ptx::smem_u32(sH_hi), 2048), hLo0 = ptx::desc_lo(ptx::smem_u32(sH_lo), 2048);
-        const uint32_t ring0 = ptx::desc_lo(ptx::smem_u32(sRing), 2048);
-        constexpr uint32_t DHI = ptx::desc_hi(128);
-        constexpr uint32_t SLAB_STEP = (B_SLAB_ELEMS * 2) >> 4, K16_STEP = (2 * 2048) >> 4, SLICE_STEP = (8 * 2048) >> 4;
-        uint32_t cnt = 0;                                   // 1-based index of the MMA step
-        for (int64_t it = 0; it < my_tiles; ++it) {
-            for (int t = 1; t < T; ++t) {
-                ++cnt;
+        if (leader) {
+            // ===== MMA issuer: uniform control flow on the whole warp, one elected lane issues =====
+            const bool issue = ptx::elect_one();
+            uint32_t stage = 0, phase = 0;
+            uint32_t ug0 = 0, ug1 = 0;
+            const uint32_t hHi0 = ptx::desc_lo(ptx::smem_u32(sH_hi), 2048), hLo0 = ptx::desc_lo(ptx::smem_u32(sH_lo), 2048);
+            const uint32_t ring0 = ptx::desc_lo(ptx::smem_u32(sRing), B_ROWS * 16);
+            constexpr uint32_t DHI = ptx::desc_hi(128);
+            constexpr uint32_t SLAB_STEP = (STAGE_ELEMS * 2) >> 4, K16_A = (2 * 2048) >> 4, K16_B = (2 * B_ROWS * 16) >> 4,
+                               SLICE_STEP = (8 * 2048) >> 4;
+            auto mma = [&](uint32_t d, uint64_t da, uint64_t db, uint32_t acc) {
+                if (PAIR) ptx::umma2_f16(d, da, db, idesc, acc); else ptx::umma_f16(d, da, db, idesc, acc);
+            };
+            auto commit = [&](uint32_t bar) { if (PAIR) ptx::umma2_commit(bar, 3); else ptx::umma_commit(bar); };
+            auto wait_slab = [&]() {
+                TWAIT(11, BAR(stage), phase);
+                if (PAIR) TWAIT(11, BAR(B_PSLAB + stage), phase);
+                ptx::tc_fence_after();
+            };
+            uint32_t cnt = 0;                                   // 1-based index of the MMA step
+            for (int64_t it = 0; it < my_tiles; ++it) {
+                for (int t = 1; t < T; ++t) {
+                    ++cnt;
 #pragma unroll 1
-                for (int j = 0; j < NCH; ++j) {
-                    const int g = j & 1;
-                    uint32_t& ug = g ? ug1 : ug0;
-                    TWAIT(9, BAR(2 * R + 2 + g), (ug & 1) ^ 1);
-                    ptx::tc_fence_after();
-                    const uint32_t d = tmem + g * 128;
-#pragma unroll 1
-                    for (int s = 0; s < KS; ++s) {
-                        if (j == 0) {          // h_{t-1} slice s has landed in shared memory
-                            TWAIT(10, BAR(B_HREADY + s), (cnt - 1) & 1);
-                            ptx::tc_fence_after();
-                        }
-                        const uint32_t ah = hHi0 + s * SLICE_STEP, al = hLo0 + s * SLICE_STEP;
-                        TWAIT(11, BAR(stage), phase);
+                    for (int j = 0; j < NCH; ++j) {
+                        const int g = j & 1;
+                        uint32_t& ug = g ? ug1 : ug0;
+                        TWAIT(9, BAR(B_ACCE + g), (ug & 1) ^ 1);
                         ptx::tc_fence_after();
-                        uint32_t bl = ring0 + stage * SLAB_STEP;
-                        if (issue) {
-#pragma unroll
-                            for (int k = 0; k < 4; ++k)
-                                ptx::umma_f16(d, ptx::desc_join(DHI, ah + k * K16_STEP), ptx::desc_join(DHI, bl + k * K16_STEP), idesc, (s | k) != 0);
-                            if (a.passes == 3) {
-#pragma unroll
-                                for (int k = 0; k < 4; ++k)
-                                    ptx::umma_f16(d, ptx::desc_join(DHI, al + k * K16_STEP), ptx::desc_join(DHI, bl + k * K16_STEP), idesc, 1);
+                        const uint32_t d = tmem + g * 128;
+#pragma unroll 1
+                        for (int s = 0; s < KS; ++s) {
+                            if (j == 0) {          // h_{t-1} slice s has landed in shared memory (of both CTAs)
+                                TWAIT(10, BAR(B_HREADY + s), (cnt - 1) & 1);
+                                if (PAIR) TWAIT(10, BAR(B_PH + s), (cnt - 1) & 1);
+                                ptx::tc_fence_after();
                             }
-                            ptx::umma_commit(BAR(R + stage));
-                        }
-                        if (++stage == R) { stage = 0; phase ^= 1; }
-                        if (a.passes == 3) {
-                            TWAIT(11, BAR(stage), phase);
-                            ptx::tc_fence_after();
-                            bl = ring0 + stage * SLAB_STEP;
+                            const uint32_t ah = hHi0 + s * SLICE_STEP, al = hLo0 + s * SLICE_STEP;
+                            wait_slab();
+                            uint32_t bl = ring0 + stage * SLAB_STEP;
                             if (issue) {
 #pragma unroll
                                 for (int k = 0; k < 4; ++k)
-                                    ptx::umma_f16(d, ptx::desc_join(DHI, ah + k * K16_STEP), ptx::desc_join(DHI, bl + k * K16_STEP), idesc, 1);
-                                ptx::umma_commit(BAR(R + stage));
+                                    mma(d, ptx::desc_join(DHI, ah + k * K16_A), ptx::desc_join(DHI, bl + k * K16_B), (s | k) != 0);
+                                if (a.passes == 3) {
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k)
+                                        mma(d, ptx::desc_join(DHI, al + k * K16_A), ptx::desc_join(DHI, bl + k * K16_B), 1);
+                                }
+                                commit(BAR(R + stage));
                             }
                             if (++stage == R) { stage = 0; phase ^= 1; }
+                            if (a.passes == 3) {
+                                wait_slab();
+                                bl = ring0 + stage * SLAB_STEP;
+                                if (issue) {
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k)
+                                        mma(d, ptx::desc_join(DHI, ah + k * K16_A), ptx::desc_join(DHI, bl + k * K16_B), 1);
+                                    commit(BAR(R + stage));
+                                }
+                                if (++stage == R) { stage = 0; phase ^= 1; }
+                            }
                         }
+                        if (issue) commit(BAR(B_ACCF + g));
+                        ++ug;
                     }
-                    if (issue) ptx::umma_commit(BAR(2 * R + g));
-                    ++ug;
+                    if (issue) commit(BAR(B_STEP));     // every MMA reading h_{t-1} has retired
                 }
-                if (issue) ptx::umma_commit(BAR(2 * R + 4));     // every MMA reading h_{t-1} has retired
             }
+        } else if (lane == 0) {
+            // ===== peer forwarder: mirrors the issuer's wait sequence on this CTA's barriers and arrives on the leader's =====
+            uint32_t stage = 0, phase = 0, cnt = 0;
+            const uint32_t pslab = ptx::mapa(BAR(B_PSLAB), 0), ph = ptx::mapa(BAR(B_PH), 0);
+            for (int64_t it = 0; it < my_tiles; ++it)
+                for (int t = 1; t < T; ++t) {
+                    ++cnt;
+                    for (int j = 0; j < NCH; ++j)
+                        for (int s = 0; s < KS; ++s) {
+                            if (j == 0) {
+                                ptx::mbar_wait(BAR(B_HREADY + s), (cnt - 1) & 1);
+                                ptx::mbar_arrive_cluster(ph + 8u * s);
+                            }
+                            for (int part = 0; part < slabs_per_k; ++part) {
+                                ptx::mbar_wait(BAR(stage), phase);
+                                ptx::mbar_arrive_cluster(pslab + 8u * stage);
+                                if (++stage == R) { stage = 0; phase ^= 1; }
+                            }
+                        }
+                }
         }
-    } else if (warp == 3) {
+    } else if (warp == 2) {
         // ===== h loader: scratch (L2) -> shared memory, one k-slice at a time =====
         if (lane == 0) {
             uint32_t idx = 0;                                   // 1-based index of the h vector being loaded
@@ -1069,7 +1135,7 @@ __global__ void __launch_bounds__(RECUR_THREADS, 1) recur_kernel(RecurArgs a) {
                 for (int t = 0; t < T - 1; ++t) {
                     ++idx;
                     // all MMAs that read the previous contents of sH must have retired: that is MMA step idx-1
-                    if (idx >= 2) TWAIT(12, BAR(2 * R + 4), (idx - 2) & 1);
+                    if (idx >= 2) TWAIT(12, BAR(B_STEP), (idx - 2) & 1);
                     for (int s = 0; s < KS; ++s) {
                         TWAIT(13, BAR(B_HWRIT + s), (idx - 1) & 1);
                         ptx::mbar_arrive_expect_tx(BAR(B_HREADY + s), 2 * SLICE_BYTES);
@@ -1079,26 +1145,28 @@ __global__ void __launch_bounds__(RECUR_THREADS, 1) recur_kernel(RecurArgs a) {
                 }
             }
         }
-    } else if (warp >= 4) {
+    } else {
         // ===== epilogue: 4 groups of 4 warps; group g owns sub-block g (8 hidden units x 4 gates) of EVERY chunk, so all
         // 16 warps drain one accumulator together: the latency of a chunk's cell math (what the MMA issuer waits for when
         // it recycles an accumulator, and what delays h_t at the step boundary) is a quarter of a single group's =====
-        const int sb = (warp - 4) >> 2;               // this group's sub-block
+        const int sb = (warp - 3) >> 2;               // this group's sub-block (a group = 4 consecutive warps = the 4 TMEM lane quarters)
         const int q4 = warp & 3;
         const int r = q4 * 32 + lane;
         const uint32_t lane_base = (uint32_t)(q4 * 32) << 16;
         const int64_t tile_xw = (int64_t)(a.G4 / 4) * TILE_M * 4;  // floats per tile-step
+        const uint32_t acce_leader = PAIR ? ptx::mapa(BAR(B_ACCE), 0) : BAR(B_ACCE);
+        const bool h_vec4 = (a.H & 3) == 0;
         uint32_t ug0 = 0, ug1 = 0;
         // XW of (chunk j, this sub-block), gate q: column blocks j*32 + q*8 + 2*sb, +1   (a block = 128 rows x 4 floats)
-#define KPRN_LOAD_XW(dst, base, j)                                                                                  \
-    _Pragma("unroll") for (int q = 0; q < 4; ++q) {                                                               \
+#define KPRN_LOAD_XW(dst, base, j)                                                                                    \
+    _Pragma("unroll") for (int q = 0; q < 4; ++q) {                                                                  \
         const float4 x0 = *reinterpret_cast<const float4*>((base) + (int64_t)((j) * 32 + q * 8 + 2 * sb) * TILE_M * 4);     \
         const float4 x1 = *reinterpret_cast<const float4*>((base) + (int64_t)((j) * 32 + q * 8 + 2 * sb + 1) * TILE_M * 4); \
         dst[q * 8 + 0] = x0.x; dst[q * 8 + 1] = x0.y; dst[q * 8 + 2] = x0.z; dst[q * 8 + 3] = x0.w;                   \
         dst[q * 8 + 4] = x1.x; dst[q * 8 + 5] = x1.y; dst[q * 8 + 6] = x1.z; dst[q * 8 + 7] = x1.w;                   \
     }
         for (int64_t it = 0; it < my_tiles; ++it) {
-            const int64_t pt = blockIdx.x + it * gridDim.x;
+            const int64_t pt = tile_of(it);
             const int64_t n = pt * TILE_M + r;
             for (int t = 0; t < T; ++t) {
                 const float* xw_t = a.XW + (pt * T + t) * tile_xw + r * 4;
@@ -1114,7 +1182,7 @@ __global__ void __launch_bounds__(RECUR_THREADS, 1) recur_kernel(RecurArgs a) {
                         ptx::mbar_arrive(BAR(B_HWRIT + ((j - 1) >> 1)));
                     }
                     if (t > 0) {
-                        TWAIT(14, BAR(2 * R + g), ug & 1);
+                        TWAIT(14, BAR(B_ACCF + g), ug & 1);
                         ptx::tc_fence_after();
                     }
                     const uint32_t acc = tmem + lane_base + g * 128;
@@ -1130,29 +1198,49 @@ __global__ void __launch_bounds__(RECUR_THREADS, 1) recur_kernel(RecurArgs a) {
                         ptx::tc_wait_ld();
                         // the accumulator has been read: hand it back to the MMA issuer before the cell math
                         ptx::tc_fence_before();
-                        ptx::mbar_arrive(BAR(2 * R + 2 + g));
+                        __syncwarp();
+                        if (lane == 0) {
+                            if (PAIR) ptx::mbar_arrive_cluster(acce_leader + 8u * g); else ptx::mbar_arrive(BAR(B_ACCE + g));
+                        }
                         ++ug;
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) { xc[e] += ai[e]; xc[8 + e] += ag[e]; xc[16 + e] += af[e]; xc[24 + e] += ao[e]; }
+                        for (int e = 0; e < 8; e += 2) {
+                            ptx::unpack2(ptx::add2(ptx::pack2(xc[e], xc[e + 1]), ptx::pack2(ai[e], ai[e + 1])), xc[e], xc[e + 1]);
+                            ptx::unpack2(ptx::add2(ptx::pack2(xc[8 + e], xc[9 + e]), ptx::pack2(ag[e], ag[e + 1])), xc[8 + e], xc[9 + e]);
+                            ptx::unpack2(ptx::add2(ptx::pack2(xc[16 + e], xc[17 + e]), ptx::pack2(af[e], af[e + 1])), xc[16 + e], xc[17 + e]);
+                            ptx::unpack2(ptx::add2(ptx::pack2(xc[24 + e], xc[25 + e]), ptx::pack2(ao[e], ao[e + 1])), xc[24 + e], xc[25 + e]);
+                        }
                     } else {
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) cp[e] = 0.f;
+                        for (int e = 0; e < 8; ++e) cp[e] = 0.f;      // t = 0: h = c = 0 and no MMA ran
                     }
                     if (j + 1 < NCH) { KPRN_LOAD_XW(xn, xw_t, j + 1) }     // next chunk's XW, in flight during the cell math
                     float cn[8], hv[8];
+                    // FastLSTM cell, two cells per instruction on the FMA pipe (add/mul/fma .f32x2 = SASS FADD2 / FMUL2 / FFMA2).
+                    // The pre-activations arrive pre-scaled (gate_scale): xc = -x log2e (i,f,o), +2x log2e (g), so each gate costs
+                    // one ex2 and one rcp (10 MUFU per cell); no clamps needed: ex2 -> inf gives rcp -> 0.
+                    {
+                        const uint64_t one2 = ptx::pack2(1.f, 1.f), mtwo2 = ptx::pack2(-2.f, -2.f);
+                        const uint64_t k2 = ptx::pack2(2.8853900817779268f, 2.8853900817779268f);
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        // FastLSTM cell.  The pre-activations arrive pre-scaled (gate_scale): xc = -x log2e (i,f,o), +2x log2e (g),
-                        // so each gate costs one ex2; two activations share one reciprocal (8 MUFU per cell instead of 10).
-                        const float ei = ex2f(fminf(xc[e], 43.2809f)), ef = ex2f(fminf(xc[16 + e], 43.2809f));
-                        const float eo = ex2f(fminf(xc[24 + e], 43.2809f)), eg = ex2f(fminf(xc[8 + e], 43.2809f));
-                        const float pi = 1.f + ei, pf = 1.f + ef, po = 1.f + eo, pg = 1.f + eg;
-                        const float rif = rcpf(pi * pf), rog = rcpf(po * pg);
-                        const float i_ = pf * rif, f_ = pi * rif, o_ = pg * rog;
-                        const float g_ = fmaf(-2.f * po, rog, 1.f);
-                        cn[e] = fmaf(i_, g_, f_ * cp[e]);
-                        const float th = fmaf(-2.f, rcpf(ex2f(cn[e] * 2.8853900817779268f) + 1.f), 1.f);
-                        hv[e] = o_ * th;
+                        for (int p = 0; p < 4; ++p) {
+                            const int e = 2 * p;
+                            const uint64_t pi = ptx::add2(ptx::pack2(ex2f(xc[e]), ex2f(xc[e + 1])), one2);
+                            const uint64_t pg = ptx::add2(ptx::pack2(ex2f(xc[8 + e]), ex2f(xc[9 + e])), one2);
+                            const uint64_t pf = ptx::add2(ptx::pack2(ex2f(xc[16 + e]), ex2f(xc[17 + e])), one2);
+                            const uint64_t po = ptx::add2(ptx::pack2(ex2f(xc[24 + e]), ex2f(xc[25 + e])), one2);
+                            const uint64_t i_ = ptx::pack2(rcpf(ptx::lo2(pi)), rcpf(ptx::hi2(pi)));
+                            const uint64_t f_ = ptx::pack2(rcpf(ptx::lo2(pf)), rcpf(ptx::hi2(pf)));
+                            const uint64_t o_ = ptx::pack2(rcpf(ptx::lo2(po)), rcpf(ptx::hi2(po)));
+                            const uint64_t g_ = ptx::fma2(ptx::pack2(rcpf(ptx::lo2(pg)), rcpf(ptx::hi2(pg))), mtwo2, one2);
+                            const uint64_t c2 = ptx::fma2(i_, g_, ptx::mul2(f_, ptx::pack2(cp[e], cp[e + 1])));
+                            const uint64_t a2 = ptx::mul2(c2, k2);
+                            const uint64_t pt2 = ptx::add2(ptx::pack2(ex2f(ptx::lo2(a2)), ex2f(ptx::hi2(a2))), one2);
+                            const uint64_t th = ptx::fma2(ptx::pack2(rcpf(ptx::lo2(pt2)), rcpf(ptx::hi2(pt2))), mtwo2, one2);
+                            const uint64_t h2 = ptx::mul2(o_, th);
+                            cn[e] = ptx::lo2(c2); cn[e + 1] = ptx::hi2(c2);
+                            hv[e] = ptx::lo2(h2); hv[e + 1] = ptx::hi2(h2);
+                        }
                     }
                     ptx::tmem_st8(cst + sb * 8, cn);
                     if (!last) {
@@ -1162,15 +1250,20 @@ __global__ void __launch_bounds__(RECUR_THREADS, 1) recur_kernel(RecurArgs a) {
                         *reinterpret_cast<uint4*>(scratch + kc * 2048 + r * 16) = hi;
                         *reinterpret_cast<uint4*>(scratch + H_BYTES + kc * 2048 + r * 16) = lo;
                         // publication of these writes (proxy fence + arrive) is deferred by one chunk: by then the
-                        // stores have drained and the fence costs nothing (see the top of the loop / after the loop)
+                        // stores have drained and the fence costs nothing (see the top of the lambda / after the loop)
                     } else if (n < a.N) {
                         // SelectTable(-1): last hidden state, standard [N,H] layout for the head
                         float* dst = a.hT + n * a.H + j * 32 + sb * 8;
+                        if (h_vec4 && j * 32 + sb * 8 + 8 <= a.H) {      // full-sector stores (scalar stores cost 8 partial sectors)
+                            *reinterpret_cast<float4*>(dst) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+                            *reinterpret_cast<float4*>(dst + 4) = make_float4(hv[4], hv[5], hv[6], hv[7]);
+                        } else {
 #pragma unroll
-                        for (int e = 0; e < 8; ++e)
-                            if (j * 32 + sb * 8 + e < a.H) dst[e] = hv[e];
+                            for (int e = 0; e < 8; ++e)
+                                if (j * 32 + sb * 8 + e < a.H) dst[e] = hv[e];
+                        }
                     }
-                                };
+                };
 #pragma unroll 1
                 for (int j = 0; j < NCH; j += 2) {
                     chunk(j, xa, xb);
@@ -1185,16 +1278,16 @@ __global__ void __launch_bounds__(RECUR_THREADS, 1) recur_kernel(RecurArgs a) {
         }
 #undef KPRN_LOAD_XW
     }
-    if (a.dbg && lane == 0) {
-        // one representative lane per role: warps 0..3 and the first warp of each epilogue warpgroup
-        if (warp < 4 || warp == 4 || warp == 8) {
+    if (a.dbg && lane == 0 && leader) {
+        // one representative lane per role: warps 0..2 and the first warp of the first two epilogue groups
+        if (warp <= 3 || warp == 7) {
             for (int i = 0; i < 15; ++i) if (dbg_acc[i]) atomicAdd(a.dbg + i, (unsigned long long)dbg_acc[i]);
             if (warp == 1) atomicAdd(a.dbg + 15, (unsigned long long)(clock64() - dbg_t0));
         }
     }
     ptx::tc_fence_before();
-    __syncthreads();
-    if (warp == 2) ptx::tmem_dealloc(tmem, 512);
+    if (PAIR) ptx::cluster_sync(); else __syncthreads();
+    if (warp == 2) { if (PAIR) ptx::tmem_dealloc2(tmem, 512); else ptx::tmem_dealloc(tmem, 512); }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1241,7 +1334,7 @@ static int tc_pack(kprn_ctx* ctx) {
     split_entity_kernel<<<(unsigned)cdiv(ne, 256), 256, 0, ctx->stream>>>(ctx->d_params + l.E_e, c.V_e, c.d_e, s->KE, s->E_hi, s->E_lo);
     KPRN_LAUNCH_CHECK(ctx);
     int64_t nh = (int64_t)s->NCH * s->KSh * B_SLAB_ELEMS;
-    pack_wh_kernel<<<(unsigned)cdiv(nh, 256), 256, 0, ctx->stream>>>(ctx->d_params + l.Wh, c.H, s->NCH, s->KSh, s->Wh);
+    pack_wh_kernel<<<(unsigned)cdiv(nh, 256), 256, 0, ctx->stream>>>(ctx->d_params + l.Wh, c.H, s->NCH, s->KSh, s->recur_pairs ? 1 : 0, s->Wh);
     KPRN_LAUNCH_CHECK(ctx);
     ptr_table_kernel<<<(unsigned)(c.V_t * c.V_r), 256, 0, ctx->stream>>>(ctx->d_params, l, c.d_t, c.d_e, c.d_r, c.H, (int)c.V_r, s->G4, s->Ptr);
     KPRN_LAUNCH_CHECK(ctx);
@@ -1254,7 +1347,24 @@ static int tc_pack(kprn_ctx* ctx) {
 }
 
 static size_t proj_smem(int KE, int NOH) { return (size_t)(KE / 8 + 8 * NOH) * 2048 + (size_t)(KE / 8) * 2048 + PROJ_RING * B_SLAB_ELEMS * 2 + 512; }
-static size_t recur_smem(int Hp) { return (size_t)2 * TILE_M * Hp * 2 + RECUR_RING * B_SLAB_ELEMS * 2 + 384; }
+static size_t recur_smem(int Hp, bool pair) {
+    return (size_t)2 * TILE_M * Hp * 2 + (pair ? (size_t)RECUR_RING_PAIR * B_SLAB_ELEMS : (size_t)RECUR_RING * B_SLAB_ELEMS * 2) + RECUR_BAR_BYTES;
+}
+template <int HP, bool PAIR>
+static cudaError_t launch_recur(const RecurArgs& a, int64_t grid, cudaStream_t stream) {
+    static bool attr_set = false;   // per instantiation
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(recur_kernel<HP, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)recur_smem(HP, PAIR));
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(RECUR_THREADS); cfg.dynamicSmemBytes = recur_smem(HP, PAIR); cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = PAIR ? 2 : 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, recur_kernel<HP, PAIR>, a);
+}
 
 int tc_forward(kprn_ctx* ctx, const int32_t* d_ids, const int32_t* d_seg, int64_t N, int64_t S, bool train) {
     const kprn_config& c = ctx->cfg;
@@ -1271,6 +1381,7 @@ int tc_forward(kprn_ctx* ctx, const int32_t* d_ids, const int32_t* d_seg, int64_
         { const char* d = getenv("KPRN_TC_DEBUG"); s->debug = d && d[0] == '1'; }
         { const char* d = getenv("KPRN_TC_PAIRS"); s->use_pairs = !(d && d[0] == '0'); }
         { const char* d = getenv("KPRN_TC_GATHER4"); s->use_gather4 = !(d && d[0] == '0'); }
+        { const char* d = getenv("KPRN_TC_RECUR_PAIRS"); s->recur_pairs = !(d && d[0] == '0'); }
         if (prop.major != 10) { set_error("tensor-core path needs sm_100 (found sm_%d%d)", prop.major, prop.minor); return KPRN_ECUDA; }
     }
     TcState* s = ctx->tc;
@@ -1278,9 +1389,6 @@ int tc_forward(kprn_ctx* ctx, const int32_t* d_ids, const int32_t* d_seg, int64_
         KPRN_CUDA(cudaFuncSetAttribute(proj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)proj_smem(s->KE, s->NOH)));
         KPRN_CUDA(cudaFuncSetAttribute(proj2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)proj_smem(s->KE, s->NOH)));
         KPRN_CUDA(cudaFuncSetAttribute(proj3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)proj_smem(s->KE, s->NOH)));
-        KPRN_CUDA(cudaFuncSetAttribute(recur_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)recur_smem(64)));
-        KPRN_CUDA(cudaFuncSetAttribute(recur_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)recur_smem(128)));
-        KPRN_CUDA(cudaFuncSetAttribute(recur_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)recur_smem(256)));
         s->attrs_set = true;
     }
     KPRN_TRY(tc_pack(ctx));
@@ -1317,16 +1425,22 @@ int tc_forward(kprn_ctx* ctx, const int32_t* d_ids, const int32_t* d_seg, int64_
     {
         RecurArgs a;
         int64_t grid_r = ptiles < s->num_sms ? ptiles : s->num_sms;
+        if (s->recur_pairs) { const int64_t tp = (ptiles + 1) / 2; grid_r = 2 * (tp < s->num_sms / 2 ? tp : s->num_sms / 2); }
         KPRN_TRY(ensure(s->hscratch, (size_t)grid_r * 2 * TILE_M * s->Hp * 2));
         a.XW = s->xw.as<float>(); a.W = s->Wh; a.hT = s->hT.as<float>(); a.hscratch = s->hscratch.as<bf16>(); a.N = N; a.T = c.T; a.H = c.H; a.G4 = s->G4;
         a.num_tiles = ptiles; a.passes = passes; a.dbg = dbg ? dbg + 16 : nullptr;
 
-        int64_t grid = ptiles < s->num_sms ? ptiles : s->num_sms;
         cudaEvent_t e0;
         KPRN_TRY(prof_begin(ctx, &e0));
-        if (s->Hp == 64) recur_kernel<64><<<(unsigned)grid, RECUR_THREADS, recur_smem(64), ctx->stream>>>(a);
-        else if (s->Hp == 128) recur_kernel<128><<<(unsigned)grid, RECUR_THREADS, recur_smem(128), ctx->stream>>>(a);
-        else recur_kernel<256><<<(unsigned)grid, RECUR_THREADS, recur_smem(256), ctx->stream>>>(a);
+        if (s->recur_pairs) {     // a single tile is computed by both CTAs of the one pair
+            if (s->Hp == 64) KPRN_CUDA((launch_recur<64, true>(a, grid_r, ctx->stream)));
+            else if (s->Hp == 128) KPRN_CUDA((launch_recur<128, true>(a, grid_r, ctx->stream)));
+            else KPRN_CUDA((launch_recur<256, true>(a, grid_r, ctx->stream)));
+        } else {
+            if (s->Hp == 64) KPRN_CUDA((launch_recur<64, false>(a, grid_r, ctx->stream)));
+            else if (s->Hp == 128) KPRN_CUDA((launch_recur<128, false>(a, grid_r, ctx->stream)));
+            else KPRN_CUDA((launch_recur<256, false>(a, grid_r, ctx->stream)));
+        }
         KPRN_LAUNCH_CHECK(ctx);
         KPRN_TRY(prof_end(ctx, e0, 2));
     }

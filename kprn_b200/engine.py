@@ -8,7 +8,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libkprn_b200.so")
+LIB_PATH = os.environ.get("KPRN_B200_LIB") or os.path.join(_HERE, "libkprn_b200.so")   # same override as the Lua shim
 
 CELL_LSTM, CELL_RNN = 0, 1
 POOL_LSE, POOL_MAX, POOL_TOPK = 0, 1, 2

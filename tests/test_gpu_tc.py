@@ -24,6 +24,27 @@ TC_CASES = [
 ]
 
 
+# shapes outside the fused kernels (H or d_e > 256, Elman cell): the generic engine with its products on tcgen05 (tc_gemm)
+GENERIC_TC_CASES = [
+    dict(N=300, seed=15, d_t=8, d_e=512, d_r=8, H=512, V_e=800),                    # BASELINE configs[4], d = 512
+    dict(N=300, seed=16, d_t=8, d_e=320, d_r=8, H=128, V_e=800),                    # only the entity width is too large
+    dict(N=400, seed=17, d_t=16, d_e=128, d_r=16, H=128, V_e=800, cell=1),          # Elman ReLU + MaskZero
+]
+
+
+@pytest.mark.parametrize("kw", GENERIC_TC_CASES)
+def test_generic_engine_on_tensor_cores_matches_oracle(kw):
+    o, params, ids, seg, labels = make_case(**kw)
+    ref = o.forward(params, ids, seg)
+    e = engine_for(o, precision=1)
+    e.set_params(params)
+    scores, logits = e.forward(ids, seg, want_logits=True)
+    assert_rel(e.path_logits(ids.shape[0]), ref["path_logits"], what="path_logits")
+    assert_rel(scores, ref["scores"], what="scores")
+    assert_rel(e.forward(ids, seg), ref["scores"], what="scores-only path")
+    e.close()
+
+
 @pytest.mark.parametrize("kw", TC_CASES)
 def test_tc_forward_matches_oracle(kw):
     o, params, ids, seg, labels = make_case(**kw)
