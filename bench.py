@@ -167,7 +167,7 @@ def workload_config(d, n_paths, gpus):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture (profiles/), bytes
-TRAFFIC = {"proj": 1.781e9, "recur": 1.871e9}   # profiles/r01_v4_summary.md (proj3_kernel, recur_kernel<256>)
+TRAFFIC = {"proj": 1.774e9, "recur": 1.885e9}   # dram read + write per launch, profiles/r01_v5_summary.md (proj3_kernel, recur_kernel<256, pair>)
 
 
 def main():
@@ -336,7 +336,7 @@ def main():
                 "note": "achieved = algorithmic flops / CUDA-event launch time; the tensor cores execute %dx the hoisted flops "
                         "(bf16 hi/lo split) so frac <= ~0.45 in this mode even at 100%% tensor-pipe utilisation" % mult}
         if dom:
-            roof.update({"kernel": {"proj": "proj3_kernel (x-projection, TMA gather4 + cta_group::2)", "recur": "recur_kernel<256> (recurrence)"}.get(dom, dom), "achieved": kern[dom]["achieved_tflops"],
+            roof.update({"kernel": {"proj": "proj3_kernel (x-projection, TMA gather4 + cta_group::2)", "recur": "recur_kernel<256, pair> (recurrence, cta_group::2)"}.get(dom, dom), "achieved": kern[dom]["achieved_tflops"],
                          "frac": kern[dom]["achieved_tflops"] / peak, "launch_ms": kern[dom]["launch_ms"],
                          "share_of_step": kern[dom]["launch_ms"] / ms_per_step})
         if "gate_phase" in kern:

@@ -1425,7 +1425,10 @@ int tc_forward(kprn_ctx* ctx, const int32_t* d_ids, const int32_t* d_seg, int64_
     {
         RecurArgs a;
         int64_t grid_r = ptiles < s->num_sms ? ptiles : s->num_sms;
-        if (s->recur_pairs) { const int64_t tp = (ptiles + 1) / 2; grid_r = 2 * (tp < s->num_sms / 2 ? tp : s->num_sms / 2); }
+        int sms_r = s->num_sms;
+        { const char* d = getenv("KPRN_TC_RECUR_SMS"); if (d && atoi(d) >= 2 && atoi(d) <= s->num_sms) sms_r = atoi(d); }   // experiment knob
+        if (grid_r > sms_r) grid_r = sms_r;
+        if (s->recur_pairs) { const int64_t tp = (ptiles + 1) / 2; grid_r = 2 * (tp < sms_r / 2 ? tp : sms_r / 2); }
         KPRN_TRY(ensure(s->hscratch, (size_t)grid_r * 2 * TILE_M * s->Hp * 2));
         a.XW = s->xw.as<float>(); a.W = s->Wh; a.hT = s->hT.as<float>(); a.hscratch = s->hscratch.as<bf16>(); a.N = N; a.T = c.T; a.H = c.H; a.G4 = s->G4;
         a.num_tiles = ptiles; a.passes = passes; a.dbg = dbg ? dbg + 16 : nullptr;

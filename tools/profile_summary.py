@@ -31,7 +31,10 @@ if rep:
             "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
             "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "launch__registers_per_thread", "sm__warps_active.avg.pct_of_peak_sustained_active",
             "launch__grid_size", "launch__block_size", "smsp__cycles_active.avg", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
-            "lts__t_bytes.sum", "l1tex__t_bytes.sum", "smsp__inst_executed.sum", "sm__cycles_elapsed.max"]
+            "lts__t_bytes.sum", "l1tex__t_bytes.sum", "smsp__inst_executed.sum", "sm__cycles_elapsed.max",
+            "lts__t_sectors.sum", "lts__t_sectors_srcunit_tex.sum", "lts__cycles_elapsed.avg", "l1tex__m_xbar2l1tex_read_bytes.sum",
+            "l1tex__m_l1tex2xbar_write_bytes.sum", "l1tex__m_xbar2l1tex_read_bytes_mem_global_op_tma_ld.sum",
+            "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active"]
     out.write("\n## `ncu --set full` capture (one launch per kernel)\n\n| metric | unit | " + " | ".join(r[h.index("Kernel Name")].split("(")[0][:24] for r in rr[2:]) + " |\n")
     out.write("|---|---|" + "---|" * len(rr[2:]) + "\n")
     for i, name in enumerate(h):
