@@ -110,6 +110,8 @@ def cpu_port_throughput(d, budget_s=15.0, threads=None):
     """Times the fp64 CPU restatement (oracle port) on a bounded sample of the same workload."""
     from kprn_b200 import synth
     from oracle.kprn_oracle import Oracle
+    # all host cores this process may run on, whatever OMP_NUM_THREADS says (torchrun sets it to 1 for every rank)
+    Oracle.set_num_threads(threads or len(os.sched_getaffinity(0)))
     ids_all = synth.make_paths(N_PATHS, T=T, V_e=V_E, seed=12345)
     # compact the entity table to the rows this sample touches (same arithmetic, bounded host memory)
     def run(n):

@@ -85,6 +85,15 @@ int okprn_num_threads(void) {
 #endif
 }
 
+/* torchrun exports OMP_NUM_THREADS=1 to every rank: the timed CPU baseline sets its thread count explicitly */
+void okprn_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 static inline double sigm(double x) { return 1.0 / (1.0 + exp(-x)); }
 
 /* C[m][n] (+)= sum_k A[m][k] * B[n][k]   (y = x W^T, nn.Linear semantics: W is [out,in]) */

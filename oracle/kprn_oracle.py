@@ -168,3 +168,8 @@ class Oracle:
     @staticmethod
     def num_threads():
         return int(lib().okprn_num_threads())
+
+    @staticmethod
+    def set_num_threads(n):
+        """OpenMP threads of the C restatement (torchrun exports OMP_NUM_THREADS=1; bench.py's CPU arm asks for all host cores)."""
+        lib().okprn_set_num_threads(int(n))
