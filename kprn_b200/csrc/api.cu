@@ -231,6 +231,7 @@ static int forward_device_impl(kprn_ctx* ctx, const int32_t* d_ids, const int32_
     ctx->have_loss_grad = false;
     // scores-only fast path: nothing downstream of nn.Select(2,classId) needs the other L-1 columns
     ctx->cls_only = !train && !want_logits && c.head_layers == 1;
+    ctx->head_part4 = nullptr;      // set by the fused tensor-core forward when it leaves the head to the pool kernel
     bool use_tc = c.precision != KPRN_PREC_FP32 && tc_supported(ctx);
     // shapes the fused kernels do not cover (H or d_e > 256, Elman cell, large type x relation product): the generic
     // engine runs, with its large products on tcgen05 (bf16x3) for scoring; TC_SPLIT training stays on fp32 FFMA

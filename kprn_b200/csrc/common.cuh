@@ -42,6 +42,8 @@ struct kprn_ctx {
     bool have_fwd = false, have_train_cache = false, have_loss_grad = false;
     bool ids_on_host_copy = false;
     bool cls_only = false;          // last forward materialised only the class column (scores-only fast path)
+    const float* head_part4 = nullptr;   // scores-only tensor-core forward: [4][head_npad] partial head dot products (else null)
+    int64_t head_npad = 0;
     bool gemm_on_tc = false;        // scoring forward of a shape the fused tensor-core kernels do not cover: products via tc_gemm
     const int32_t* d_ids = nullptr;      // ids of the last forward (ctx-owned copy or caller's device ptr)
     const int32_t* d_seg = nullptr;

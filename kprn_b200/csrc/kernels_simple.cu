@@ -227,32 +227,39 @@ __global__ void pool_fwd_kernel(const float* __restrict__ s, const int32_t* __re
     }
 }
 
-// Scores-only LSE pool: a warp-shuffle segmented reduction keyed by the (user,item) segment -- one warp per segment, lanes
-// stride over the segment's paths keeping an online (max, sum-exp) pair, merged across lanes with a shuffle butterfly.
+// Scores-only LSE pool: a warp-shuffle segmented reduction keyed by the (user,item) segment.  G lanes per segment (G = 32: one
+// warp per segment; G = 4: eight segments per warp, for batches whose segments hold a few paths each): the lanes stride over the
+// segment's paths keeping an online (max, sum-exp) pair, merged across the group with a shuffle butterfly.
 // Same math as LogSumExp.lua:13-30 for column classId, then nn.Sigmoid (OneModel.lua:294).
-__global__ void pool_lse_cls_warp_kernel(const float* __restrict__ s, const int32_t* __restrict__ seg, int64_t S, int L, float ig,
-                                         int cls, float* __restrict__ seg_logits, float* __restrict__ scores,
+// Path logit p = s[p*stride + col], or -- after the fused tensor-core forward -- bias + the four partial dot products
+// part4[g*npad + p] that the recurrence's epilogue groups left (summed in a fixed order: deterministic).
+template <int G>
+__global__ void pool_lse_cls_warp_kernel(const float* __restrict__ s, int64_t stride, int col, const float* __restrict__ part4,
+                                         int64_t npad, const float* __restrict__ bias, const int32_t* __restrict__ seg, int64_t S, int L,
+                                         float ig, int cls, float* __restrict__ seg_logits, float* __restrict__ scores,
                                          float* __restrict__ out_scores) {
-    const int64_t k = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (k >= S) return;
-    const int lane = threadIdx.x & 31;
-    const int64_t a = seg[k], b = seg[k + 1];
+    const int64_t k = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const int lane = threadIdx.x & (G - 1);
+    const bool live = k < S;                      // whole groups are live or not; dead groups still take part in the shuffles
+    const int64_t a = live ? seg[k] : 0, b = live ? seg[k + 1] : 0;
+    const float b0 = part4 ? *bias : 0.f;
     float m = -INFINITY, z = 0.f;
-    for (int64_t p = a + lane; p < b; p += 32) {
-        const float v = s[p * L + cls] * ig;
+    for (int64_t p = a + lane; p < b; p += G) {
+        const float raw = part4 ? ((part4[p] + part4[npad + p]) + (part4[2 * npad + p] + part4[3 * npad + p])) + b0 : s[p * stride + col];
+        const float v = raw * ig;
         const float nm = fmaxf(m, v);
         z = z * expf(m - nm) + expf(v - nm);      // exp(-inf) = 0 on the first element
         m = nm;
     }
 #pragma unroll
-    for (int o = 16; o; o >>= 1) {
+    for (int o = G / 2; o; o >>= 1) {
         const float om = __shfl_xor_sync(0xffffffffu, m, o), oz = __shfl_xor_sync(0xffffffffu, z, o);
         const float nm = fmaxf(m, om);
         const float za = (m == -INFINITY) ? 0.f : z * expf(m - nm), zb = (om == -INFINITY) ? 0.f : oz * expf(om - nm);
         z = za + zb;
         m = nm;
     }
-    if (lane == 0) {
+    if (live && lane == 0) {
         const float out = (b > a) ? (m + logf(z)) / ig : 0.f;
         seg_logits[k * L + cls] = out;
         const float pr = sigmoidf_(out);
@@ -267,9 +274,18 @@ int pool_forward(kprn_ctx* ctx, const int32_t* d_seg, int64_t S, float* d_out_sc
     KPRN_TRY(ensure(ctx->scores, sizeof(float) * S));
     float ig = c.inv_gamma == 0.f ? 1.f : c.inv_gamma;
     if (ctx->cls_only && c.pool == KPRN_POOL_LSE) {
-        pool_lse_cls_warp_kernel<<<(unsigned)cdiv(S, 8), 256, 0, ctx->stream>>>(ctx->path_logits.as<float>(), d_seg, S, c.L, ig,
-                                                                              c.class_id - 1, ctx->seg_logits.as<float>(),
-                                                                              ctx->scores.as<float>(), d_out_scores);
+        const float* part4 = ctx->head_part4;
+        const float* bias = ctx->d_params + ctx->lay.bo + (c.class_id - 1);
+        const float* pl = ctx->path_logits.as<float>();
+        if (ctx->N <= 6 * S) {       // a few paths per (user,item) pair: 4 lanes per segment
+            pool_lse_cls_warp_kernel<4><<<(unsigned)cdiv(S * 4, 256), 256, 0, ctx->stream>>>(
+                pl, c.L, c.class_id - 1, part4, ctx->head_npad, bias, d_seg, S, c.L, ig, c.class_id - 1, ctx->seg_logits.as<float>(),
+                ctx->scores.as<float>(), d_out_scores);
+        } else {
+            pool_lse_cls_warp_kernel<32><<<(unsigned)cdiv(S * 32, 256), 256, 0, ctx->stream>>>(
+                pl, c.L, c.class_id - 1, part4, ctx->head_npad, bias, d_seg, S, c.L, ig, c.class_id - 1, ctx->seg_logits.as<float>(),
+                ctx->scores.as<float>(), d_out_scores);
+        }
         KPRN_LAUNCH_CHECK(ctx);
         return KPRN_OK;
     }

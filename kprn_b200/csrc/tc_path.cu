@@ -55,7 +55,7 @@ struct TcState {
     bf16* E_hi = nullptr; bf16* E_lo = nullptr;
     bf16* WxE = nullptr; bf16* Wh = nullptr;
     float* Ptr = nullptr;
-    DBuf xw, hT, hscratch, dbg;
+    DBuf xw, hT, hscratch, dbg, part4;
     bool debug = false;
     bool use_gather4 = true;   // TMA tile::gather4 for the entity rows (KPRN_TC_GATHER4=0 -> LDGSTS gather of proj2)
     bool have_tmaps = false;
@@ -924,6 +924,9 @@ proj3_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ 
 struct RecurArgs {
     const float* XW; const bf16* W; float* hT; bf16* hscratch; int64_t N; int T; int H; int G4; int64_t num_tiles; int passes;
     unsigned long long* dbg;
+    // scores-only path (A5 fused): row classId of the head weight and the [4][npad] partial dot products h_T . wo, one per epilogue
+    // group; null = write h_T for the head kernels instead
+    const float* wo; float* part4; int64_t npad;
 };
 
 __device__ __forceinline__ float ex2f(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -1156,6 +1159,7 @@ __global__ void __launch_bounds__(RECUR_THREADS, 1) recur_kernel(RecurArgs a) {
         const int64_t tile_xw = (int64_t)(a.G4 / 4) * TILE_M * 4;  // floats per tile-step
         const uint32_t acce_leader = PAIR ? ptx::mapa(BAR(B_ACCE), 0) : BAR(B_ACCE);
         const bool h_vec4 = (a.H & 3) == 0;
+        const bool wo_vec4 = h_vec4 && (reinterpret_cast<uintptr_t>(a.wo) & 15) == 0;    // the flat parameter vector aligns nothing
         uint32_t ug0 = 0, ug1 = 0;
         // XW of (chunk j, this sub-block), gate q: column blocks j*32 + q*8 + 2*sb, +1   (a block = 128 rows x 4 floats)
 #define KPRN_LOAD_XW(dst, base, j)                                                                                    \
@@ -1172,6 +1176,7 @@ __global__ void __launch_bounds__(RECUR_THREADS, 1) recur_kernel(RecurArgs a) {
                 const float* xw_t = a.XW + (pt * T + t) * tile_xw + r * 4;
                 const bool last = (t == T - 1);
                 float xa[32], xb[32];                 // XW of the current / next chunk, ping-pong (no register copies)
+                float dot = 0.f;                      // last step, scores-only: this thread's share of h_T . wo
                 KPRN_LOAD_XW(xa, xw_t, 0)
                 auto chunk = [&](const int j, float (&xc)[32], float (&xn)[32]) {
                     const int g = j & 1;
@@ -1251,6 +1256,19 @@ __global__ void __launch_bounds__(RECUR_THREADS, 1) recur_kernel(RecurArgs a) {
                         *reinterpret_cast<uint4*>(scratch + H_BYTES + kc * 2048 + r * 16) = lo;
                         // publication of these writes (proxy fence + arrive) is deferred by one chunk: by then the
                         // stores have drained and the fence costs nothing (see the top of the lambda / after the loop)
+                    } else if (a.part4) {
+                        // A5 fused (nn.Linear row classId on SelectTable(-1)): partial dot product over this thread's 8 units;
+                        // padded units (>= H) hold h = 0 exactly, their weights are not read
+                        const int u0 = j * 32 + sb * 8;
+                        if (wo_vec4 && u0 + 8 <= a.H) {
+                            const float4 w0 = *reinterpret_cast<const float4*>(a.wo + u0), w1 = *reinterpret_cast<const float4*>(a.wo + u0 + 4);
+                            dot = fmaf(hv[0], w0.x, dot); dot = fmaf(hv[1], w0.y, dot); dot = fmaf(hv[2], w0.z, dot); dot = fmaf(hv[3], w0.w, dot);
+                            dot = fmaf(hv[4], w1.x, dot); dot = fmaf(hv[5], w1.y, dot); dot = fmaf(hv[6], w1.z, dot); dot = fmaf(hv[7], w1.w, dot);
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 8; ++e)
+                                if (u0 + e < a.H) dot = fmaf(hv[e], a.wo[u0 + e], dot);
+                        }
                     } else if (n < a.N) {
                         // SelectTable(-1): last hidden state, standard [N,H] layout for the head
                         float* dst = a.hT + n * a.H + j * 32 + sb * 8;
@@ -1273,6 +1291,7 @@ __global__ void __launch_bounds__(RECUR_THREADS, 1) recur_kernel(RecurArgs a) {
                     asm volatile("fence.proxy.async.global;" ::: "memory");
                     ptx::mbar_arrive(BAR(B_HWRIT + ((NCH - 1) >> 1)));
                 }
+                if (last && a.part4 && n < a.N) a.part4[sb * a.npad + n] = dot;     // summed (fixed order) + bias in the pool kernel
                 ptx::tc_wait_st();        // c_t is read back (tcgen05.ld) by this thread in the next step
             }
         }
@@ -1432,6 +1451,14 @@ int tc_forward(kprn_ctx* ctx, const int32_t* d_ids, const int32_t* d_seg, int64_
         KPRN_TRY(ensure(s->hscratch, (size_t)grid_r * 2 * TILE_M * s->Hp * 2));
         a.XW = s->xw.as<float>(); a.W = s->Wh; a.hT = s->hT.as<float>(); a.hscratch = s->hscratch.as<bf16>(); a.N = N; a.T = c.T; a.H = c.H; a.G4 = s->G4;
         a.num_tiles = ptiles; a.passes = passes; a.dbg = dbg ? dbg + 16 : nullptr;
+        a.wo = nullptr; a.part4 = nullptr; a.npad = ptiles * TILE_M;
+        ctx->head_part4 = nullptr;
+        if (ctx->cls_only && c.pool == KPRN_POOL_LSE) {      // the pool kernel finishes the head: sum of 4 partials + bias
+            KPRN_TRY(ensure(s->part4, sizeof(float) * 4 * (size_t)a.npad));
+            a.part4 = s->part4.as<float>();
+            a.wo = ctx->d_params + ctx->lay.Wo + (int64_t)(c.class_id - 1) * c.H;
+            ctx->head_part4 = a.part4; ctx->head_npad = a.npad;
+        }
 
         cudaEvent_t e0;
         KPRN_TRY(prof_begin(ctx, &e0));
@@ -1460,7 +1487,9 @@ int tc_forward(kprn_ctx* ctx, const int32_t* d_ids, const int32_t* d_seg, int64_
                 h[31] / nr_, h[24] / nr_, h[25] / nr_, h[26] / nr_, h[27] / nr_, h[28] / nr_, h[29] / nr_, h[30] / nr_);
     }
     // A5: head on the last hidden state (fp32 CUDA cores; 0.2 % of the flops)
-    if (ctx->cls_only) {
+    if (ctx->head_part4) {
+        // nothing to launch: see pool_forward
+    } else if (ctx->cls_only) {
         KPRN_TRY(head_forward_cls(ctx, s->hT.as<float>(), c.H, 0, N));
     } else {
         float* z1 = nullptr;

@@ -172,20 +172,26 @@ def test_pinned_host_buffers_give_identical_results():
     e.close()
 
 
-def test_long_and_ragged_segments_warp_shuffle_pool():
-    """Scores-only LSE pool = one warp per segment with a shuffle butterfly: segments of 1, 31, 32, 33, 1000 paths."""
-    o, params, ids, _, _ = make_case(N=1 + 31 + 32 + 33 + 1000 + 7, seed=23)
-    seg = np.cumsum([0, 1, 31, 32, 33, 1000, 7]).astype(np.int32)
+@pytest.mark.parametrize("precision", [0, 1])
+@pytest.mark.parametrize("lens", [[1, 31, 32, 33, 1000, 7], [1, 2, 3, 1, 4, 2, 5, 1, 1, 6, 2, 3, 9, 1, 2] * 9, [0, 3, 0, 0, 5, 1, 0]])
+def test_long_short_and_empty_segments_warp_shuffle_pool(precision, lens):
+    """Scores-only LSE pool = shuffle butterfly over 32 lanes (long segments) or 4 lanes (batches of short segments) per
+    (user,item) pair; with precision 1 the per-path head value comes from the four partial dot products the fused
+    tensor-core forward leaves.  Empty segments (nn.MapReduce never produces one, the CSR form allows it) score sigmoid(0)."""
+    n = int(np.sum(lens))
+    o, params, ids, _, _ = make_case(N=n, seed=23, d_t=8, d_e=64, d_r=8, H=64, V_e=400)
+    seg = np.cumsum([0] + list(lens)).astype(np.int32)
     ref = o.forward(params, ids, seg)
-    for precision in (0, 1):
-        e = engine_for(o, precision=precision) if precision == 0 else None
-        if e is None:
-            continue
-        e.set_params(params)
-        assert_rel(e.forward(ids, seg), ref["scores"], what="scores-only pool")
-        s_full, lg = e.forward(ids, seg, want_logits=True)
-        assert_rel(lg, ref["seg_logits"], what="full pool")
-        e.close()
+    e = engine_for(o, precision=precision)
+    e.set_params(params)
+    got = e.forward(ids, seg)
+    nz = np.array(lens) > 0
+    assert_rel(got[nz], ref["scores"][nz], what="scores-only pool")
+    assert np.all(got[~nz] == 0.5)
+    s_full, lg = e.forward(ids, seg, want_logits=True)
+    assert_rel(lg[nz], ref["seg_logits"][nz], what="full pool")
+    assert_rel(e.forward(ids, seg)[nz], ref["scores"][nz], what="scores-only again after a full forward")
+    e.close()
 
 
 def test_fallback_kernels_still_match():
