@@ -209,6 +209,12 @@ __device__ __forceinline__ uint32_t desc_lo_sw128(uint32_t smem_addr) { return (
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
+// 256-bit global store (sm_100: STG.256): one full 32-byte sector per thread
+__device__ __forceinline__ void stg256(float* p, const float* v) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+}
+
 // ---- packed fp32 pairs (sm_100: add/mul/fma .f32x2 on 64-bit registers = SASS FADD2 / FMUL2 / FFMA2) ----
 __device__ __forceinline__ uint64_t pack2(float a, float b) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
 __device__ __forceinline__ void unpack2(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }

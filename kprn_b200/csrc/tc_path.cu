@@ -56,6 +56,8 @@ struct TcState {
     bf16* WxE = nullptr; bf16* Wh = nullptr;
     float* Ptr = nullptr;
     DBuf xw, hT, hscratch, dbg, part4;
+    DBuf dd_table, dd_slot_of, dd_pos, dd_slot, dd_ids, dd_count;   // step-input deduplication
+    bool dedup = true;         // project each distinct (type, entity, relation) triple once (KPRN_TC_DEDUP=0: every step)
     bool debug = false;
     bool use_gather4 = true;   // TMA tile::gather4 for the entity rows (KPRN_TC_GATHER4=0 -> LDGSTS gather of proj2)
     bool have_tmaps = false;
@@ -191,8 +193,9 @@ __global__ void ptr_table_kernel(const float* __restrict__ P, Layout l, int d_t,
 
 // ---------------------------------------------------------------------------------------------
 // kernel "proj": XW tile (128 path-steps x 4Hp) = [gather(E_e) | onehot(type,rel)] [Wx_e | P_tr]^T on tcgen05.
-// XW layout: [tile m = pathtile*T + t][column block (4Hp/4)][row 128][4 floats], columns in permuted (chunk) order,
-// so that one tile-step is a contiguous 128 x 4Hp x 4 B block and every warp access is a contiguous 512 B.
+// XW layout: [tile][column group (4Hp/8)][row 128][8 floats], columns in permuted (chunk) order; a tile is 128 rows of the
+// projected list (distinct step inputs, or (path tile, t) without deduplication) = one contiguous 128 x 4Hp x 4 B block; every
+// thread access is one 32-byte sector (256-bit LDG / STG), a warp access 1 KB contiguous.
 // Roles: warp 0 TMA producer (weight slabs), warp 1 MMA issuer, warps 2-3 gather (LDGSTS of pre-split entity rows +
 // one-hot slice), warps 4-11 epilogue (TMEM -> global).  4 accumulators of 128 columns; the A tile is released to the
 // gather warps k-slice by k-slice while the last column chunk of the tile is still being multiplied.
@@ -202,9 +205,16 @@ struct ProjArgs {
     const bf16* E_hi; const bf16* E_lo; const bf16* W; float* XW;
     int KE, KSe, NOH, NS, NCH, G4; int64_t num_tiles; int passes;   // passes: 3 = bf16x3, 1 = hi*hi only
     unsigned long long* dbg;   // optional wait-cycle counters (KPRN_TC_DEBUG=1): see tc_debug_dump
+    const int32_t* n_dev;      // when set: the row count lives on the device (distinct step inputs, see dedup below); T is 1
 };
 
+// the projection of a deduplicated step list learns its size on the device (no host round trip): N = *n_dev rows, T = 1
+__device__ __forceinline__ void proj_resolve_size(ProjArgs& a) {
+    if (a.n_dev) { a.N = *a.n_dev; a.num_tiles = (a.N + TILE_M - 1) / TILE_M; }
+}
+
 __global__ void __launch_bounds__(NUM_THREADS, 1) proj_kernel(ProjArgs a) {
+    proj_resolve_size(a);
     extern __shared__ __align__(1024) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int R = PROJ_RING;
@@ -385,7 +395,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) proj_kernel(ProjArgs a) {
             const int nt = (int)(au % a.NCH);
             const int buf = au & 3;
             const int64_t m = blockIdx.x + it * gridDim.x;
-            float* xw = a.XW + ((m * (a.G4 / 4) + nt * 32) * TILE_M + r) * 4;
+            float* xw = a.XW + ((m * (a.G4 / 8) + nt * 16) * TILE_M + r) * 8;
             if (nt == 0 && it + 1 < my_tiles) {
                 // pull the entity rows of the NEXT tile into L2 (one row per thread) so that the gather warps' LDGSTS
                 // see L2 latency instead of HBM latency: the A tile is single-buffered, its refill is on the critical path
@@ -410,8 +420,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) proj_kernel(ProjArgs a) {
                 ptx::tmem_ld32(tbase + blk * 32, v);
                 ptx::tc_wait_ld();
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    *reinterpret_cast<float4*>(xw + (int64_t)(blk * 8 + i) * TILE_M * 4) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                for (int i = 0; i < 4; ++i) ptx::stg256(xw + (int64_t)(blk * 4 + i) * TILE_M * 8, v + 8 * i);     // one 32-byte sector per thread
             }
             ptx::tc_fence_before();
             ptx::mbar_arrive(BAR(B_ACCE + buf));
@@ -438,6 +447,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) proj_kernel(ProjArgs a) {
 // "my half of the slab / my A slice / my accumulator drain" to the leader's barriers with remote mbarrier arrives.
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PROJ2_THREADS, 1) proj2_kernel(ProjArgs a) {
+    proj_resolve_size(a);
     extern __shared__ __align__(1024) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int R = PROJ_RING;
@@ -644,7 +654,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PROJ2_THREADS, 1) pr
             const int np = (int)(au % NP);
             const int buf = au & 1;
             const int64_t m = tile_of(it);
-            float* xw = a.XW + ((m * (a.G4 / 4) + np * 64) * TILE_M + r) * 4;
+            float* xw = a.XW + ((m * (a.G4 / 8) + np * 32) * TILE_M + r) * 8;
             TWAIT(5, BAR(B_ACCF + buf), (au >> 1) & 1);
             ptx::tc_fence_after();
             const uint32_t tbase = tmem + ((uint32_t)(q4 * 32) << 16) + buf * 256;
@@ -654,8 +664,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PROJ2_THREADS, 1) pr
                 ptx::tmem_ld32(tbase + blk * 32, v);
                 ptx::tc_wait_ld();
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    *reinterpret_cast<float4*>(xw + (int64_t)(blk * 8 + i) * TILE_M * 4) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                for (int i = 0; i < 4; ++i) ptx::stg256(xw + (int64_t)(blk * 4 + i) * TILE_M * 8, v + 8 * i);     // one 32-byte sector per thread
             }
             ptx::tc_fence_before();
             __syncwarp();
@@ -682,6 +691,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PROJ2_THREADS, 1) pr
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 proj3_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo, ProjArgs a) {
+    proj_resolve_size(a);
     extern __shared__ __align__(1024) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int R = PROJ_RING;
@@ -882,7 +892,7 @@ proj3_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ 
             const int np = (int)(au % NP);
             const int buf = au & 1;
             const int64_t m = tile_of(it);
-            float* xw = a.XW + ((m * (a.G4 / 4) + np * 64) * TILE_M + r) * 4;
+            float* xw = a.XW + ((m * (a.G4 / 8) + np * 32) * TILE_M + r) * 8;
             TWAIT(5, BAR(B_ACCF + buf), (au >> 1) & 1);
             ptx::tc_fence_after();
             const uint32_t tbase = tmem + ((uint32_t)(q4 * 32) << 16) + buf * 256;
@@ -892,8 +902,7 @@ proj3_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ 
                 ptx::tmem_ld32(tbase + blk * 32, v);
                 ptx::tc_wait_ld();
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    *reinterpret_cast<float4*>(xw + (int64_t)(blk * 8 + i) * TILE_M * 4) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                for (int i = 0; i < 4; ++i) ptx::stg256(xw + (int64_t)(blk * 4 + i) * TILE_M * 8, v + 8 * i);     // one 32-byte sector per thread
             }
             ptx::tc_fence_before();
             __syncwarp();
@@ -927,6 +936,9 @@ struct RecurArgs {
     // scores-only path (A5 fused): row classId of the head weight and the [4][npad] partial dot products h_T . wo, one per epilogue
     // group; null = write h_T for the head kernels instead
     const float* wo; float* part4; int64_t npad;
+    // XW row of (path n, step t) = slot[n*T + t] (a row index into the projection of the DISTINCT step inputs); null = n's own
+    // row (tile (n/128)*T + t, row n%128)
+    const int32_t* slot;
 };
 
 __device__ __forceinline__ float ex2f(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -1161,19 +1173,28 @@ __global__ void __launch_bounds__(RECUR_THREADS, 1) recur_kernel(RecurArgs a) {
         const bool h_vec4 = (a.H & 3) == 0;
         const bool wo_vec4 = h_vec4 && (reinterpret_cast<uintptr_t>(a.wo) & 15) == 0;    // the flat parameter vector aligns nothing
         uint32_t ug0 = 0, ug1 = 0;
-        // XW of (chunk j, this sub-block), gate q: column blocks j*32 + q*8 + 2*sb, +1   (a block = 128 rows x 4 floats)
+        // XW of (chunk j, this sub-block), gate q: the 8 columns j*128 + q*32 + sb*8 .. +7 = column group j*16 + q*4 + sb.
+        // XW layout [tile][column group (4Hp/8)][row 128][8 floats]: the two 128-bit loads of a thread share one 32-byte sector
+        // (a single 256-bit load measured 4 % slower here; the projection's 256-bit stores are fine).
 #define KPRN_LOAD_XW(dst, base, j)                                                                                    \
     _Pragma("unroll") for (int q = 0; q < 4; ++q) {                                                                  \
-        const float4 x0 = *reinterpret_cast<const float4*>((base) + (int64_t)((j) * 32 + q * 8 + 2 * sb) * TILE_M * 4);     \
-        const float4 x1 = *reinterpret_cast<const float4*>((base) + (int64_t)((j) * 32 + q * 8 + 2 * sb + 1) * TILE_M * 4); \
+        const float4 x0 = *reinterpret_cast<const float4*>((base) + (int64_t)((j) * 16 + q * 4 + sb) * TILE_M * 8);     \
+        const float4 x1 = *reinterpret_cast<const float4*>((base) + (int64_t)((j) * 16 + q * 4 + sb) * TILE_M * 8 + 4); \
         dst[q * 8 + 0] = x0.x; dst[q * 8 + 1] = x0.y; dst[q * 8 + 2] = x0.z; dst[q * 8 + 3] = x0.w;                   \
         dst[q * 8 + 4] = x1.x; dst[q * 8 + 5] = x1.y; dst[q * 8 + 6] = x1.z; dst[q * 8 + 7] = x1.w;                   \
     }
         for (int64_t it = 0; it < my_tiles; ++it) {
             const int64_t pt = tile_of(it);
             const int64_t n = pt * TILE_M + r;
+            const int64_t nc = n < a.N ? n : a.N - 1;                     // ragged last tile: any valid row
+            int32_t slot_next = a.slot ? a.slot[nc * T] : 0;
             for (int t = 0; t < T; ++t) {
-                const float* xw_t = a.XW + (pt * T + t) * tile_xw + r * 4;
+                const int32_t slot = slot_next;
+                if (a.slot && t + 1 < T) slot_next = a.slot[nc * T + t + 1];   // next step's row index, in flight during this step
+                // rows are numbered in the order the recurrence reads them (see the dedup kernels): the first occurrences inside a
+                // warp are consecutive rows of one tile, repeated triples (pad steps, a pair's shared user / item) share a row
+                const float* xw_t = a.slot ? a.XW + (int64_t)(slot >> 7) * tile_xw + (slot & 127) * 8
+                                           : a.XW + (pt * T + t) * tile_xw + r * 8;
                 const bool last = (t == T - 1);
                 float xa[32], xb[32];                 // XW of the current / next chunk, ping-pong (no register copies)
                 float dot = 0.f;                      // last step, scores-only: this thread's share of h_T . wo
@@ -1309,6 +1330,143 @@ __global__ void __launch_bounds__(RECUR_THREADS, 1) recur_kernel(RecurArgs a) {
     if (warp == 2) { if (PAIR) ptx::tmem_dealloc2(tmem, 512); else ptx::tmem_dealloc(tmem, 512); }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Step-input deduplication.  The projection x_t Wx^T + bx depends only on the (type, entity, relation) triple of a step,
+// and a batch repeats triples heavily: every left-pad step is the same triple, all paths of a (user,item) pair start at
+// the same user and end at the same item, popular entities recur (55 % distinct in the synthetic bench batches, fewer in
+// mined paths).  So the projection runs once per DISTINCT triple and the recurrence reads its XW rows through a
+// row-index map.  Rows are numbered by FIRST OCCURRENCE IN THE ORDER THE RECURRENCE READS THEM -- o = ((tile*T + t)*128 + r)
+// for path n = tile*128 + r, step t -- so the first occurrences inside one warp load are consecutive rows (coalesced as
+// before) and repeats inside a warp hit the same sector.  Open-addressing hash table (64-bit keys, linear probing) with an
+// atomicMin of o per key, a two-level prefix sum over the first-occurrence flags, no host round trip: the projection
+// kernels read the distinct count from device memory.  Everything (row numbering included) is deterministic.
+constexpr unsigned long long DEDUP_EMPTY = ~0ull;
+constexpr int DEDUP_BLOCK = 1024;          // read-order indices per block of the flag scan
+
+__device__ __forceinline__ uint32_t dedup_hash(unsigned long long k, uint32_t mask) {
+    k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
+    return (uint32_t)k & mask;
+}
+// read-order index o -> flat step index (n*T + t), or -1 for the rows of a ragged last tile
+__device__ __forceinline__ int64_t dedup_step_of(int64_t o, int64_t N, int T) {
+    const int64_t tile_t = o >> 7, tile = tile_t / T;
+    const int64_t n = tile * TILE_M + (o & 127);
+    return n < N ? n * T + (tile_t - tile * T) : -1;
+}
+
+// pos[o] = table position of the triple read at o; first[pos] = min o over its occurrences.  Equal triples inside a warp
+// (a pad column of a tile is one triple) elect one lane; a plain load before the CAS keeps hot keys from serialising.
+__global__ void dedup_insert_kernel(const int32_t* __restrict__ ids, int64_t n_order, int64_t N, int T, int64_t V_t, int64_t V_e,
+                                    int64_t V_r, unsigned long long* table, uint32_t* first, uint32_t mask, uint32_t* __restrict__ pos) {
+    const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t i = o < n_order ? dedup_step_of(o, N, T) : -1;
+    const bool active = i >= 0;
+    unsigned long long key = DEDUP_EMPTY;
+    if (active) {
+        int64_t ta = (int64_t)ids[i * 3] - 1, en = (int64_t)ids[i * 3 + 1] - 1, rb = (int64_t)ids[i * 3 + 2] - 1;
+        ta = ta < 0 ? 0 : (ta >= V_t ? V_t - 1 : ta);
+        en = en < 0 ? 0 : (en >= V_e ? V_e - 1 : en);
+        rb = rb < 0 ? 0 : (rb >= V_r ? V_r - 1 : rb);
+        key = ((unsigned long long)en * (unsigned long long)V_t + (unsigned long long)ta) * (unsigned long long)V_r + (unsigned long long)rb;
+    }
+    const unsigned peers = __match_any_sync(0xffffffffu, key);
+    const int leader = __ffs(peers) - 1;           // lowest lane = lowest o of the group
+    uint32_t p = 0;
+    if ((int)(threadIdx.x & 31) == leader && active) {
+        uint32_t h = dedup_hash(key, mask);
+        for (;;) {
+            unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(table + h);
+            if (cur == DEDUP_EMPTY) cur = atomicCAS(table + h, DEDUP_EMPTY, key);
+            if (cur == DEDUP_EMPTY || cur == key) break;
+            h = (h + 1) & mask;
+        }
+        p = h;
+        if (*reinterpret_cast<volatile uint32_t*>(first + p) > (uint32_t)o) atomicMin(first + p, (uint32_t)o);
+    }
+    p = __shfl_sync(0xffffffffu, p, leader);
+    if (o < n_order) pos[o] = active ? p : 0xFFFFFFFFu;
+}
+
+// block-wide exclusive scan of one flag per thread x 4 (256 threads): returns this thread's exclusive offset, total in *tot
+__device__ __forceinline__ int dedup_block_scan(int c, int* tot) {
+    __shared__ int warp_tot[8];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+    if (lane == 31) warp_tot[w] = incl;
+    __syncthreads();
+    int off = 0, t = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { if (j < w) off += warp_tot[j]; t += warp_tot[j]; }
+    __syncthreads();
+    *tot = t;
+    return off + incl - c;
+}
+__device__ __forceinline__ int dedup_flags(const uint32_t* __restrict__ pos, const uint32_t* __restrict__ first, int64_t n_order,
+                                           int64_t o0, bool (&f)[4]) {
+    int c = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int64_t o = o0 + j;
+        const uint32_t p = o < n_order ? pos[o] : 0xFFFFFFFFu;
+        f[j] = p != 0xFFFFFFFFu && first[p] == (uint32_t)o;
+        c += f[j];
+    }
+    return c;
+}
+__global__ void dedup_blocksum_kernel(const uint32_t* __restrict__ pos, const uint32_t* __restrict__ first, int64_t n_order, int32_t* __restrict__ bsum) {
+    bool f[4];
+    int tot;
+    const int c = dedup_flags(pos, first, n_order, ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4, f);
+    dedup_block_scan(c, &tot);
+    if (threadIdx.x == 0) bsum[blockIdx.x] = tot;
+}
+// one block: exclusive scan of the block sums in place, total = number of distinct triples
+__global__ void dedup_scan_sums_kernel(int32_t* bsum, int nb, int32_t* __restrict__ count) {
+    __shared__ int carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int b0 = 0; b0 < nb; b0 += 256) {
+        const int b = b0 + threadIdx.x;
+        const int v = b < nb ? bsum[b] : 0;
+        int tot;
+        const int ex = dedup_block_scan(v, &tot);
+        const int carry = carry_s;
+        if (b < nb) bsum[b] = carry + ex;
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s = carry + tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *count = carry_s;
+}
+// rank of every first occurrence = its row; the first-occurrence thread records it for its key and writes the triple
+__global__ void dedup_assign_kernel(const int32_t* __restrict__ ids, const uint32_t* __restrict__ pos, const uint32_t* __restrict__ first,
+                                    int64_t n_order, int64_t N, int T, const int32_t* __restrict__ boff, uint32_t* __restrict__ slot_of,
+                                    int32_t* __restrict__ ids_d) {
+    bool f[4];
+    int tot;
+    const int64_t o0 = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4;
+    const int c = dedup_flags(pos, first, n_order, o0, f);
+    int row = boff[blockIdx.x] + dedup_block_scan(c, &tot);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        if (f[j]) {
+            const int64_t i = dedup_step_of(o0 + j, N, T);
+            slot_of[pos[o0 + j]] = (uint32_t)row;
+            ids_d[(int64_t)row * 3] = ids[i * 3]; ids_d[(int64_t)row * 3 + 1] = ids[i * 3 + 1]; ids_d[(int64_t)row * 3 + 2] = ids[i * 3 + 2];
+            ++row;
+        }
+}
+__global__ void dedup_map_kernel(const uint32_t* __restrict__ pos, const uint32_t* __restrict__ slot_of, int64_t n_order, int64_t N, int T,
+                                 int32_t* __restrict__ slot) {
+    const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= n_order) return;
+    const int64_t i = dedup_step_of(o, N, T);
+    if (i >= 0) slot[i] = (int32_t)slot_of[pos[o]];
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 
@@ -1401,6 +1559,7 @@ int tc_forward(kprn_ctx* ctx, const int32_t* d_ids, const int32_t* d_seg, int64_
         { const char* d = getenv("KPRN_TC_PAIRS"); s->use_pairs = !(d && d[0] == '0'); }
         { const char* d = getenv("KPRN_TC_GATHER4"); s->use_gather4 = !(d && d[0] == '0'); }
         { const char* d = getenv("KPRN_TC_RECUR_PAIRS"); s->recur_pairs = !(d && d[0] == '0'); }
+        { const char* d = getenv("KPRN_TC_DEDUP"); s->dedup = !(d && d[0] == '0'); }
         if (prop.major != 10) { set_error("tensor-core path needs sm_100 (found sm_%d%d)", prop.major, prop.minor); return KPRN_ECUDA; }
     }
     TcState* s = ctx->tc;
@@ -1427,9 +1586,42 @@ int tc_forward(kprn_ctx* ctx, const int32_t* d_ids, const int32_t* d_seg, int64_
         a.ids = d_ids; a.N = N; a.T = c.T; a.V_e = c.V_e; a.V_t = (int)c.V_t; a.V_r = (int)c.V_r;
         a.E_hi = s->E_hi; a.E_lo = s->E_lo; a.W = s->WxE; a.XW = s->xw.as<float>();
         a.KE = s->KE; a.KSe = s->KSe; a.NOH = s->NOH; a.NS = s->NS; a.NCH = s->NCH; a.G4 = s->G4; a.num_tiles = ptiles * c.T; a.passes = passes; a.dbg = dbg;
-        int64_t grid = a.num_tiles < s->num_sms ? a.num_tiles : s->num_sms;
+        a.n_dev = nullptr;
         cudaEvent_t e0;
         KPRN_TRY(prof_begin(ctx, &e0));
+        const int64_t n_steps = N * c.T, n_order = ptiles * c.T * TILE_M;       // n_order: read-order indices incl. the ragged tail
+        if (s->dedup && n_order < (1ll << 30)) {
+            uint32_t M = 1024;
+            while ((int64_t)M < 2 * n_steps) M <<= 1;
+            const int nb = (int)cdiv(n_order, DEDUP_BLOCK);
+            KPRN_TRY(ensure(s->dd_table, (sizeof(unsigned long long) + sizeof(uint32_t)) * (size_t)M));     // keys, then first[]
+            KPRN_TRY(ensure(s->dd_slot_of, sizeof(uint32_t) * (size_t)M));
+            KPRN_TRY(ensure(s->dd_pos, sizeof(uint32_t) * (size_t)n_order));
+            KPRN_TRY(ensure(s->dd_slot, sizeof(int32_t) * (size_t)n_steps));
+            KPRN_TRY(ensure(s->dd_ids, sizeof(int32_t) * 3 * (size_t)n_steps));
+            KPRN_TRY(ensure(s->dd_count, 256 + sizeof(int32_t) * (size_t)nb));
+            unsigned long long* table = s->dd_table.as<unsigned long long>();
+            uint32_t* first = reinterpret_cast<uint32_t*>(table + M);
+            int32_t* count = s->dd_count.as<int32_t>();
+            int32_t* bsum = count + 64;
+            KPRN_CUDA(cudaMemsetAsync(table, 0xFF, (sizeof(unsigned long long) + sizeof(uint32_t)) * (size_t)M, ctx->stream));
+            dedup_insert_kernel<<<(unsigned)cdiv(n_order, 256), 256, 0, ctx->stream>>>(d_ids, n_order, N, c.T, c.V_t, c.V_e, c.V_r, table, first, M - 1,
+                                                                                      s->dd_pos.as<uint32_t>());
+            KPRN_LAUNCH_CHECK(ctx);
+            dedup_blocksum_kernel<<<(unsigned)nb, 256, 0, ctx->stream>>>(s->dd_pos.as<uint32_t>(), first, n_order, bsum);
+            KPRN_LAUNCH_CHECK(ctx);
+            dedup_scan_sums_kernel<<<1, 256, 0, ctx->stream>>>(bsum, nb, count);
+            KPRN_LAUNCH_CHECK(ctx);
+            dedup_assign_kernel<<<(unsigned)nb, 256, 0, ctx->stream>>>(d_ids, s->dd_pos.as<uint32_t>(), first, n_order, N, c.T, bsum,
+                                                                       s->dd_slot_of.as<uint32_t>(), s->dd_ids.as<int32_t>());
+            KPRN_LAUNCH_CHECK(ctx);
+            dedup_map_kernel<<<(unsigned)cdiv(n_order, 256), 256, 0, ctx->stream>>>(s->dd_pos.as<uint32_t>(), s->dd_slot_of.as<uint32_t>(), n_order, N, c.T,
+                                                                                    s->dd_slot.as<int32_t>());
+            KPRN_LAUNCH_CHECK(ctx);
+            // the projection sees a list of (at most n_steps) single-step "paths"; its real length is read on the device
+            a.ids = s->dd_ids.as<int32_t>(); a.N = n_steps; a.T = 1; a.num_tiles = cdiv(n_steps, TILE_M); a.n_dev = count;
+        }
+        int64_t grid = a.num_tiles < s->num_sms ? a.num_tiles : s->num_sms;
         if (s->use_pairs && a.num_tiles >= 2) {
             int64_t pairs = (a.num_tiles + 1) / 2;
             int64_t g2 = 2 * (pairs < s->num_sms / 2 ? pairs : s->num_sms / 2);
@@ -1452,6 +1644,7 @@ int tc_forward(kprn_ctx* ctx, const int32_t* d_ids, const int32_t* d_seg, int64_
         a.XW = s->xw.as<float>(); a.W = s->Wh; a.hT = s->hT.as<float>(); a.hscratch = s->hscratch.as<bf16>(); a.N = N; a.T = c.T; a.H = c.H; a.G4 = s->G4;
         a.num_tiles = ptiles; a.passes = passes; a.dbg = dbg ? dbg + 16 : nullptr;
         a.wo = nullptr; a.part4 = nullptr; a.npad = ptiles * TILE_M;
+        a.slot = (s->dedup && ptiles * c.T * TILE_M < (1ll << 30)) ? s->dd_slot.as<int32_t>() : nullptr;
         ctx->head_part4 = nullptr;
         if (ctx->cls_only && c.pool == KPRN_POOL_LSE) {      // the pool kernel finishes the head: sum of 4 partials + bias
             KPRN_TRY(ensure(s->part4, sizeof(float) * 4 * (size_t)a.npad));
