@@ -223,8 +223,11 @@ static int forward_device_impl(kprn_ctx* ctx, const int32_t* d_ids, const int32_
     const kprn_config& c = ctx->cfg;
     if (N <= 0 || S <= 0) { set_error("empty batch: N=%lld S=%lld", (long long)N, (long long)S); return KPRN_EINVAL; }
     if (N * (int64_t)c.T * 3 >= (1ll << 40)) { set_error("batch too large"); return KPRN_EINVAL; }
-    validate_ids_kernel2<<<(unsigned)cdiv(N * c.T, 256), 256, 0, ctx->stream>>>(d_ids, N * c.T, c.V_t, c.V_e, c.V_r, ctx->d_err);
-    KPRN_LAUNCH_CHECK(ctx);
+    // the fused tensor-core forward validates the ids inside its first kernel (the deduplication's hash insert)
+    if (!(!train && c.precision != KPRN_PREC_FP32 && tc_supported(ctx) && tc_validates_ids(ctx, N))) {
+        validate_ids_kernel2<<<(unsigned)cdiv(N * c.T, 256), 256, 0, ctx->stream>>>(d_ids, N * c.T, c.V_t, c.V_e, c.V_r, ctx->d_err);
+        KPRN_LAUNCH_CHECK(ctx);
+    }
     check_seg_kernel<<<(unsigned)cdiv(S + 1, 256), 256, 0, ctx->stream>>>(d_seg, S, N, ctx->d_err);
     KPRN_LAUNCH_CHECK(ctx);
     ctx->N = N; ctx->S = S; ctx->d_ids = d_ids; ctx->d_seg = d_seg;

@@ -113,6 +113,7 @@ int tc_gemm(kprn_ctx* ctx, int64_t M, int64_t N, int64_t K, const float* A, int6
 
 // ---- tensor-core path (tc_path.cu) ----
 bool tc_supported(const kprn_ctx* ctx);
+bool tc_validates_ids(const kprn_ctx* ctx, int64_t N);   // true when tc_forward(train = false) will flag out-of-range ids itself
 int tc_forward(kprn_ctx* ctx, const int32_t* d_ids, const int32_t* d_seg, int64_t N, int64_t S, bool train);
 void tc_destroy(kprn_ctx* ctx);
 

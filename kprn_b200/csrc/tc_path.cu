@@ -56,7 +56,7 @@ struct TcState {
     bf16* WxE = nullptr; bf16* Wh = nullptr;
     float* Ptr = nullptr;
     DBuf xw, hT, hscratch, dbg, part4;
-    DBuf dd_table, dd_slot_of, dd_pos, dd_slot, dd_ids, dd_count;   // step-input deduplication
+    DBuf dd_table, dd_slot_of, dd_pos, dd_ids, dd_count;   // step-input deduplication
     bool dedup = true;         // project each distinct (type, entity, relation) triple once (KPRN_TC_DEDUP=0: every step)
     bool debug = false;
     bool use_gather4 = true;   // TMA tile::gather4 for the entity rows (KPRN_TC_GATHER4=0 -> LDGSTS gather of proj2)
@@ -80,6 +80,11 @@ bool tc_supported(const kprn_ctx* ctx) {
     int noh = (int)((c.V_t * c.V_r + 63) / 64);
     if (noh > 2 || KE / 64 + noh > MAX_NS) return false;   // (type,relation) combos ride the MMA as a one-hot k-slice
     return true;
+}
+
+static bool dedup_enabled() { const char* d = getenv("KPRN_TC_DEDUP"); return !(d && d[0] == '0'); }
+bool tc_validates_ids(const kprn_ctx* ctx, int64_t N) {
+    return dedup_enabled() && (N + TILE_M - 1) / TILE_M * TILE_M * (int64_t)ctx->cfg.T < (1ll << 30);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -936,9 +941,9 @@ struct RecurArgs {
     // scores-only path (A5 fused): row classId of the head weight and the [4][npad] partial dot products h_T . wo, one per epilogue
     // group; null = write h_T for the head kernels instead
     const float* wo; float* part4; int64_t npad;
-    // XW row of (path n, step t) = slot[n*T + t] (a row index into the projection of the DISTINCT step inputs); null = n's own
-    // row (tile (n/128)*T + t, row n%128)
-    const int32_t* slot;
+    // XW row of (path tile, t, r) = slot_of[pos[(tile*T + t)*128 + r]] (a row of the projection of the DISTINCT step inputs,
+    // see the dedup kernels); null = its own row (tile tile*T + t, row r)
+    const uint32_t* pos; const uint32_t* slot_of;
 };
 
 __device__ __forceinline__ float ex2f(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -1186,14 +1191,18 @@ __global__ void __launch_bounds__(RECUR_THREADS, 1) recur_kernel(RecurArgs a) {
         for (int64_t it = 0; it < my_tiles; ++it) {
             const int64_t pt = tile_of(it);
             const int64_t n = pt * TILE_M + r;
-            const int64_t nc = n < a.N ? n : a.N - 1;                     // ragged last tile: any valid row
-            int32_t slot_next = a.slot ? a.slot[nc * T] : 0;
+            // row index of this thread's XW row per step (rows past N in a ragged last tile: any valid row)
+            auto row_of = [&](int t) -> uint32_t {
+                const uint32_t p = a.pos[(pt * T + t) * TILE_M + r];
+                return p == 0xFFFFFFFFu ? 0u : a.slot_of[p];
+            };
+            uint32_t slot_next = a.pos ? row_of(0) : 0u;
             for (int t = 0; t < T; ++t) {
-                const int32_t slot = slot_next;
-                if (a.slot && t + 1 < T) slot_next = a.slot[nc * T + t + 1];   // next step's row index, in flight during this step
+                const uint32_t slot = slot_next;
+                if (a.pos && t + 1 < T) slot_next = row_of(t + 1);       // next step's row index, in flight during this step
                 // rows are numbered in the order the recurrence reads them (see the dedup kernels): the first occurrences inside a
                 // warp are consecutive rows of one tile, repeated triples (pad steps, a pair's shared user / item) share a row
-                const float* xw_t = a.slot ? a.XW + (int64_t)(slot >> 7) * tile_xw + (slot & 127) * 8
+                const float* xw_t = a.pos ? a.XW + (int64_t)(slot >> 7) * tile_xw + (slot & 127) * 8
                                            : a.XW + (pt * T + t) * tile_xw + r * 8;
                 const bool last = (t == T - 1);
                 float xa[32], xb[32];                 // XW of the current / next chunk, ping-pong (no register copies)
@@ -1339,8 +1348,8 @@ __global__ void __launch_bounds__(RECUR_THREADS, 1) recur_kernel(RecurArgs a) {
 // row-index map.  Rows are numbered by FIRST OCCURRENCE IN THE ORDER THE RECURRENCE READS THEM -- o = ((tile*T + t)*128 + r)
 // for path n = tile*128 + r, step t -- so the first occurrences inside one warp load are consecutive rows (coalesced as
 // before) and repeats inside a warp hit the same sector.  Open-addressing hash table (64-bit keys, linear probing) with an
-// atomicMin of o per key, a two-level prefix sum over the first-occurrence flags, no host round trip: the projection
-// kernels read the distinct count from device memory.  Everything (row numbering included) is deterministic.
+// atomicMin of o per key and a block-level prefix sum over the first-occurrence flags; two small kernels, no host round
+// trip: the projection kernels read the distinct count from device memory, the recurrence resolves row = slot_of[pos[o]].
 constexpr unsigned long long DEDUP_EMPTY = ~0ull;
 constexpr int DEDUP_BLOCK = 1024;          // read-order indices per block of the flag scan
 
@@ -1358,13 +1367,16 @@ __device__ __forceinline__ int64_t dedup_step_of(int64_t o, int64_t N, int T) {
 // pos[o] = table position of the triple read at o; first[pos] = min o over its occurrences.  Equal triples inside a warp
 // (a pad column of a tile is one triple) elect one lane; a plain load before the CAS keeps hot keys from serialising.
 __global__ void dedup_insert_kernel(const int32_t* __restrict__ ids, int64_t n_order, int64_t N, int T, int64_t V_t, int64_t V_e,
-                                    int64_t V_r, unsigned long long* table, uint32_t* first, uint32_t mask, uint32_t* __restrict__ pos) {
+                                    int64_t V_r, unsigned long long* table, uint32_t* first, uint32_t mask, uint32_t* __restrict__ pos,
+                                    int32_t* err) {
     const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t i = o < n_order ? dedup_step_of(o, N, T) : -1;
     const bool active = i >= 0;
     unsigned long long key = DEDUP_EMPTY;
     if (active) {
         int64_t ta = (int64_t)ids[i * 3] - 1, en = (int64_t)ids[i * 3 + 1] - 1, rb = (int64_t)ids[i * 3 + 2] - 1;
+        // a bad id raises in the reference (nn.LookupTable index out of range): flagged here, reported by the forward call
+        if (ta < 0 || ta >= V_t || en < 0 || en >= V_e || rb < 0 || rb >= V_r) atomicExch(err, 1);
         ta = ta < 0 ? 0 : (ta >= V_t ? V_t - 1 : ta);
         en = en < 0 ? 0 : (en >= V_e ? V_e - 1 : en);
         rb = rb < 0 ? 0 : (rb >= V_r ? V_r - 1 : rb);
@@ -1416,40 +1428,21 @@ __device__ __forceinline__ int dedup_flags(const uint32_t* __restrict__ pos, con
     }
     return c;
 }
-__global__ void dedup_blocksum_kernel(const uint32_t* __restrict__ pos, const uint32_t* __restrict__ first, int64_t n_order, int32_t* __restrict__ bsum) {
-    bool f[4];
-    int tot;
-    const int c = dedup_flags(pos, first, n_order, ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4, f);
-    dedup_block_scan(c, &tot);
-    if (threadIdx.x == 0) bsum[blockIdx.x] = tot;
-}
-// one block: exclusive scan of the block sums in place, total = number of distinct triples
-__global__ void dedup_scan_sums_kernel(int32_t* bsum, int nb, int32_t* __restrict__ count) {
-    __shared__ int carry_s;
-    if (threadIdx.x == 0) carry_s = 0;
-    __syncthreads();
-    for (int b0 = 0; b0 < nb; b0 += 256) {
-        const int b = b0 + threadIdx.x;
-        const int v = b < nb ? bsum[b] : 0;
-        int tot;
-        const int ex = dedup_block_scan(v, &tot);
-        const int carry = carry_s;
-        if (b < nb) bsum[b] = carry + ex;
-        __syncthreads();
-        if (threadIdx.x == 0) carry_s = carry + tot;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) *count = carry_s;
-}
-// rank of every first occurrence = its row; the first-occurrence thread records it for its key and writes the triple
+// Row of every first occurrence: consecutive inside a block of 1024 read-order indices (what the recurrence's warp loads
+// need), blocks placed by one atomicAdd each (their order varies from run to run; the values computed do not).  The
+// first-occurrence thread records the row for its key and writes the triple to the list the projection reads.
 __global__ void dedup_assign_kernel(const int32_t* __restrict__ ids, const uint32_t* __restrict__ pos, const uint32_t* __restrict__ first,
-                                    int64_t n_order, int64_t N, int T, const int32_t* __restrict__ boff, uint32_t* __restrict__ slot_of,
+                                    int64_t n_order, int64_t N, int T, int32_t* count, uint32_t* __restrict__ slot_of,
                                     int32_t* __restrict__ ids_d) {
+    __shared__ int base_s;
     bool f[4];
     int tot;
     const int64_t o0 = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4;
     const int c = dedup_flags(pos, first, n_order, o0, f);
-    int row = boff[blockIdx.x] + dedup_block_scan(c, &tot);
+    const int ex = dedup_block_scan(c, &tot);
+    if (threadIdx.x == 0) base_s = tot ? atomicAdd(count, tot) : 0;
+    __syncthreads();
+    int row = base_s + ex;
 #pragma unroll
     for (int j = 0; j < 4; ++j)
         if (f[j]) {
@@ -1458,13 +1451,6 @@ __global__ void dedup_assign_kernel(const int32_t* __restrict__ ids, const uint3
             ids_d[(int64_t)row * 3] = ids[i * 3]; ids_d[(int64_t)row * 3 + 1] = ids[i * 3 + 1]; ids_d[(int64_t)row * 3 + 2] = ids[i * 3 + 2];
             ++row;
         }
-}
-__global__ void dedup_map_kernel(const uint32_t* __restrict__ pos, const uint32_t* __restrict__ slot_of, int64_t n_order, int64_t N, int T,
-                                 int32_t* __restrict__ slot) {
-    const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (o >= n_order) return;
-    const int64_t i = dedup_step_of(o, N, T);
-    if (i >= 0) slot[i] = (int32_t)slot_of[pos[o]];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1559,7 +1545,7 @@ int tc_forward(kprn_ctx* ctx, const int32_t* d_ids, const int32_t* d_seg, int64_
         { const char* d = getenv("KPRN_TC_PAIRS"); s->use_pairs = !(d && d[0] == '0'); }
         { const char* d = getenv("KPRN_TC_GATHER4"); s->use_gather4 = !(d && d[0] == '0'); }
         { const char* d = getenv("KPRN_TC_RECUR_PAIRS"); s->recur_pairs = !(d && d[0] == '0'); }
-        { const char* d = getenv("KPRN_TC_DEDUP"); s->dedup = !(d && d[0] == '0'); }
+        s->dedup = dedup_enabled();
         if (prop.major != 10) { set_error("tensor-core path needs sm_100 (found sm_%d%d)", prop.major, prop.minor); return KPRN_ECUDA; }
     }
     TcState* s = ctx->tc;
@@ -1597,26 +1583,18 @@ int tc_forward(kprn_ctx* ctx, const int32_t* d_ids, const int32_t* d_seg, int64_
             KPRN_TRY(ensure(s->dd_table, (sizeof(unsigned long long) + sizeof(uint32_t)) * (size_t)M));     // keys, then first[]
             KPRN_TRY(ensure(s->dd_slot_of, sizeof(uint32_t) * (size_t)M));
             KPRN_TRY(ensure(s->dd_pos, sizeof(uint32_t) * (size_t)n_order));
-            KPRN_TRY(ensure(s->dd_slot, sizeof(int32_t) * (size_t)n_steps));
             KPRN_TRY(ensure(s->dd_ids, sizeof(int32_t) * 3 * (size_t)n_steps));
-            KPRN_TRY(ensure(s->dd_count, 256 + sizeof(int32_t) * (size_t)nb));
+            KPRN_TRY(ensure(s->dd_count, 256));
             unsigned long long* table = s->dd_table.as<unsigned long long>();
             uint32_t* first = reinterpret_cast<uint32_t*>(table + M);
             int32_t* count = s->dd_count.as<int32_t>();
-            int32_t* bsum = count + 64;
             KPRN_CUDA(cudaMemsetAsync(table, 0xFF, (sizeof(unsigned long long) + sizeof(uint32_t)) * (size_t)M, ctx->stream));
+            KPRN_CUDA(cudaMemsetAsync(count, 0, sizeof(int32_t), ctx->stream));
             dedup_insert_kernel<<<(unsigned)cdiv(n_order, 256), 256, 0, ctx->stream>>>(d_ids, n_order, N, c.T, c.V_t, c.V_e, c.V_r, table, first, M - 1,
-                                                                                      s->dd_pos.as<uint32_t>());
+                                                                                      s->dd_pos.as<uint32_t>(), ctx->d_err);
             KPRN_LAUNCH_CHECK(ctx);
-            dedup_blocksum_kernel<<<(unsigned)nb, 256, 0, ctx->stream>>>(s->dd_pos.as<uint32_t>(), first, n_order, bsum);
-            KPRN_LAUNCH_CHECK(ctx);
-            dedup_scan_sums_kernel<<<1, 256, 0, ctx->stream>>>(bsum, nb, count);
-            KPRN_LAUNCH_CHECK(ctx);
-            dedup_assign_kernel<<<(unsigned)nb, 256, 0, ctx->stream>>>(d_ids, s->dd_pos.as<uint32_t>(), first, n_order, N, c.T, bsum,
+            dedup_assign_kernel<<<(unsigned)nb, 256, 0, ctx->stream>>>(d_ids, s->dd_pos.as<uint32_t>(), first, n_order, N, c.T, count,
                                                                        s->dd_slot_of.as<uint32_t>(), s->dd_ids.as<int32_t>());
-            KPRN_LAUNCH_CHECK(ctx);
-            dedup_map_kernel<<<(unsigned)cdiv(n_order, 256), 256, 0, ctx->stream>>>(s->dd_pos.as<uint32_t>(), s->dd_slot_of.as<uint32_t>(), n_order, N, c.T,
-                                                                                    s->dd_slot.as<int32_t>());
             KPRN_LAUNCH_CHECK(ctx);
             // the projection sees a list of (at most n_steps) single-step "paths"; its real length is read on the device
             a.ids = s->dd_ids.as<int32_t>(); a.N = n_steps; a.T = 1; a.num_tiles = cdiv(n_steps, TILE_M); a.n_dev = count;
@@ -1644,7 +1622,8 @@ int tc_forward(kprn_ctx* ctx, const int32_t* d_ids, const int32_t* d_seg, int64_
         a.XW = s->xw.as<float>(); a.W = s->Wh; a.hT = s->hT.as<float>(); a.hscratch = s->hscratch.as<bf16>(); a.N = N; a.T = c.T; a.H = c.H; a.G4 = s->G4;
         a.num_tiles = ptiles; a.passes = passes; a.dbg = dbg ? dbg + 16 : nullptr;
         a.wo = nullptr; a.part4 = nullptr; a.npad = ptiles * TILE_M;
-        a.slot = (s->dedup && ptiles * c.T * TILE_M < (1ll << 30)) ? s->dd_slot.as<int32_t>() : nullptr;
+        const bool dd = s->dedup && ptiles * c.T * TILE_M < (1ll << 30);
+        a.pos = dd ? s->dd_pos.as<uint32_t>() : nullptr; a.slot_of = dd ? s->dd_slot_of.as<uint32_t>() : nullptr;
         ctx->head_part4 = nullptr;
         if (ctx->cls_only && c.pool == KPRN_POOL_LSE) {      // the pool kernel finishes the head: sum of 4 partials + bias
             KPRN_TRY(ensure(s->part4, sizeof(float) * 4 * (size_t)a.npad));

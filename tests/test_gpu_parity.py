@@ -125,14 +125,16 @@ def test_train_batch_matches_oracle_trainBatch():
     e.close()
 
 
-def test_errors_are_loud():
+@pytest.mark.parametrize("precision", [0, 1])
+def test_errors_are_loud(precision):
     from kprn_b200.engine import KprnError
-    o, params, ids, seg, labels = make_case(N=32, seed=14)
-    e = engine_for(o)
+    o, params, ids, seg, labels = make_case(N=32, seed=14, d_t=8, d_e=64, d_r=8, H=64)
+    e = engine_for(o, precision=precision)
     e.set_params(params)
-    bad = ids.copy(); bad[3, 2, 1] = o.cfg.V_e + 1
-    with pytest.raises(KprnError):
-        e.forward(bad, seg)
+    for col, v in ((1, o.cfg.V_e + 1), (1, 0), (0, o.cfg.V_t + 1), (2, -3)):     # nn.LookupTable raises on any of these
+        bad = ids.copy(); bad[3, 2, col] = v
+        with pytest.raises(KprnError):
+            e.forward(bad, seg)
     with pytest.raises(KprnError):
         e.backward()                      # no training forward yet
     badseg = seg.copy(); badseg[-1] -= 1
