@@ -169,7 +169,7 @@ def workload_config(d, n_paths, gpus):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture (profiles/), bytes
-TRAFFIC = {"proj": 1.774e9, "recur": 1.885e9}   # dram read + write per launch, profiles/r01_v5_summary.md (proj3_kernel, recur_kernel<256, pair>)
+TRAFFIC = {"proj": 1.040e9, "recur": 1.459e9}   # dram read + write per launch, profiles/r01_v6_summary.md (proj3_kernel, recur_kernel<256, pair>)
 
 
 def main():

@@ -216,3 +216,19 @@ def test_fallback_kernels_still_match():
                 {"KPRN_TC_DEDUP": "0", "KPRN_TC_PAIRS": "0", "KPRN_TC_RECUR_PAIRS": "0"}):
         out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True, timeout=300)
         assert out.returncode == 0 and "ok" in out.stdout, (env, out.stderr[-800:])
+
+
+def test_dedup_is_bit_identical_to_projecting_every_step(monkeypatch):
+    """Projecting each distinct (type, entity, relation) step input once changes where a row of XW lives, not its value."""
+    o, params, ids, seg, labels = make_case(N=3000, seed=31, d_t=16, d_e=128, d_r=16, H=128, V_e=300, length_mode="realistic")
+    e1 = engine_for(o, precision=1)
+    e1.set_params(params)
+    a = e1.forward(ids, seg)
+    e1.close()
+    monkeypatch.setenv("KPRN_TC_DEDUP", "0")
+    e2 = engine_for(o, precision=1)
+    e2.set_params(params)
+    b = e2.forward(ids, seg)
+    e2.close()
+    np.testing.assert_array_equal(a, b)
+    assert_rel(a, o.forward(params, ids, seg)["scores"], what="scores")
