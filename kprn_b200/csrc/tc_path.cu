@@ -1680,9 +1680,8 @@ void tc_destroy(kprn_ctx* ctx) {
     if (s->WxE) cudaFree(s->WxE);
     if (s->Wh) cudaFree(s->Wh);
     if (s->Ptr) cudaFree(s->Ptr);
-    if (s->xw.p) cudaFree(s->xw.p);
-    if (s->hT.p) cudaFree(s->hT.p);
-    if (s->hscratch.p) cudaFree(s->hscratch.p);
+    for (DBuf* b : {&s->xw, &s->hT, &s->hscratch, &s->dbg, &s->part4, &s->dd_table, &s->dd_slot_of, &s->dd_pos, &s->dd_ids, &s->dd_count})
+        if (b->p) { cudaFree(b->p); b->p = nullptr; b->cap = 0; }
     delete s;
     ctx->tc = nullptr;
 }
