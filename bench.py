@@ -106,7 +106,7 @@ def make_batches(n_batches, n_paths, seed=12345):
     return out
 
 
-def cpu_port_throughput(d, budget_s=15.0, threads=None):
+def cpu_port_throughput(d, budget_s=15.0, threads=None, dims=None):
     """Times the fp64 CPU restatement (oracle port) on a bounded sample of the same workload."""
     from kprn_b200 import synth
     from oracle.kprn_oracle import Oracle
@@ -119,7 +119,8 @@ def cpu_port_throughput(d, budget_s=15.0, threads=None):
         ids = ids_all[:n].copy()
         uniq, inv = np.unique(ids[:, :, 1], return_inverse=True)
         ids[:, :, 1] = inv.reshape(n, T) + 1
-        o = Oracle(T=T, d_t=d, d_e=d, d_r=d, H=d, L=L, V_e=len(uniq))
+        dt_, de_, dr_ = dims or (d, d, d)
+        o = Oracle(T=T, d_t=dt_, d_e=de_, d_r=dr_, H=d, L=L, V_e=len(uniq))
         params = o.init_params(12345)
         seg = synth.make_segments(n, seed=12345)
         o.forward(params, ids[:min(n, 64)], np.array([0, min(n, 64)], dtype=np.int32))   # warm-up
@@ -151,19 +152,20 @@ def run_reference(args):
     if rank != 0:
         return 0
     d = args.d
+    dims = (d, d, d) if args.conv == "A" else (d // 4, d // 2, d // 4)
     times, n_s = [], 0
     total = args.steps + args.warmup
     budget = max(2.0, min(20.0, 150.0 / total))
     vals = []
     for i in range(total):
-        v, n_s, dt, cores = cpu_port_throughput(d, budget_s=budget)
+        v, n_s, dt, cores = cpu_port_throughput(d, budget_s=budget, dims=dims)
         if i >= args.warmup:
             vals.append(v); times.append(dt)
     value = float(np.mean(vals))
     line = {"impl": "reference", "metric": "paths/sec scored", "value": value, "unit": "paths/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(times)),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(d, args.paths, args.gpus),
+            "config": workload_config(d, args.paths, args.gpus, dims),
             "cpu_baseline": {"value": value, "unit": "paths/s", "cores": cores, "kind": "port",
                              "sample": "%d paths of the %d-path batch per step, fp64 C restatement with OpenMP "
                                        "(Torch7 cannot run in this image)" % (n_s, args.paths)},
@@ -172,9 +174,12 @@ def run_reference(args):
     return 0
 
 
-def workload_config(d, n_paths, gpus):
-    return {"workload": "BASELINE configs[1]: KG paths len<=6 (T=6, left-padded), d=%d convention A "
-                        "(d_t=d_e=d_r=H=%d, D=%d), %d paths/GPU/step, forward+pool (LSTM, L=46, LSE, sigmoid)" % (d, d, 3 * d, n_paths),
+def workload_config(d, n_paths, gpus, dims=None):
+    dt_, de_, dr_ = dims or (d, d, d)
+    conv = "A" if (dt_, de_, dr_) == (d, d, d) else "B (reference ratio 1:2:1)"
+    return {"workload": "BASELINE configs[1]: KG paths len<=6 (T=6, left-padded), d=%d convention %s "
+                        "(d_t=%d, d_e=%d, d_r=%d, H=%d, D=%d), %d paths/GPU/step, forward+pool (LSTM, L=46, LSE, sigmoid)"
+                        % (d, conv, dt_, de_, dr_, d, dt_ + de_ + dr_, n_paths),
             "paths_per_gpu": n_paths, "T": T, "d": d, "V_e": V_E, "segments": "1+Geom(0.57) paths per (user,item), CSR",
             "entities": "Zipf(1.05) over 2.85M rows", "parallelism": "paths sharded x%d, no data-path collective" % gpus,
             "l2": "8 rotating input batches; per-step working set (gathered rows + activations) exceeds the 126 MB L2"}
@@ -191,6 +196,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--d", type=int, default=256)
+    ap.add_argument("--conv", choices=["A", "B"], default="A",
+                    help="dimension convention (SURVEY 8d): A (headline) d_t=d_e=d_r=H=d; B (reference ratio) d_e=d/2, d_t=d_r=d/4, H=d")
     ap.add_argument("--paths", type=int, default=N_PATHS)
     ap.add_argument("--precision", type=int, default=-1, help="-1 auto (tensor-core split if supported), 0 fp32, 1 split, 2 fast")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -212,18 +219,19 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     d = args.d
+    d_t, d_e, d_r = (d, d, d) if args.conv == "A" else (d // 4, d // 2, d // 4)
     n_paths = args.paths
     prec = args.precision
     eng = None
     if prec < 0:
         try:
-            eng = engine.Engine(T=T, d_t=d, d_e=d, d_r=d, H=d, L=L, V_e=V_E, precision=engine.PREC_TC_SPLIT, device=local)
+            eng = engine.Engine(T=T, d_t=d_t, d_e=d_e, d_r=d_r, H=d, L=L, V_e=V_E, precision=engine.PREC_TC_SPLIT, device=local)
             prec = engine.PREC_TC_SPLIT
         except engine.KprnError:
             eng = None
     if eng is None:
         prec = max(prec, 0) if args.precision >= 0 else engine.PREC_FP32
-        eng = engine.Engine(T=T, d_t=d, d_e=d, d_r=d, H=d, L=L, V_e=V_E, precision=prec, device=local)
+        eng = engine.Engine(T=T, d_t=d_t, d_e=d_e, d_r=d_r, H=d, L=L, V_e=V_E, precision=prec, device=local)
     eng.init_uniform(0.1, 12345)
     eng.zero_row(engine.TABLE_TYPE, 6)
     eng.zero_row(engine.TABLE_ENTITY, V_E)
@@ -254,7 +262,7 @@ def main():
         if args.precision < 0 and prec != engine.PREC_FP32:
             eng.close()
             prec = engine.PREC_FP32
-            eng = engine.Engine(T=T, d_t=d, d_e=d, d_r=d, H=d, L=L, V_e=V_E, precision=prec, device=local)
+            eng = engine.Engine(T=T, d_t=d_t, d_e=d_e, d_r=d_r, H=d, L=L, V_e=V_E, precision=prec, device=local)
             eng.init_uniform(0.1, 12345)
             eng.set_stream(stream.cuda_stream)
             step_device(0)
@@ -324,18 +332,18 @@ def main():
 
     if rank == 0:
         pk, pk_src = peaks()
-        fpp = flops_per_path(d, d, d, d)
+        fpp = flops_per_path(d_t, d_e, d_r, d)
         mode = {0: "fp32 FFMA (CUDA cores)", 1: "tcgen05 kind::f16, 3-pass hi/lo split", 2: "tcgen05 kind::f16 single pass",
                 3: "tcgen05 kind::f16, 3-pass hi/lo split"}[prec]
         mult = {0: 1, 1: 3, 2: 1, 3: 3}[prec]
-        D, H = 3 * d, d
+        D, H = d_t + d_e + d_r, d
         # algorithmic flops per launch: proj = the input projection x_t Wx^T of all T steps,
         # recur = the recurrent projection h Wh^T of all T steps (pad steps and t=0 count: the reference computes them)
         alg = {"proj": T * 2 * D * 4 * H * n_paths, "recur": T * 2 * H * 4 * H * n_paths, "gate_phase": fpp * n_paths}
         # flops the tensor cores actually execute per launch in the fused path (bf16x3): the projection runs once per DISTINCT
         # step input, 3 passes over the entity columns + 2 over the one-hot (type,relation) slice; the recurrence 3 passes over
         # T-1 steps (h_0 = 0)
-        ke, hp = -(-d // 64) * 64, (64 if d <= 64 else 128 if d <= 128 else 256)
+        ke, hp = -(-d_e // 64) * 64, (64 if d <= 64 else 128 if d <= 128 else 256)
         dedup_on = os.environ.get("KPRN_TC_DEDUP", "1") != "0"
         rows = distinct_rows if dedup_on else n_paths * T
         exe = {"proj": rows * 2 * (3 * ke + 2 * 64) * 4 * hp, "recur": n_paths * (T - 1) * 2 * hp * 4 * hp * 3}
@@ -374,13 +382,13 @@ def main():
         line = {"metric": "paths/sec scored", "value": value, "unit": "paths/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32" if prec == 0 else "f32 (bf16x3 split MMA, fp32 accumulate)", "data": "synthetic",
-                "config": workload_config(d, n_paths, world),
+                "config": workload_config(d, n_paths, world, (d_t, d_e, d_r)),
                 "e2e": {"value": e2e_value, "unit": "paths/s", "h2d_bytes_per_step": h2d // args.steps,
                         "d2h_bytes_per_step": d2h // args.steps},
                 "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roof,
-                "hbm": {"gather_gbs": gather_bytes_per_path(d, d, d) * value / world / 1e9, "peak_gbs": pk["hbm_gbs"]}}
+                "hbm": {"gather_gbs": gather_bytes_per_path(d_t, d_e, d_r) * value / world / 1e9, "peak_gbs": pk["hbm_gbs"]}}
         if not args.no_cpu_baseline:
-            v, n_s, dt, cores = cpu_port_throughput(d, budget_s=15.0)
+            v, n_s, dt, cores = cpu_port_throughput(d, budget_s=15.0, dims=(d_t, d_e, d_r))
             line["cpu_baseline"] = {"value": v, "unit": "paths/s", "cores": cores, "kind": "port",
                                     "sample": "%d paths of the batch, fp64 C restatement + OpenMP, %.1f s" % (n_s, dt)}
         print(json.dumps(line))
