@@ -84,7 +84,8 @@ bool tc_supported(const kprn_ctx* ctx) {
 
 static bool dedup_enabled() { const char* d = getenv("KPRN_TC_DEDUP"); return !(d && d[0] == '0'); }
 bool tc_validates_ids(const kprn_ctx* ctx, int64_t N) {
-    return dedup_enabled() && (N + TILE_M - 1) / TILE_M * TILE_M * (int64_t)ctx->cfg.T < (1ll << 30);
+    const bool dd = ctx->tc ? ctx->tc->dedup : dedup_enabled();     // the ctx latches the knob at its first forward
+    return dd && (N + TILE_M - 1) / TILE_M * TILE_M * (int64_t)ctx->cfg.T < (1ll << 30);
 }
 
 // ---------------------------------------------------------------------------------------------
