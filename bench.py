@@ -106,45 +106,62 @@ def make_batches(n_batches, n_paths, seed=12345):
     return out
 
 
-def cpu_port_throughput(d, budget_s=15.0, threads=None, dims=None):
-    """Times the fp64 CPU restatement (oracle port) on a bounded sample of the same workload."""
+def cpu_sample(d, dims, n, threads=None, keep=False, proxy=False):
+    """Runs the fp64 CPU restatement (or, proxy=True, the PyTorch-CPU fp64 model) on the first n paths of batch 0 -- the very
+    batch the GPU arm times -- with the SAME parameter values the device holds (synth.device_uniform replays
+    kprn_init_uniform; the entity table is compacted to the rows the sample touches: same arithmetic, bounded host memory).
+    Returns (seconds, outputs or None, (ids, seg))."""
     from kprn_b200 import synth
     from oracle.kprn_oracle import Oracle
+    dt_, de_, dr_ = dims
+    ids = synth.make_paths(N_PATHS, T=T, V_e=V_E, seed=12345, length_mode="realistic", entity_mode="zipf")[:n]
+    seg = synth.make_segments(n, seed=12345, mode="realistic")
+    ids_c, rows = synth.compact_entities(ids)
+    o = Oracle(T=T, d_t=dt_, d_e=de_, d_r=dr_, H=d, L=L, V_e=len(rows))
+    sizes = {"E_t": 6 * dt_, "E_r": 9 * dr_, "Wx": 4 * d * (dt_ + de_ + dr_), "bx": 4 * d, "Wh": 4 * d * d, "Wo": L * d, "bo": L}
+    params = synth.compact_params(synth.full_offsets(dt_, de_, dr_, d, L, V_e=V_E), o.offsets, o.n_params, rows, de_, sizes, 0.1, 12345,
+                                  zero_rows=[("E_t", 6, dt_), ("E_e", V_E, de_), ("E_r", 9, dr_)])
+    if proxy:
+        from oracle import torch_proxy
+        import torch
+        if threads:
+            torch.set_num_threads(threads)
+        torch_proxy.forward(o, params, ids_c[:64], np.array([0, 64], dtype=np.int32))
+        t0 = time.perf_counter()
+        pl, sc = torch_proxy.forward(o, params, ids_c, seg)
+        dt = time.perf_counter() - t0
+        return dt, ({"path_logits": pl, "scores": sc} if keep else None), (ids, seg)
+    if threads:
+        Oracle.set_num_threads(threads)
+    o.forward(params, ids_c[:64], np.array([0, 64], dtype=np.int32))   # warm-up
+    t0 = time.perf_counter()
+    out = o.forward(params, ids_c, seg)
+    dt = time.perf_counter() - t0
+    return dt, (out if keep else None), (ids, seg)
+
+
+def cpu_port_throughput(d, budget_s=15.0, threads=None, dims=None, keep=False, proxy=False):
+    """Times a CPU arm on a bounded sample of the same workload (about budget_s seconds of CPU work)."""
+    from oracle.kprn_oracle import Oracle
+    dims = dims or (d, d, d)
     # all host cores this process may run on, whatever OMP_NUM_THREADS says (torchrun sets it to 1 for every rank)
     ncpu = len(os.sched_getaffinity(0))
-    Oracle.set_num_threads(threads or ncpu)
-    ids_all = synth.make_paths(N_PATHS, T=T, V_e=V_E, seed=12345)
-    # compact the entity table to the rows this sample touches (same arithmetic, bounded host memory)
-    def run(n):
-        ids = ids_all[:n].copy()
-        uniq, inv = np.unique(ids[:, :, 1], return_inverse=True)
-        ids[:, :, 1] = inv.reshape(n, T) + 1
-        dt_, de_, dr_ = dims or (d, d, d)
-        o = Oracle(T=T, d_t=dt_, d_e=de_, d_r=dr_, H=d, L=L, V_e=len(uniq))
-        params = o.init_params(12345)
-        seg = synth.make_segments(n, seed=12345)
-        o.forward(params, ids[:min(n, 64)], np.array([0, min(n, 64)], dtype=np.int32))   # warm-up
-        t0 = time.perf_counter()
-        o.forward(params, ids, seg)
-        return time.perf_counter() - t0
+    use = threads or ncpu
     n = 256
-    dt = run(n)
-    if not threads and ncpu >= 64:
+    dt, _, _ = cpu_sample(d, dims, n, use, proxy=proxy)
+    if not threads and ncpu >= 64 and not proxy:
         # two-socket hosts: the (NUMA-unaware) port is sometimes faster on half the threads -- give the baseline its better setting
-        Oracle.set_num_threads(ncpu // 2)
-        dt_half = min(run(n), run(n))
-        Oracle.set_num_threads(ncpu)
-        dt_full = min(run(n), run(n))
-        if dt_half < dt_full:
-            Oracle.set_num_threads(ncpu // 2)
-            dt = dt_half
-        else:
-            dt = dt_full
+        dt_half = min(cpu_sample(d, dims, n, ncpu // 2)[0] for _ in range(2))
+        dt_full = min(cpu_sample(d, dims, n, ncpu)[0] for _ in range(2))
+        use, dt = (ncpu // 2, dt_half) if dt_half < dt_full else (ncpu, dt_full)
     rate = n / dt
     n2 = int(min(N_PATHS, max(256, rate * budget_s)))
     n2 = (n2 // 64) * 64
-    dt2 = run(n2)
-    return n2 / dt2, n2, dt2, Oracle.num_threads()
+    dt2, out, sample = cpu_sample(d, dims, n2, use, keep=keep, proxy=proxy)
+    cores = use
+    if not proxy:
+        cores = Oracle.num_threads()
+    return n2 / dt2, n2, dt2, cores, out, sample
 
 
 def run_reference(args):
@@ -158,7 +175,7 @@ def run_reference(args):
     budget = max(2.0, min(20.0, 150.0 / total))
     vals = []
     for i in range(total):
-        v, n_s, dt, cores = cpu_port_throughput(d, budget_s=budget, dims=dims)
+        v, n_s, dt, cores, _, _ = cpu_port_throughput(d, budget_s=budget, dims=dims)
         if i >= args.warmup:
             vals.append(v); times.append(dt)
     value = float(np.mean(vals))
@@ -185,8 +202,28 @@ def workload_config(d, n_paths, gpus, dims=None):
             "l2": "8 rotating input batches; per-step working set (gathered rows + activations) exceeds the 126 MB L2"}
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture (profiles/), bytes
-TRAFFIC = {"proj": 1.040e9, "recur": 1.503e9}   # dram read + write per launch, profiles/r01_v6_summary.md (proj3_kernel, recur_kernel<256, pair>)
+def profile_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch, read from the newest committed `ncu --set full` capture
+    (profiles/*_traffic.json, written by tools/profile_summary.py from the .ncu-rep). Returns ({kernel: bytes}, source)."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")))
+    if not files:
+        return {}, None
+    j = json.load(open(files[-1]))
+    return ({k: v["dram_read_bytes"] + v["dram_write_bytes"] for k, v in j["kernels"].items()},
+            os.path.relpath(files[-1], ROOT) + " <- " + j.get("source", ""))
+
+
+def time_device(eng, step_fn, steps, stream, barrier):
+    import torch
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for i in range(steps):
+        step_fn(i)
+    ev1.record(stream)
+    barrier()
+    return ev0.elapsed_time(ev1) / steps
 
 
 def main():
@@ -201,6 +238,8 @@ def main():
     ap.add_argument("--paths", type=int, default=N_PATHS)
     ap.add_argument("--precision", type=int, default=-1, help="-1 auto (tensor-core split if supported), 0 fp32, 1 split, 2 fast")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip value_dedup_off / value_uniform_entities / e2e_f64ids")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-step block")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -327,6 +366,96 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_s = float(te.item())
     e2e_value = world * n_paths * args.steps / e2e_s
+
+    extras = {}
+    if world == 1 and not args.no_extras:
+        xs = max(5, min(args.steps, 20))
+        # (1) deduplication off: every step of every path is projected (the data-independent figure)
+        if prec != engine.PREC_FP32:
+            eng.set_option("dedup", 0)
+            for i in range(3):
+                step_device(i)
+            ms = time_device(eng, step_device, xs, stream, barrier)
+            extras["value_dedup_off"] = {"value": n_paths / (ms * 1e-3), "unit": "paths/s", "ms_per_step": ms, "steps": xs,
+                                         "note": "KPRN dedup knob off: projection runs on all N*T step inputs"}
+            eng.set_option("dedup", -1)
+        # (2) uniform entities: no hot rows, worst case for the L2 and for the deduplication
+        from kprn_b200 import synth
+        ub = []
+        for b in range(4):
+            ids_u = synth.make_paths(n_paths, T=T, V_e=V_E, seed=777 + b, length_mode="realistic", entity_mode="uniform")
+            seg_u = synth.make_segments(n_paths, seed=777 + b, mode="realistic")
+            ub.append((torch.from_numpy(ids_u).cuda(), torch.from_numpy(seg_u).cuda(), len(seg_u) - 1))
+        d_scores_u = torch.empty(max(x[2] for x in ub), dtype=torch.float32, device="cuda")
+
+        def step_uniform(i):
+            a_, b_, S_ = ub[i % 4]
+            eng.forward_device(a_.data_ptr(), b_.data_ptr(), n_paths, S_, train=False, d_scores=d_scores_u.data_ptr())
+        for i in range(3):
+            step_uniform(i)
+        ms = time_device(eng, step_uniform, xs, stream, barrier)
+        ku = ub[0][0].cpu().numpy().reshape(-1, 3).astype(np.int64)
+        extras["value_uniform_entities"] = {"value": n_paths / (ms * 1e-3), "unit": "paths/s", "ms_per_step": ms, "steps": xs,
+                                            "distinct_fraction": len(np.unique((ku[:, 1] * 64 + ku[:, 0]) * 64 + ku[:, 2])) / float(ku.shape[0]),
+                                            "note": "entities ~ U{1..V_e-2} instead of Zipf(1.05); dedup on"}
+        del ub
+        # (3) the reference's own tensor layout: DoubleTensor [B,P,T,3] of 1-based ids (what the Lua shim passes, Batcher.lua:43-54)
+        Pb = 4
+        Bb = n_paths // Pb
+        f64 = []
+        for ids, _ in batches[:4]:
+            hp = engine.pinned_empty((Bb, Pb, T, 3), np.float64)
+            hp[...] = ids[:Bb * Pb].reshape(Bb, Pb, T, 3)
+            f64.append((hp, np.array(hp)))            # page-locked, pageable
+        res = {}
+        for which, name in ((0, "pinned"), (1, "pageable")):
+            for i in range(2):
+                eng.forward_f64ids(f64[i % 4][which])
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for i in range(xs):
+                eng.forward_f64ids(f64[i % 4][which])
+            torch.cuda.synchronize()
+            res[name] = Bb * Pb * xs / (time.perf_counter() - t0)
+        extras["e2e_f64ids"] = {"value": res["pinned"], "value_pageable": res["pageable"], "unit": "paths/s", "steps": xs,
+                                "h2d_bytes_per_step": int(f64[0][0].nbytes), "d2h_bytes_per_step": Bb * 4,
+                                "note": "kprn_forward_f64ids: DoubleTensor[B=%d,P=%d,T,3] host buffer (144 B/path), dense buckets" % (Bb, Pb)}
+        del f64
+
+    # ---- train: one MyOptimizer:trainBatch-equivalent step (pad rows -> zero grad -> forward -> BCE -> backward -> Adam) ----
+    train = None
+    if not args.no_train:
+        from kprn_b200 import synth
+        tprec = engine.PREC_TC_ALL if prec != engine.PREC_FP32 else engine.PREC_FP32
+        try:
+            teng = eng
+            if prec != tprec:
+                teng = engine.Engine(T=T, d_t=d_t, d_e=d_e, d_r=d_r, H=d, L=L, V_e=V_E, precision=tprec, device=local)
+                teng.init_uniform(0.1, 12345)
+                teng.set_stream(stream.cuda_stream)
+            labels = [synth.make_labels(len(seg) - 1, 12345 + b) for b, (_, seg) in enumerate(batches)]
+            pads = (6, V_E, 9)
+            ts = max(3, min(args.steps, 10))
+            losses = []
+            for i in range(2):
+                losses.append(teng.train_batch_bce(host[i % NB][0], host[i % NB][1], labels[i % NB], pad_rows=pads))
+            barrier()
+            t0 = time.perf_counter()
+            for i in range(ts):
+                losses.append(teng.train_batch_bce(host[i % NB][0], host[i % NB][1], labels[i % NB], pad_rows=pads))
+            torch.cuda.synchronize()
+            tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            t_ms = 1e3 * float(tt.item()) / ts
+            train = {"ms_per_step": t_ms, "value": world * n_paths / (t_ms * 1e-3), "unit": "paths/s", "steps": ts,
+                     "mode": "kprn_train_batch_bce, precision %d, host ids (H2D inside), dense optim.adam over %d params" % (tprec, teng.n_params),
+                     "loss_first": losses[0], "loss_last": losses[-1],
+                     "fwd_bwd_flops_per_path": 3 * flops_per_path(d_t, d_e, d_r, d)}
+            if teng is not eng:
+                teng.close()
+        except engine.KprnError as err:
+            train = {"error": str(err)}
     time.sleep(0.2)
     sampler.stop()
 
@@ -366,7 +495,7 @@ def main():
         roof = {"bound": "tensor", "unit": "TFLOP/s", "peak": peak,
                 "peak_source": pk_src + " bf16_tflops_sustained (kernels timed inside a long step)",
                 "mode": mode, "mma_multiplicity": mult,
-                "traffic": TRAFFIC.get(dom) if (d == 256 and n_paths == 65536 and prec == 1) else None, "kernels": kern,
+                "traffic": None, "kernels": kern,
                 "distinct_step_inputs": {"rows_per_batch": distinct_rows, "fraction_of_steps": distinct_frac, "dedup": dedup_on},
                 "note": "achieved = algorithmic flops (what the reference computes: every step of every path, dense D+H columns) / "
                         "CUDA-event launch time. The fused path executes fewer: type/relation lookups are hoisted into a 54-row table, "
@@ -379,6 +508,11 @@ def main():
                          "share_of_step": kern[dom]["launch_ms"] / ms_per_step})
         if "gate_phase" in kern:
             roof["gate_phase_frac"] = kern["gate_phase"]["achieved_tflops"] / peak
+        if dom and d == 256 and n_paths == 65536 and prec == 1 and args.conv == "A":
+            traffic, tsrc = profile_traffic()
+            roof["traffic"] = traffic.get(dom)
+            roof["traffic_source"] = tsrc
+            roof["traffic_all_kernels"] = traffic
         line = {"metric": "paths/sec scored", "value": value, "unit": "paths/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32" if prec == 0 else "f32 (bf16x3 split MMA, fp32 accumulate)", "data": "synthetic",
@@ -387,15 +521,47 @@ def main():
                         "d2h_bytes_per_step": d2h // args.steps},
                 "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roof,
                 "hbm": {"gather_gbs": gather_bytes_per_path(d_t, d_e, d_r) * value / world / 1e9, "peak_gbs": pk["hbm_gbs"]}}
-        if not args.no_cpu_baseline:
-            v, n_s, dt, cores = cpu_port_throughput(d, budget_s=15.0, dims=(d_t, d_e, d_r))
+        line.update(extras)
+        if train is not None:
+            line["train"] = train
+        if not args.no_cpu_baseline and world == 1:
+            v, n_s, dt, cores, ref, (s_ids, s_seg) = cpu_port_throughput(d, budget_s=15.0, dims=(d_t, d_e, d_r), keep=True)
             line["cpu_baseline"] = {"value": v, "unit": "paths/s", "cores": cores, "kind": "port",
-                                    "sample": "%d paths of the batch, fp64 C restatement + OpenMP, %.1f s" % (n_s, dt)}
+                                    "sample": "first %d paths of batch 0 (the batch the GPU arm times), fp64 C restatement + OpenMP, %.1f s" % (n_s, dt)}
+            vp, n_p, dtp, cp, _, _ = cpu_port_throughput(d, budget_s=8.0, dims=(d_t, d_e, d_r), proxy=True)
+            line["cpu_baseline_proxy"] = {"value": vp, "unit": "paths/s", "cores": cp, "kind": "proxy",
+                                          "sample": "first %d paths of batch 0, PyTorch-CPU fp64 (MKL/oneDNN addmm + elementwise), %.1f s; "
+                                                    "stand-in for Torch7+MKL, never 'Torch7'" % (n_p, dtp)}
+            # ---- parity: the GPU path against the oracle outputs of the sample just timed (same paths, same parameter values;
+            #      outside every timed region; the oracle is the checker here) ----
+            try:
+                if eng is None:
+                    eng = engine.Engine(T=T, d_t=d_t, d_e=d_e, d_r=d_r, H=d, L=L, V_e=V_E, precision=prec, device=local)
+                    eng.init_uniform(0.1, 12345)
+                    eng.zero_row(engine.TABLE_TYPE, 6); eng.zero_row(engine.TABLE_ENTITY, V_E); eng.zero_row(engine.TABLE_RELATION, 9)
+                sc_full, lg = eng.forward(s_ids, s_seg, want_logits=True)
+                pl = eng.path_logits(n_s).astype(np.float64)
+                sc = eng.forward(s_ids, s_seg).astype(np.float64)           # the scores-only path that was timed
+
+                def relerr(a_, e_):
+                    fl = np.sqrt(np.mean(e_ * e_))
+                    return float(np.max(np.abs(a_ - e_) / np.maximum(np.abs(e_), fl)))
+                line["parity"] = {"paths": int(n_s), "segments": int(len(s_seg) - 1),
+                                  "max_rel_logit": relerr(pl, ref["path_logits"]),
+                                  "max_rel_seg_logit": relerr(lg.astype(np.float64), ref["seg_logits"]),
+                                  "max_rel_score": relerr(sc, ref["scores"]),
+                                  "five_decimal_mismatches": int(sum(1 for a_, b_ in zip(sc, ref["scores"]) if "%.5f" % a_ != "%.5f" % b_)),
+                                  "tolerance": 1e-4,
+                                  "definition": "max |gpu - fp64 oracle| / max(|oracle|, rms(oracle)) over all %d x %d path logits / pooled logits / scores; "
+                                                "oracle = fp64 C restatement on the device's own parameter values (parity unpinned: Torch7 cannot run here)" % (n_s, L)}
+            except Exception as err:          # the bench line must still print
+                line["parity"] = {"error": repr(err)}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    eng.close()
+    if eng is not None:
+        eng.close()
     return 0
 
 

@@ -94,8 +94,12 @@ int kprn_set_params_f64(kprn_ctx* ctx, const double* host, int64_t n);  /* Torch
 int kprn_get_params(kprn_ctx* ctx, float* host, int64_t n);             /* saver hook OneModel.lua:393-401 */
 int kprn_get_grads(kprn_ctx* ctx, float* host, int64_t n);
 int kprn_init_uniform(kprn_ctx* ctx, float scale, uint64_t seed);       /* param:uniform(-s,s), OneModel.lua:306-309 */
-/* raw device views for the host-side NCCL all-reduce (one process per GPU) */
+/* raw device views of the flat vectors (an external optimizer / collective working on the device; replaces the flat
+ * CudaTensor views of getParameters(), MyOptimizer.lua:42).  kprn_params_device marks the parameters changed once, at the
+ * call; a caller that KEEPS the pointer and writes through it later must call kprn_params_dirty(ctx) after every write so
+ * that the tensor-core forward re-packs its bf16 operand copies (otherwise it scores with the previous values). */
 int kprn_params_device(kprn_ctx* ctx, float** dptr, int64_t* n);
+int kprn_params_dirty(kprn_ctx* ctx);
 int kprn_grads_device(kprn_ctx* ctx, float** dptr, int64_t* n);
 
 /* params[1][idx]:zero() of MyOptimizer:zeroPadTokens (MyOptimizer.lua:74-93); row is 1-based. */
@@ -152,6 +156,10 @@ int kprn_adam_step(kprn_ctx* ctx, float lr, float beta1, float beta2, float eps)
 int kprn_train_batch_bce(kprn_ctx* ctx, const int32_t* ids, const int32_t* seg_offsets, int64_t N, int64_t S,
                          const float* labels, const int64_t* pad_rows3, int32_t regularize, int32_t use_clip,
                          float clip_norm, float l2, float lr, float beta1, float beta2, float eps, float* loss);
+
+/* engine knobs (no reference counterpart; they never change results).  Keys:
+ *   "dedup"  1/0: project each distinct (type, entity, relation) step input once / every step (-1: KPRN_TC_DEDUP env, default on) */
+int kprn_set_option(kprn_ctx* ctx, const char* key, int64_t value);
 
 /* counters for bench.py: kernels launched by this library since the last reset */
 int kprn_launch_count(kprn_ctx* ctx, int64_t* n, int32_t reset);

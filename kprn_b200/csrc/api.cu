@@ -407,6 +407,11 @@ int kprn_params_device(kprn_ctx* ctx, float** dptr, int64_t* n) {
     return KPRN_OK;
 }
 
+int kprn_params_dirty(kprn_ctx* ctx) {
+    if (!ctx) { set_error("null ctx"); return KPRN_EINVAL; }
+    return params_changed(ctx);
+}
+
 int kprn_grads_device(kprn_ctx* ctx, float** dptr, int64_t* n) {
     if (!ctx || !dptr || !n) { set_error("null argument"); return KPRN_EINVAL; }
     *dptr = ctx->d_grads; *n = ctx->lay.total;
@@ -456,6 +461,8 @@ static int h2d(kprn_ctx* ctx, void* dst, const void* src, size_t bytes, size_t s
 static int forward_host_common(kprn_ctx* ctx, int64_t N, int64_t S, int32_t train, float* out_scores, float* out_logits) {
     // ids / seg are already on the device in ctx->ids_buf / ctx->seg_buf
     const kprn_config& c = ctx->cfg;
+    // a flag left by an earlier kprn_forward_device that nobody collected (kprn_sync) must not fail this call
+    KPRN_CUDA(cudaMemsetAsync(ctx->d_err, 0, sizeof(int32_t), ctx->stream));
     KPRN_TRY(forward_device_impl(ctx, ctx->ids_buf.as<int32_t>(), ctx->seg_buf.as<int32_t>(), N, S, train != 0, out_logits != nullptr, nullptr, nullptr));
     size_t need = sizeof(float) * (size_t)(S + S * c.L);
     KPRN_TRY(ensure_stage(ctx, need));
@@ -501,12 +508,19 @@ int kprn_forward_f64ids(kprn_ctx* ctx, const double* ids_f64, int64_t B, int64_t
     int64_t N = B * P, n = N * c.T * 3;
     KPRN_TRY(ensure(ctx->ids_buf, sizeof(int32_t) * n));
     KPRN_TRY(ensure(ctx->seg_buf, sizeof(int32_t) * (B + 1)));
-    KPRN_TRY(ensure(ctx->ws_dx, sizeof(double) * n));
-    KPRN_TRY(ensure_stage(ctx, sizeof(double) * n));
-    memcpy(ctx->h_stage, ids_f64, sizeof(double) * n);
-    KPRN_CUDA(cudaMemcpyAsync(ctx->ws_dx.p, ctx->h_stage, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
-    f64ids_to_i32_kernel<<<(unsigned)cdiv(n, 256), 256, 0, ctx->stream>>>(ctx->ws_dx.as<double>(), ctx->ids_buf.as<int32_t>(), n);
-    KPRN_LAUNCH_CHECK(ctx);
+    if (is_pinned(ids_f64)) {
+        // page-locked DoubleTensor storage (kprn_pinned_alloc): DMA the doubles as they are, convert on the device
+        KPRN_TRY(ensure(ctx->ws_dx, sizeof(double) * n));
+        KPRN_CUDA(cudaMemcpyAsync(ctx->ws_dx.p, ids_f64, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+        f64ids_to_i32_kernel<<<(unsigned)cdiv(n, 256), 256, 0, ctx->stream>>>(ctx->ws_dx.as<double>(), ctx->ids_buf.as<int32_t>(), n);
+        KPRN_LAUNCH_CHECK(ctx);
+    } else {
+        // pageable storage has to be staged anyway: convert while staging (half the DMA bytes, no device-side pass)
+        KPRN_TRY(ensure_stage(ctx, sizeof(int32_t) * n));
+        int32_t* st = (int32_t*)ctx->h_stage;
+        for (int64_t i = 0; i < n; ++i) st[i] = (int32_t)llrint(ids_f64[i]);
+        KPRN_CUDA(cudaMemcpyAsync(ctx->ids_buf.p, st, sizeof(int32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
+    }
     dense_seg_kernel<<<(unsigned)cdiv(B + 1, 256), 256, 0, ctx->stream>>>(ctx->seg_buf.as<int32_t>(), B, (int32_t)P);
     KPRN_LAUNCH_CHECK(ctx);
     return forward_host_common(ctx, N, B, train, out_scores, out_logits);
@@ -597,6 +611,8 @@ int kprn_loss_bpr(kprn_ctx* ctx, const int32_t* pos_seg, const int32_t* neg_seg,
 int kprn_backward(kprn_ctx* ctx, const float* grad_scores, float scale) {
     KPRN_TRY(check_ctx(ctx));
     if (!ctx->have_fwd || !ctx->have_train_cache) { set_error("backward: needs a forward with train=1 first"); return KPRN_ESTATE; }
+    // kprn_forward_device only raises the device flag on a bad id / bad segment table: read it before the scatter uses the ids
+    KPRN_TRY(check_err_flag(ctx));
     const int64_t S = ctx->S;
     if (grad_scores) {
         KPRN_TRY(ensure(ctx->dscores, sizeof(float) * S));
@@ -655,8 +671,13 @@ int kprn_grad_add_params(kprn_ctx* ctx, float l2) {
 int kprn_adam_step(kprn_ctx* ctx, float lr, float b1, float b2, float eps) {
     KPRN_TRY(check_ctx(ctx));
     const int64_t n = ctx->lay.total;
-    if (!ctx->d_m) {
+    if (!ctx->d_m || !ctx->d_v) {
+        if (ctx->d_m) { cudaFree(ctx->d_m); ctx->d_m = nullptr; }
+        if (ctx->d_v) { cudaFree(ctx->d_v); ctx->d_v = nullptr; }
         if (cudaMalloc(&ctx->d_m, sizeof(float) * n) != cudaSuccess || cudaMalloc(&ctx->d_v, sizeof(float) * n) != cudaSuccess) {
+            cudaGetLastError();
+            if (ctx->d_m) { cudaFree(ctx->d_m); ctx->d_m = nullptr; }
+            ctx->d_v = nullptr;
             set_error("adam: out of device memory for optimizer state");
             return KPRN_ENOMEM;
         }
@@ -692,6 +713,13 @@ int kprn_train_batch_bce(kprn_ctx* ctx, const int32_t* ids, const int32_t* seg, 
     KPRN_TRY(kprn_adam_step(ctx, lr, b1, b2, eps));
     for (int t = 0; t < 3 && pad3; ++t) if (pad3[t] > 0) KPRN_TRY(kprn_zero_row(ctx, t, pad3[t]));
     return KPRN_OK;
+}
+
+int kprn_set_option(kprn_ctx* ctx, const char* key, int64_t value) {
+    if (!ctx || !key) { set_error("null argument"); return KPRN_EINVAL; }
+    if (!strcmp(key, "dedup")) { ctx->opt_dedup = value < 0 ? -1 : (value != 0); return KPRN_OK; }
+    set_error("set_option: unknown key '%s'", key);
+    return KPRN_EINVAL;
 }
 
 int kprn_launch_count(kprn_ctx* ctx, int64_t* n, int32_t reset) {

@@ -62,6 +62,7 @@ struct kprn_ctx {
     struct ProfSpan { cudaEvent_t e0, e1; int slot; };
     std::vector<ProfSpan> prof_pending;
     kprn::TcState* tc = nullptr;
+    int opt_dedup = -1;                 // kprn_set_option("dedup"): -1 = KPRN_TC_DEDUP / default (on), 0 / 1 = forced
 };
 
 namespace kprn {

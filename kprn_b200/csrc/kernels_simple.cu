@@ -489,7 +489,7 @@ __global__ void rnn_cell_bwd_kernel(const float* __restrict__ act, int64_t ldact
 // LookupTable:accGradParameters -- scatter-add of dX rows.  The two tiny tables (type, relation) are reduced in
 // shared memory per block first; entity rows go straight to global float atomics (RED.ADD).
 __global__ void scatter_embed_kernel(const float* __restrict__ dX, const int32_t* __restrict__ ids, Layout l,
-                                     int d_t, int d_e, int d_r, int64_t V_t, int64_t V_r, int T, int64_t n0, int64_t CH,
+                                     int d_t, int d_e, int d_r, int64_t V_t, int64_t V_e, int64_t V_r, int T, int64_t n0, int64_t CH,
                                      int64_t rows, int rows_per_block, float* __restrict__ grads, int use_smem) {
     extern __shared__ float sm[];   // [V_t*d_t + V_r*d_r] when use_smem
     const int n_small = (int)(V_t * d_t + V_r * d_r);
@@ -503,7 +503,9 @@ __global__ void scatter_embed_kernel(const float* __restrict__ dX, const int32_t
         int t = (int)(r / CH);
         int64_t p = r % CH;
         const int32_t* id = ids + ((n0 + p) * T + t) * 3;
+        // out-of-range ids are flagged by the forward (kprn_sync / kprn_backward report them); never scatter outside the tables
         int64_t it = id[0] - 1, ie = id[1] - 1, ir = id[2] - 1;
+        if (it < 0 || it >= V_t || ie < 0 || ie >= V_e || ir < 0 || ir >= V_r) continue;
         const float* dx = dX + r * l.D;
         for (int k = threadIdx.x; k < l.D; k += blockDim.x) {
             float v = dx[k];
@@ -617,7 +619,7 @@ int simple_backward(kprn_ctx* ctx, float scale) {
             size_t smem = sizeof(float) * (size_t)(c.V_t * c.d_t + c.V_r * c.d_r);
             int use_smem = smem <= 40 * 1024;
             scatter_embed_kernel<<<(unsigned)cdiv(rows, rpb), 256, use_smem ? smem : 0, ctx->stream>>>(
-                dX, ctx->d_ids, l, c.d_t, c.d_e, c.d_r, c.V_t, c.V_r, T, n0, nb, rows, rpb, gr, use_smem);
+                dX, ctx->d_ids, l, c.d_t, c.d_e, c.d_r, c.V_t, c.V_e, c.V_r, T, n0, nb, rows, rpb, gr, use_smem);
             KPRN_LAUNCH_CHECK(ctx);
         }
     }

@@ -241,8 +241,6 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(GemmArgs a) {
     if (warp == 0) ptx::tmem_dealloc(tmem, 256);
 }
 
-static bool g_attr_set = false;
-
 // Returns KPRN_OK and sets *handled when the product ran on tensor cores.
 int tc_gemm(kprn_ctx* ctx, int64_t M, int64_t N, int64_t K, const float* A, int64_t sAm, int64_t sAk, const float* B,
             int64_t sBk, int64_t sBn, float* C, int64_t ldc, bool accumulate, int splitk, bool* handled) {
@@ -251,10 +249,8 @@ int tc_gemm(kprn_ctx* ctx, int64_t M, int64_t N, int64_t K, const float* A, int6
     if (M * N * K < (1ll << 24)) return KPRN_OK;                      // small products stay on the FFMA kernel
     if (!(sAk == 1 || sAm == 1) || !(sBk == 1 || sBn == 1)) return KPRN_OK;
     const size_t smem = G_STAGES * G_STAGE_BYTES + 256;
-    if (!g_attr_set) {
-        KPRN_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        g_attr_set = true;
-    }
+    // per-device opt-in: set on every launch (a process may hold ctxs on several devices)
+    KPRN_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (splitk < 1) splitk = 1;
     // split K until the grid covers the machine (the weight-gradient products have tiny M x N and a huge K)
     const int64_t tiles = cdiv(M, GM) * cdiv(N, GN);

@@ -82,9 +82,13 @@ bool tc_supported(const kprn_ctx* ctx) {
     return true;
 }
 
-static bool dedup_enabled() { const char* d = getenv("KPRN_TC_DEDUP"); return !(d && d[0] == '0'); }
+static bool dedup_enabled(const kprn_ctx* ctx) {
+    if (ctx->opt_dedup >= 0) return ctx->opt_dedup != 0;            // kprn_set_option(ctx, "dedup", v)
+    const char* d = getenv("KPRN_TC_DEDUP");
+    return !(d && d[0] == '0');
+}
 bool tc_validates_ids(const kprn_ctx* ctx, int64_t N) {
-    const bool dd = ctx->tc ? ctx->tc->dedup : dedup_enabled();     // the ctx latches the knob at its first forward
+    const bool dd = dedup_enabled(ctx);
     return dd && (N + TILE_M - 1) / TILE_M * TILE_M * (int64_t)ctx->cfg.T < (1ll << 30);
 }
 
@@ -1485,13 +1489,20 @@ static int tc_pack(kprn_ctx* ctx) {
     const kprn_config& c = ctx->cfg;
     const Layout& l = ctx->lay;
     if (s->packed_version == ctx->params_version) return KPRN_OK;
-    if (!s->E_hi) {
-        size_t eb = sizeof(bf16) * (size_t)c.V_e * s->KE;
-        KPRN_CUDA(cudaMalloc(&s->E_hi, eb));
-        KPRN_CUDA(cudaMalloc(&s->E_lo, eb));
-        KPRN_CUDA(cudaMalloc(&s->WxE, sizeof(bf16) * (size_t)s->NCH * s->NS * 2 * B_SLAB_ELEMS));
-        KPRN_CUDA(cudaMalloc(&s->Wh, sizeof(bf16) * (size_t)s->NCH * s->KSh * 2 * B_SLAB_ELEMS));
-        KPRN_CUDA(cudaMalloc(&s->Ptr, sizeof(float) * (size_t)c.V_t * c.V_r * s->G4));
+    if (!s->E_hi || !s->E_lo || !s->WxE || !s->Wh || !s->Ptr) {
+        // all or nothing: a failed allocation must not leave a half-built state that the next call takes for complete
+        void** ptrs[5] = {(void**)&s->E_hi, (void**)&s->E_lo, (void**)&s->WxE, (void**)&s->Wh, (void**)&s->Ptr};
+        for (void** pp : ptrs) if (*pp) { cudaFree(*pp); *pp = nullptr; }
+        const size_t eb = sizeof(bf16) * (size_t)c.V_e * s->KE;
+        const size_t sizes[5] = {eb, eb, sizeof(bf16) * (size_t)s->NCH * s->NS * 2 * B_SLAB_ELEMS,
+                                 sizeof(bf16) * (size_t)s->NCH * s->KSh * 2 * B_SLAB_ELEMS, sizeof(float) * (size_t)c.V_t * c.V_r * s->G4};
+        for (int i = 0; i < 5; ++i) {
+            cudaError_t e = cudaMalloc(ptrs[i], sizes[i]);
+            if (e != cudaSuccess) {
+                for (void** pp : ptrs) if (*pp) { cudaFree(*pp); *pp = nullptr; }
+                return cuda_fail(e, "cudaMalloc (packed operands)", __FILE__, __LINE__);
+            }
+        }
         s->have_tmaps = make_entity_tensor_maps(s, c.V_e);
     }
     int64_t ne = c.V_e * (int64_t)s->KE;
@@ -1516,11 +1527,9 @@ static size_t recur_smem(int Hp, bool pair) {
 }
 template <int HP, bool PAIR>
 static cudaError_t launch_recur(const RecurArgs& a, int64_t grid, cudaStream_t stream) {
-    static bool attr_set = false;   // per instantiation
-    if (!attr_set) {
+    {   // the opt-in is per device (a process may hold ctxs on several): set it on every launch, it costs nothing
         cudaError_t e = cudaFuncSetAttribute(recur_kernel<HP, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)recur_smem(HP, PAIR));
         if (e != cudaSuccess) return e;
-        attr_set = true;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(RECUR_THREADS); cfg.dynamicSmemBytes = recur_smem(HP, PAIR); cfg.stream = stream;
@@ -1546,10 +1555,14 @@ int tc_forward(kprn_ctx* ctx, const int32_t* d_ids, const int32_t* d_seg, int64_
         { const char* d = getenv("KPRN_TC_PAIRS"); s->use_pairs = !(d && d[0] == '0'); }
         { const char* d = getenv("KPRN_TC_GATHER4"); s->use_gather4 = !(d && d[0] == '0'); }
         { const char* d = getenv("KPRN_TC_RECUR_PAIRS"); s->recur_pairs = !(d && d[0] == '0'); }
-        s->dedup = dedup_enabled();
-        if (prop.major != 10) { set_error("tensor-core path needs sm_100 (found sm_%d%d)", prop.major, prop.minor); return KPRN_ECUDA; }
+        if (prop.major != 10) {
+            delete ctx->tc; ctx->tc = nullptr;      // a retry must meet this check again
+            set_error("tensor-core path needs sm_100 (found sm_%d%d)", prop.major, prop.minor);
+            return KPRN_ECUDA;
+        }
     }
     TcState* s = ctx->tc;
+    s->dedup = dedup_enabled(ctx);
     if (!s->attrs_set) {
         KPRN_CUDA(cudaFuncSetAttribute(proj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)proj_smem(s->KE, s->NOH)));
         KPRN_CUDA(cudaFuncSetAttribute(proj2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)proj_smem(s->KE, s->NOH)));

@@ -54,6 +54,7 @@ ABI = {
     "kprn_get_grads": [C.c_void_p, _F32P, C.c_int64],
     "kprn_init_uniform": [C.c_void_p, C.c_float, C.c_uint64],
     "kprn_params_device": [C.c_void_p, C.POINTER(C.c_void_p), _I64P],
+    "kprn_params_dirty": [C.c_void_p],
     "kprn_grads_device": [C.c_void_p, C.POINTER(C.c_void_p), _I64P],
     "kprn_zero_row": [C.c_void_p, C.c_int, C.c_int64],
     "kprn_forward": [C.c_void_p, _I32P, _I32P, C.c_int64, C.c_int64, C.c_int32, C.c_int32, _F32P, _F32P],
@@ -72,6 +73,7 @@ ABI = {
     "kprn_adam_step": [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float],
     "kprn_train_batch_bce": [C.c_void_p, _I32P, _I32P, C.c_int64, C.c_int64, _F32P, _I64P, C.c_int32, C.c_int32,
                              C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _F32P],
+    "kprn_set_option": [C.c_void_p, C.c_char_p, C.c_int64],
     "kprn_launch_count": [C.c_void_p, _I64P, C.c_int32],
     "kprn_profile": [C.c_void_p, C.c_int32],
     "kprn_profile_read": [C.c_void_p, _F32P, _I64P, C.c_int32],
@@ -190,6 +192,10 @@ class Engine:
         _chk(self.lib.kprn_params_device(self.h, C.byref(p), C.byref(n)))
         return int(p.value), int(n.value)
 
+    def params_dirty(self):
+        """After writing through a pointer kept from params_device(): the tensor-core forward must re-pack its operands."""
+        _chk(self.lib.kprn_params_dirty(self.h))
+
     def grads_device(self):
         p, n = C.c_void_p(), C.c_int64()
         _chk(self.lib.kprn_grads_device(self.h, C.byref(p), C.byref(n)))
@@ -288,6 +294,9 @@ class Engine:
 
     def sync(self):
         _chk(self.lib.kprn_sync(self.h))
+
+    def set_option(self, key, value):
+        _chk(self.lib.kprn_set_option(self.h, key.encode(), int(value)))
 
     def launch_count(self, reset=False):
         n = C.c_int64()

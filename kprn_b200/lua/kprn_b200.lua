@@ -38,6 +38,7 @@ int kprn_get_params(kprn_ctx* ctx, float* host, int64_t n);
 int kprn_get_grads(kprn_ctx* ctx, float* host, int64_t n);
 int kprn_init_uniform(kprn_ctx* ctx, float scale, uint64_t seed);
 int kprn_params_device(kprn_ctx* ctx, float** dptr, int64_t* n);
+int kprn_params_dirty(kprn_ctx* ctx);
 int kprn_grads_device(kprn_ctx* ctx, float** dptr, int64_t* n);
 int kprn_zero_row(kprn_ctx* ctx, int table, int64_t row_1based);
 int kprn_forward(kprn_ctx* ctx, const int32_t* ids, const int32_t* seg_offsets, int64_t N, int64_t S,
@@ -61,6 +62,7 @@ int kprn_adam_step(kprn_ctx* ctx, float lr, float beta1, float beta2, float eps)
 int kprn_train_batch_bce(kprn_ctx* ctx, const int32_t* ids, const int32_t* seg_offsets, int64_t N, int64_t S,
                          const float* labels, const int64_t* pad_rows3, int32_t regularize, int32_t use_clip,
                          float clip_norm, float l2, float lr, float beta1, float beta2, float eps, float* loss);
+int kprn_set_option(kprn_ctx* ctx, const char* key, int64_t value);
 int kprn_launch_count(kprn_ctx* ctx, int64_t* n, int32_t reset);
 int kprn_profile(kprn_ctx* ctx, int32_t enable);
 int kprn_profile_read(kprn_ctx* ctx, float* ms3, int64_t* n3, int32_t reset);
@@ -151,14 +153,16 @@ end
 -- updateGradInput / accGradParameters may be invoked separately (MapReduce.lua:58-71): cache the upstream
 -- gradient in the former, run BPTT once per forward in the latter.
 function Scorer:updateGradInput(input, gradOutput)
-   self._gradCached = gradOutput:float():contiguous()
+   -- gradOutput == nil: the criterion ran on the device (model:bce / model:bpr) and its gradient is cached there
+   self._gradCached = gradOutput and gradOutput:float():contiguous() or nil
    return self.gradInput
 end
 
 function Scorer:accGradParameters(input, gradOutput, scale)
    if self._didBackward then return end
    local g = (gradOutput and gradOutput:float():contiguous()) or self._gradCached
-   check(C.kprn_backward(self.ctx, g:data(), scale or 1))
+   -- nil -> NULL: kprn_backward then uses the loss gradient cached by kprn_loss_bce / kprn_loss_bpr (as nn.py does)
+   check(C.kprn_backward(self.ctx, g and g:data() or nil, scale or 1))
    self._didBackward = true
 end
 

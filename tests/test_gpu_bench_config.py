@@ -1,0 +1,81 @@
+"""Parity AT the benchmarked configuration (BASELINE.json configs[1]): d_t=d_e=d_r=H=256 (conv. A) and the reference ratio
+(conv. B), the full 2 851 220-row entity table, realistic CSR segments, Zipf and uniform entities, >= 4096 paths -- the
+tensor-core path against the fp64 oracle on path logits (all L columns), pooled logits and scores, 1e-4 relative
+(tests/util.py:assert_rel; rms floor for entries that are near zero by cancellation).
+
+The checker holds a compact entity table (the rows the batch touches) filled with exactly the values kprn_init_uniform put on
+the device (synth.device_uniform replays the device's counter-based generator), so the 2.9 GB table never leaves the GPU.
+Reference call site: SP/eval/test_from_checkpoint.lua:98-124."""
+import numpy as np
+import pytest
+
+from kprn_b200 import synth
+from oracle.kprn_oracle import Oracle
+from tests.util import assert_rel
+
+pytestmark = pytest.mark.gpu
+
+V_E = 2851220
+T, L = 6, 46
+
+
+def _sizes(e):
+    c = e.cfg
+    D, G = c.d_t + c.d_e + c.d_r, 4 * c.H
+    return {"E_t": c.V_t * c.d_t, "E_r": c.V_r * c.d_r, "Wx": G * D, "bx": G, "Wh": G * c.H, "Wo": c.L * c.H, "bo": c.L}
+
+
+def oracle_twin(e, ids, seed=12345, scale=0.1):
+    """(oracle over the compact table, its params, compact ids) for an engine initialised with init_uniform + pad rows zeroed."""
+    c = e.cfg
+    ids_c, rows = synth.compact_entities(ids)
+    o = Oracle(T=c.T, d_t=c.d_t, d_e=c.d_e, d_r=c.d_r, H=c.H, L=c.L, V_t=c.V_t, V_e=len(rows), V_r=c.V_r)
+    params = synth.compact_params(e.offsets, o.offsets, o.n_params, rows, c.d_e, _sizes(e), scale, seed,
+                                  zero_rows=[("E_t", c.V_t, c.d_t), ("E_e", c.V_e, c.d_e), ("E_r", c.V_r, c.d_r)])
+    return o, params, ids_c
+
+
+CASES = [
+    dict(name="convA-zipf", dims=(256, 256, 256, 256), n=4096, entity_mode="zipf"),
+    dict(name="convA-uniform", dims=(256, 256, 256, 256), n=4096, entity_mode="uniform"),
+    dict(name="convB-zipf", dims=(64, 128, 64, 256), n=4096, entity_mode="zipf"),
+    dict(name="convA-zipf-ragged", dims=(256, 256, 256, 256), n=4500, entity_mode="zipf"),      # last tile ragged, > 32 tiles
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_bench_config_matches_oracle(case):
+    from kprn_b200 import engine
+    d_t, d_e, d_r, H = case["dims"]
+    n = case["n"]
+    e = engine.Engine(T=T, d_t=d_t, d_e=d_e, d_r=d_r, H=H, L=L, V_e=V_E, precision=engine.PREC_TC_SPLIT)
+    e.init_uniform(0.1, 12345)
+    e.zero_row(engine.TABLE_TYPE, 6); e.zero_row(engine.TABLE_ENTITY, V_E); e.zero_row(engine.TABLE_RELATION, 9)
+    ids = synth.make_paths(n, T=T, V_e=V_E, seed=12345, length_mode="realistic", entity_mode=case["entity_mode"])
+    seg = synth.make_segments(n, seed=12345, mode="realistic")
+    o, params, ids_c = oracle_twin(e, ids)
+    ref = o.forward(params, ids_c, seg)
+    scores, logits = e.forward(ids, seg, want_logits=True)
+    pl = e.path_logits(n)
+    assert_rel(pl, ref["path_logits"], what="path_logits (all L columns)")
+    assert_rel(logits, ref["seg_logits"], what="seg_logits")
+    assert_rel(scores, ref["scores"], what="scores")
+    # the scores-only fast path (head fused into the recurrence's last-step epilogue) -- the path bench.py times
+    s2 = e.forward(ids, seg)
+    assert_rel(s2, ref["scores"], what="scores, scores-only path")
+    cls = e.forward(ids, seg, want_logits=True)[1][:, 0]
+    assert_rel(cls, ref["seg_logits"][:, 0], what="class logit")
+    # %.5f strings as test_from_checkpoint.lua:112 prints them
+    mism = sum(1 for a, b in zip(s2, ref["scores"]) if "%.5f" % a != "%.5f" % b)
+    assert mism <= max(1, len(s2) // 2000), "%d of %d five-decimal score strings differ" % (mism, len(s2))
+    e.close()
+
+
+def test_device_uniform_replays_the_device_generator():
+    from kprn_b200 import engine
+    e = engine.Engine(T=T, d_t=8, d_e=16, d_r=8, H=16, L=L, V_e=1000, precision=engine.PREC_FP32)
+    e.init_uniform(0.1, 777)
+    p = e.get_params()
+    q = synth.device_uniform(np.arange(p.size), 0.1, 777)
+    assert np.array_equal(p, q)
+    e.close()

@@ -9,7 +9,7 @@ for kw in (dict(N=333, seed=33, d_t=50, d_e=100, d_r=50, H=250, V_e=3000), dict(
     ref = o.forward(params, ids, seg, cache=True)
     loss_ref, dsc = o.bce(ref["scores"], labels)
     g_ref = o.backward(params, ids, seg, ref, dsc)
-    for prec in (0, 1):
+    for prec in (0, 3):
         e = engine_for(o, precision=prec)
         e.set_params(params); e.zero_grad()
         e.forward(ids, seg, train=True); e.loss_bce(labels); e.backward()

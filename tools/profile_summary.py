@@ -40,5 +40,17 @@ if rep:
     for i, name in enumerate(h):
         if name in want and name != "Kernel Name":
             out.write("| %s | %s | %s |\n" % (name, rr[1][i], " | ".join(r[i] for r in rr[2:])))
+    # machine-readable DRAM traffic per launch for bench.py's roofline.traffic (it reads the newest profiles/*_traffic.json)
+    import json
+    ni, ri, wi = h.index("Kernel Name"), h.index("dram__bytes_read.sum"), h.index("dram__bytes_write.sum")
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    kern = {}
+    for r in rr[2:]:
+        nm = r[ni].split("(")[0]
+        key = "proj" if "proj" in nm else ("recur" if "recur" in nm else nm[:32])
+        kern[key] = {"name": nm[:64], "dram_read_bytes": float(r[ri].replace(",", "")) * scale.get(rr[1][ri], 1.0),
+                     "dram_write_bytes": float(r[wi].replace(",", "")) * scale.get(rr[1][wi], 1.0)}
+    json.dump({"source": "profiles/%s_summary.md (ncu --set full, one launch per kernel)" % tag, "kernels": kern},
+              open(os.path.join(ROOT, "profiles", "%s_traffic.json" % tag), "w"), indent=1)
 out.close()
 print(open(os.path.join(ROOT, "profiles", "%s_summary.md" % tag)).read())
