@@ -11,8 +11,7 @@
  * turns it into error(), Torch7's convention).  Host pointers are owned by the caller and
  * are not retained after the call returns.  Device memory is owned by the ctx.  A ctx is
  * bound to one CUDA device and is not re-entrant; one ctx per host thread / Lua state.
- * One process per GPU; multi-GPU runs exchange only the buffers exposed by
- * kprn_params_device / kprn_grads_device (host side: NCCL all-reduce).
+ * One process per GPU; multi-GPU runs go through the ctx's NCCL communicator (kprn_comm_*).
  *
  * There is NO CPU fallback: if no CUDA device is usable every call fails with KPRN_ECUDA.
  */
@@ -152,10 +151,62 @@ int kprn_grad_add_params(kprn_ctx* ctx, float l2);      /* gradParameters:add(l2
 /* optim.adam on the flat vector (OneModel.lua:340-355, MyOptimizer.lua:218); dense like the reference. */
 int kprn_adam_step(kprn_ctx* ctx, float lr, float beta1, float beta2, float eps);
 /* one whole MyOptimizer:trainBatch (MyOptimizer.lua:177-221) with BCE: zero pad rows -> zero grad ->
- * forward -> BCE -> backward -> [clip + l2] -> Adam -> zero pad rows.  pad_rows[3] 1-based, 0 = none. */
+ * forward -> BCE -> backward -> [clip + l2] -> Adam -> zero pad rows.  pad_rows[3] 1-based, 0 = none.
+ * (= kprn_train_step with default options: row-sparse evaluation, same results.) */
 int kprn_train_batch_bce(kprn_ctx* ctx, const int32_t* ids, const int32_t* seg_offsets, int64_t N, int64_t S,
                          const float* labels, const int64_t* pad_rows3, int32_t regularize, int32_t use_clip,
                          float clip_norm, float l2, float lr, float beta1, float beta2, float eps, float* loss);
+
+/* nn.BPRLoss flavour of the same step (SP/model/criterion/BPRLoss.lua:18-32 on pooled scores; BASELINE configs[3]):
+ * pos_seg/neg_seg[n_pairs] are 0-based segment indices of the batch, paired element-wise. */
+int kprn_train_batch_bpr(kprn_ctx* ctx, const int32_t* ids, const int32_t* seg_offsets, int64_t N, int64_t S,
+                         const int32_t* pos_seg, const int32_t* neg_seg, int64_t n_pairs, int32_t apply_to_logits,
+                         const int64_t* pad_rows3, int32_t regularize, int32_t use_clip, float clip_norm, float l2, float lr,
+                         float beta1, float beta2, float eps, float* loss);
+
+/* The general form of MyOptimizer:trainBatch (MyOptimizer.lua:177-221).  By default the 2.85 M-row entity table is handled
+ * row-sparsely WITHOUT changing the result: the entity gradient is kept per distinct row of the batch, and optim.adam's
+ * dense update (rows without gradient still decay and move) is evaluated lazily -- replayed, with the same arithmetic, the
+ * next time a row is read, or by any call that exposes the parameters (scoring forward, kprn_get_params, ...).
+ * dense = 1 runs the reference's flow literally (dense gradient, dense Adam); it is also what l2 != 0 falls back to. */
+typedef struct kprn_train_opts {
+    int32_t loss;           /* 0 = nn.BCECriterion on labels[S]; 1 = nn.BPRLoss on (pos_seg, neg_seg) pairs */
+    int32_t bpr_on_logits;  /* BPR on the pooled class logits instead of the sigmoid scores */
+    int32_t regularize;     /* MyOptimizer.lua:196: clip and l2 apply only when set (shipped config: 0) */
+    int32_t use_clip;
+    float clip_norm, l2;
+    float lr, beta1, beta2, eps;   /* optim.adam (OneModel.lua:340-355) */
+    float grad_scale;       /* multiplies dL/dscore; S_local / S_global when this batch is one rank's shard of a step (0 = 1) */
+    int32_t dense;          /* 1 = reference-literal dense flow */
+    int32_t reserved[4];
+} kprn_train_opts;
+int kprn_train_step(kprn_ctx* ctx, const int32_t* ids, const int32_t* seg_offsets, int64_t N, int64_t S, const float* labels,
+                    const int32_t* pos_seg, const int32_t* neg_seg, int64_t n_pairs, const int64_t* pad_rows3,
+                    const kprn_train_opts* opts, float* loss);
+/* the same with the batch already resident in HBM; asynchronous on the ctx stream when single-GPU (with a communicator the
+ * row exchange needs one host round trip).  The loss stays on the device until kprn_last_loss. */
+int kprn_train_step_device(kprn_ctx* ctx, const int32_t* d_ids, const int32_t* d_seg_offsets, int64_t N, int64_t S,
+                           const float* d_labels, const int32_t* d_pos_seg, const int32_t* d_neg_seg, int64_t n_pairs,
+                           const int64_t* pad_rows3, const kprn_train_opts* opts);
+int kprn_last_loss(kprn_ctx* ctx, float* loss);
+/* distinct entity rows of the last training batch on this rank / in the union over ranks / rows moved by the all-gather */
+int kprn_train_info(kprn_ctx* ctx, int64_t* rows_local, int64_t* rows_union, int64_t* rows_gathered);
+
+/*
+ * Multi-GPU: one process per GPU, an NCCL communicator owned by the ctx (the reference is single-device,
+ * OneModel.lua:173-179).  Rank 0 calls kprn_comm_unique_id and ships the 128 bytes to the other processes (a file, a
+ * socket, torch.distributed ...); every rank then calls kprn_comm_init.  NCCL is bound at run time (libnccl.so.2).
+ * With a communicator, kprn_train_step* all-reduces the small tensors' gradients (~4 MB) and all-gathers the entity-row
+ * gradients (row ids + rows); every rank reduces each row's contributions in rank order and applies the same update, so
+ * replicas stay bit-identical.  Scoring shards by (user,item) segment and needs no collective.
+ */
+int kprn_comm_unique_id(void* id128);
+int kprn_comm_init(kprn_ctx* ctx, int32_t rank, int32_t world, const void* id128);
+int kprn_comm_destroy(kprn_ctx* ctx);
+int kprn_comm_info(kprn_ctx* ctx, int32_t* rank, int32_t* world, int64_t* bytes_moved, int64_t* collective_calls, int32_t reset);
+int kprn_broadcast_params(kprn_ctx* ctx, int32_t root);                 /* replicas start from rank `root`'s parameters */
+int kprn_allreduce_grads(kprn_ctx* ctx, int32_t average);               /* dense flat gradient, one ncclAllReduce (reference-style flow) */
+int kprn_allreduce_host_f64(kprn_ctx* ctx, double* vals, int64_t n, int32_t op_max);   /* loss / counters: n <= 64 host doubles, sum or max */
 
 /* engine knobs (no reference counterpart; they never change results).  Keys:
  *   "dedup"  1/0: project each distinct (type, entity, relation) step input once / every step (-1: KPRN_TC_DEDUP env, default on) */

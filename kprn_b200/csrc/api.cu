@@ -7,6 +7,7 @@
 
 #include <new>
 
+#include "adam.cuh"
 #include "common.cuh"
 
 namespace kprn {
@@ -133,11 +134,9 @@ __global__ void sumsq_kernel(const float* __restrict__ x, int64_t n, double* __r
 __global__ void adam_kernel(float* __restrict__ x, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                             int64_t n, float step, float b1, float b2, float eps) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        float gi = g[i];
-        float mi = fmaf(b1, m[i], (1.f - b1) * gi);
-        float vi = fmaf(b2, v[i], (1.f - b2) * gi * gi);
-        m[i] = mi; v[i] = vi;
-        x[i] -= step * mi / (sqrtf(vi) + eps);
+        float xi = x[i], mi = m[i], vi = v[i];
+        adam_elem(xi, mi, vi, g[i], step, b1, b2, eps);
+        x[i] = xi; m[i] = mi; v[i] = vi;
     }
 }
 // nn.BCECriterion (eps 1e-12, sizeAverage) + chain through nn.Sigmoid/nn.Select: writes dL/dlse_c.
@@ -157,11 +156,12 @@ __global__ void bce_kernel(const float* __restrict__ p, const float* __restrict_
 // nn.BPRLoss (criterion/BPRLoss.lua:18-32): out = sigmoid(pos-neg)+1e-4; err = -mean(log out);
 // gradInput = {-(1-out), +(1-out)} (not divided by n).  Chained to dL/dlse_c.
 __global__ void bpr_kernel(const float* __restrict__ scores, const float* __restrict__ seg_logits, int L, int cls,
-                           const int32_t* __restrict__ pos, const int32_t* __restrict__ neg, int64_t n, int on_logits,
+                           const int32_t* __restrict__ pos, const int32_t* __restrict__ neg, int64_t n, int on_logits, int64_t S,
                            double* __restrict__ loss, float* __restrict__ dlse) {
     double acc = 0.0;
     for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
         int32_t a = pos[k], b = neg[k];
+        if (a < 0 || a >= S || b < 0 || b >= S) continue;       // flagged by check_pairs_kernel
         float va, vb;
         if (on_logits) { va = seg_logits[(int64_t)a * L + cls]; vb = seg_logits[(int64_t)b * L + cls]; }
         else { va = scores[a]; vb = scores[b]; }
@@ -209,7 +209,8 @@ static int check_err_flag(kprn_ctx* ctx) {
     KPRN_CUDA(cudaStreamSynchronize(ctx->stream));
     if (flag) {
         KPRN_CUDA(cudaMemsetAsync(ctx->d_err, 0, sizeof(int32_t), ctx->stream));
-        set_error(flag == 1 ? "id out of range (ids are 1-based; nn.LookupTable would raise)" : "bad segment offsets");
+        set_error(flag == 1 ? "id out of range (ids are 1-based; nn.LookupTable would raise)"
+                            : (flag == 3 ? "BPR pair: segment index out of range" : "bad segment offsets"));
         ctx->have_fwd = false;
         return KPRN_EINVAL;
     }
@@ -218,11 +219,12 @@ static int check_err_flag(kprn_ctx* ctx) {
 
 static int params_changed(kprn_ctx* ctx) { ctx->params_version++; return KPRN_OK; }
 
-static int forward_device_impl(kprn_ctx* ctx, const int32_t* d_ids, const int32_t* d_seg, int64_t N, int64_t S,
+int forward_device_impl(kprn_ctx* ctx, const int32_t* d_ids, const int32_t* d_seg, int64_t N, int64_t S,
                                bool train, bool want_logits, float* d_out_scores, float* d_out_logits) {
     const kprn_config& c = ctx->cfg;
     if (N <= 0 || S <= 0) { set_error("empty batch: N=%lld S=%lld", (long long)N, (long long)S); return KPRN_EINVAL; }
     if (N * (int64_t)c.T * 3 >= (1ll << 40)) { set_error("batch too large"); return KPRN_EINVAL; }
+    if (!ctx->in_train_step) KPRN_TRY(train_flush(ctx));     // rows a sparse training step left behind (train.cu) must be current
     // the fused tensor-core forward validates the ids inside its first kernel (the deduplication's hash insert)
     if (!(!train && c.precision != KPRN_PREC_FP32 && tc_supported(ctx) && tc_validates_ids(ctx, N))) {
         validate_ids_kernel2<<<(unsigned)cdiv(N * c.T, 256), 256, 0, ctx->stream>>>(d_ids, N * c.T, c.V_t, c.V_e, c.V_r, ctx->d_err);
@@ -308,7 +310,10 @@ int kprn_destroy(kprn_ctx* ctx) {
     if (!ctx) return KPRN_OK;
     cudaSetDevice(ctx->device);
     if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
+    kprn_comm_destroy(ctx);
+    train_destroy(ctx);
     tc_destroy(ctx);
+    if (ctx->tmp_comm.p) cudaFree(ctx->tmp_comm.p);
     DBuf* bufs[] = {&ctx->ids_buf, &ctx->seg_buf, &ctx->path_logits, &ctx->seg_logits, &ctx->scores, &ctx->dscores,
                     &ctx->dseg_logits, &ctx->labels, &ctx->tmp_small, &ctx->act, &ctx->cst, &ctx->hst, &ctx->z1,
                     &ctx->ws_x, &ctx->ws_xw, &ctx->ws_h0, &ctx->ws_h1, &ctx->ws_c, &ctx->ws_dg, &ctx->ws_dx,
@@ -355,6 +360,7 @@ int kprn_param_offsets(kprn_ctx* ctx, int64_t* o) {
 
 int kprn_set_params(kprn_ctx* ctx, const float* host, int64_t n) {
     KPRN_TRY(check_ctx(ctx));
+    KPRN_TRY(train_flush(ctx));       // rows a sparse training step left behind are brought up to date first
     if (!host || n != ctx->lay.total) { set_error("set_params: expected %lld floats", (long long)ctx->lay.total); return KPRN_EINVAL; }
     KPRN_CUDA(cudaMemcpyAsync(ctx->d_params, host, sizeof(float) * n, cudaMemcpyHostToDevice, ctx->stream));
     KPRN_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -363,6 +369,7 @@ int kprn_set_params(kprn_ctx* ctx, const float* host, int64_t n) {
 
 int kprn_set_params_f64(kprn_ctx* ctx, const double* host, int64_t n) {
     KPRN_TRY(check_ctx(ctx));
+    KPRN_TRY(train_flush(ctx));       // rows a sparse training step left behind are brought up to date first
     if (!host || n != ctx->lay.total) { set_error("set_params_f64: expected %lld doubles", (long long)ctx->lay.total); return KPRN_EINVAL; }
     const int64_t chunk = 1ll << 24;
     KPRN_TRY(ensure(ctx->ws_dx, sizeof(double) * (size_t)(n < chunk ? n : chunk)));
@@ -378,6 +385,7 @@ int kprn_set_params_f64(kprn_ctx* ctx, const double* host, int64_t n) {
 
 int kprn_get_params(kprn_ctx* ctx, float* host, int64_t n) {
     KPRN_TRY(check_ctx(ctx));
+    KPRN_TRY(train_flush(ctx));       // rows a sparse training step left behind are brought up to date first
     if (!host || n != ctx->lay.total) { set_error("get_params: expected %lld floats", (long long)ctx->lay.total); return KPRN_EINVAL; }
     KPRN_CUDA(cudaMemcpyAsync(host, ctx->d_params, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
     KPRN_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -386,6 +394,7 @@ int kprn_get_params(kprn_ctx* ctx, float* host, int64_t n) {
 
 int kprn_get_grads(kprn_ctx* ctx, float* host, int64_t n) {
     KPRN_TRY(check_ctx(ctx));
+    KPRN_TRY(train_materialize_grads(ctx));   // dense view of a sparse step's entity gradient
     if (!host || n != ctx->lay.total) { set_error("get_grads: expected %lld floats", (long long)ctx->lay.total); return KPRN_EINVAL; }
     KPRN_CUDA(cudaMemcpyAsync(host, ctx->d_grads, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
     KPRN_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -394,6 +403,7 @@ int kprn_get_grads(kprn_ctx* ctx, float* host, int64_t n) {
 
 int kprn_init_uniform(kprn_ctx* ctx, float scale, uint64_t seed) {
     KPRN_TRY(check_ctx(ctx));
+    KPRN_TRY(train_flush(ctx));       // rows a sparse training step left behind are brought up to date first
     int64_t n = ctx->lay.total;
     init_uniform_kernel<<<(unsigned)cdiv(n, 256), 256, 0, ctx->stream>>>(ctx->d_params, n, scale, seed);
     KPRN_LAUNCH_CHECK(ctx);
@@ -402,6 +412,8 @@ int kprn_init_uniform(kprn_ctx* ctx, float scale, uint64_t seed) {
 
 int kprn_params_device(kprn_ctx* ctx, float** dptr, int64_t* n) {
     if (!ctx || !dptr || !n) { set_error("null argument"); return KPRN_EINVAL; }
+    KPRN_TRY(check_ctx(ctx));
+    KPRN_TRY(train_flush(ctx));
     *dptr = ctx->d_params; *n = ctx->lay.total;
     ctx->params_version++;   // the caller may write through the pointer
     return KPRN_OK;
@@ -414,12 +426,15 @@ int kprn_params_dirty(kprn_ctx* ctx) {
 
 int kprn_grads_device(kprn_ctx* ctx, float** dptr, int64_t* n) {
     if (!ctx || !dptr || !n) { set_error("null argument"); return KPRN_EINVAL; }
+    KPRN_TRY(check_ctx(ctx));
+    KPRN_TRY(train_materialize_grads(ctx));
     *dptr = ctx->d_grads; *n = ctx->lay.total;
     return KPRN_OK;
 }
 
 int kprn_zero_row(kprn_ctx* ctx, int table, int64_t row) {
     KPRN_TRY(check_ctx(ctx));
+    KPRN_TRY(train_flush(ctx));       // rows a sparse training step left behind are brought up to date first
     const kprn_config& c = ctx->cfg;
     int64_t V, off; int d;
     switch (table) {
@@ -440,6 +455,8 @@ int kprn_forward_device(kprn_ctx* ctx, const int32_t* d_ids, const int32_t* d_se
     return forward_device_impl(ctx, d_ids, d_seg, N, S, train != 0, d_out_logits != nullptr, d_out_scores, d_out_logits);
 }
 
+}  // extern "C"
+namespace kprn {
 static bool is_pinned(const void* p) {
     cudaPointerAttributes attr;
     if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) { cudaGetLastError(); return false; }
@@ -447,7 +464,7 @@ static bool is_pinned(const void* p) {
 }
 
 // host -> device copy on the ctx stream; pageable sources go through the ctx's pinned staging buffer at `stage_off`
-static int h2d(kprn_ctx* ctx, void* dst, const void* src, size_t bytes, size_t stage_off) {
+int host_to_device(kprn_ctx* ctx, void* dst, const void* src, size_t bytes, size_t stage_off) {
     if (is_pinned(src)) {
         KPRN_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
         return KPRN_OK;
@@ -457,6 +474,8 @@ static int h2d(kprn_ctx* ctx, void* dst, const void* src, size_t bytes, size_t s
     KPRN_CUDA(cudaMemcpyAsync(dst, (char*)ctx->h_stage + stage_off, bytes, cudaMemcpyHostToDevice, ctx->stream));
     return KPRN_OK;
 }
+}  // namespace kprn
+extern "C" {
 
 static int forward_host_common(kprn_ctx* ctx, int64_t N, int64_t S, int32_t train, float* out_scores, float* out_logits) {
     // ids / seg are already on the device in ctx->ids_buf / ctx->seg_buf
@@ -490,9 +509,9 @@ int kprn_forward(kprn_ctx* ctx, const int32_t* ids, const int32_t* seg_offsets, 
     KPRN_TRY(ensure(ctx->seg_buf, seg_bytes));
     // pinned caller memory is DMA'd directly; pageable memory is staged through pinned memory first
     if (!is_pinned(ids) || (seg_offsets && !is_pinned(seg_offsets))) KPRN_TRY(ensure_stage(ctx, ids_bytes + seg_bytes));
-    KPRN_TRY(h2d(ctx, ctx->ids_buf.p, ids, ids_bytes, 0));
+    KPRN_TRY(host_to_device(ctx, ctx->ids_buf.p, ids, ids_bytes, 0));
     if (seg_offsets) {
-        KPRN_TRY(h2d(ctx, ctx->seg_buf.p, seg_offsets, seg_bytes, ids_bytes));
+        KPRN_TRY(host_to_device(ctx, ctx->seg_buf.p, seg_offsets, seg_bytes, ids_bytes));
     } else {
         dense_seg_kernel<<<(unsigned)cdiv(S + 1, 256), 256, 0, ctx->stream>>>(ctx->seg_buf.as<int32_t>(), S, paths_per_seg);
         KPRN_LAUNCH_CHECK(ctx);
@@ -556,7 +575,10 @@ static int read_loss(kprn_ctx* ctx, double* d_loss, float* loss) {
     return KPRN_OK;
 }
 
-static int loss_bce_device(kprn_ctx* ctx, const float* d_labels, int64_t S, double** d_loss_out) {
+}  // extern "C"
+namespace kprn {
+int loss_bce_device(kprn_ctx* ctx, const float* d_labels, int64_t S, double** d_loss_out) {
+    if (S != ctx->S) { set_error("loss_bce: expected %lld labels", (long long)ctx->S); return KPRN_EINVAL; }
     KPRN_TRY(ensure(ctx->dscores, sizeof(float) * S));
     KPRN_TRY(ensure(ctx->tmp_small, 64));
     double* d_loss = ctx->tmp_small.as<double>();
@@ -568,6 +590,38 @@ static int loss_bce_device(kprn_ctx* ctx, const float* d_labels, int64_t S, doub
     *d_loss_out = d_loss;
     return KPRN_OK;
 }
+
+__global__ void check_pairs_kernel(const int32_t* __restrict__ a, const int32_t* __restrict__ b, int64_t n, int64_t S, int32_t* err) {
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n && (a[k] < 0 || a[k] >= S || b[k] < 0 || b[k] >= S)) atomicExch(err, 3);
+}
+
+// nn.BPRLoss on device-resident pair lists (0-based segment indices); bad indices raise the device error flag
+int loss_bpr_device(kprn_ctx* ctx, const int32_t* d_pos, const int32_t* d_neg, int64_t n_pairs, int on_logits, double** d_loss_out) {
+    const int64_t S = ctx->S;
+    KPRN_TRY(ensure(ctx->dscores, sizeof(float) * S));
+    KPRN_TRY(ensure(ctx->tmp_small, 64));
+    double* d_loss = ctx->tmp_small.as<double>();
+    KPRN_CUDA(cudaMemsetAsync(d_loss, 0, sizeof(double), ctx->stream));
+    KPRN_CUDA(cudaMemsetAsync(ctx->dscores.p, 0, sizeof(float) * S, ctx->stream));
+    check_pairs_kernel<<<(unsigned)cdiv(n_pairs, 256), 256, 0, ctx->stream>>>(d_pos, d_neg, n_pairs, S, ctx->d_err);
+    KPRN_LAUNCH_CHECK(ctx);
+    bpr_kernel<<<(unsigned)(cdiv(n_pairs, 256) < 592 ? cdiv(n_pairs, 256) : 592), 256, 0, ctx->stream>>>(
+        ctx->scores.as<float>(), ctx->seg_logits.as<float>(), ctx->cfg.L, ctx->cfg.class_id - 1, d_pos, d_neg, n_pairs,
+        on_logits, S, d_loss, ctx->dscores.as<float>());
+    KPRN_LAUNCH_CHECK(ctx);
+    ctx->have_loss_grad = true;
+    *d_loss_out = d_loss;
+    return KPRN_OK;
+}
+
+int backward_device(kprn_ctx* ctx, float scale) {
+    if (!ctx->have_fwd || !ctx->have_train_cache) { set_error("backward: needs a forward with train=1 first"); return KPRN_ESTATE; }
+    if (!ctx->have_loss_grad) { set_error("backward: no loss gradient (call kprn_loss_* first or pass grad_scores)"); return KPRN_ESTATE; }
+    return simple_backward(ctx, scale);
+}
+}  // namespace kprn
+extern "C" {
 
 int kprn_loss_bce(kprn_ctx* ctx, const float* labels, int64_t S, float* loss) {
     KPRN_TRY(check_ctx(ctx));
@@ -590,21 +644,12 @@ int kprn_loss_bpr(kprn_ctx* ctx, const int32_t* pos_seg, const int32_t* neg_seg,
             set_error("loss_bpr: segment index out of range at pair %lld", (long long)i);
             return KPRN_EINVAL;
         }
-    const int64_t S = ctx->S;
-    KPRN_TRY(ensure(ctx->dscores, sizeof(float) * S));
     KPRN_TRY(ensure(ctx->pair_buf, sizeof(int32_t) * 2 * n_pairs));
-    KPRN_TRY(ensure(ctx->tmp_small, 64));
     int32_t* dp = ctx->pair_buf.as<int32_t>();
     KPRN_CUDA(cudaMemcpyAsync(dp, pos_seg, sizeof(int32_t) * n_pairs, cudaMemcpyHostToDevice, ctx->stream));
     KPRN_CUDA(cudaMemcpyAsync(dp + n_pairs, neg_seg, sizeof(int32_t) * n_pairs, cudaMemcpyHostToDevice, ctx->stream));
-    double* d_loss = ctx->tmp_small.as<double>();
-    KPRN_CUDA(cudaMemsetAsync(d_loss, 0, sizeof(double), ctx->stream));
-    KPRN_CUDA(cudaMemsetAsync(ctx->dscores.p, 0, sizeof(float) * S, ctx->stream));
-    bpr_kernel<<<(unsigned)(cdiv(n_pairs, 256) < 592 ? cdiv(n_pairs, 256) : 592), 256, 0, ctx->stream>>>(
-        ctx->scores.as<float>(), ctx->seg_logits.as<float>(), ctx->cfg.L, ctx->cfg.class_id - 1, dp, dp + n_pairs, n_pairs,
-        on_logits, d_loss, ctx->dscores.as<float>());
-    KPRN_LAUNCH_CHECK(ctx);
-    ctx->have_loss_grad = true;
+    double* d_loss = nullptr;
+    KPRN_TRY(loss_bpr_device(ctx, dp, dp + n_pairs, n_pairs, on_logits, &d_loss));
     return read_loss(ctx, d_loss, loss);
 }
 
@@ -621,16 +666,19 @@ int kprn_backward(kprn_ctx* ctx, const float* grad_scores, float scale) {
         chain_scores_kernel<<<(unsigned)cdiv(S, 256), 256, 0, ctx->stream>>>(ctx->scores.as<float>(), ctx->labels.as<float>(), S,
                                                                             ctx->dscores.as<float>());
         KPRN_LAUNCH_CHECK(ctx);
+        ctx->have_loss_grad = true;
     } else if (!ctx->have_loss_grad) {
         set_error("backward: no cached loss gradient (call kprn_loss_* first or pass grad_scores)");
         return KPRN_ESTATE;
     }
-    KPRN_TRY(simple_backward(ctx, scale));
-    return KPRN_OK;
+    // reference-style flow (zeroGradParameters / backward / getParameters): the gradient accumulates in the dense flat buffer
+    KPRN_TRY(train_materialize_grads(ctx));
+    return backward_device(ctx, scale);
 }
 
 int kprn_zero_grad(kprn_ctx* ctx) {
     KPRN_TRY(check_ctx(ctx));
+    KPRN_TRY(train_materialize_grads(ctx));   // leaves the sparse state; the memset below then clears everything
     KPRN_CUDA(cudaMemsetAsync(ctx->d_grads, 0, sizeof(float) * (size_t)ctx->lay.total, ctx->stream));
     return KPRN_OK;
 }
@@ -650,12 +698,14 @@ static int grad_norm_device(kprn_ctx* ctx, float* norm) {
 
 int kprn_grad_norm(kprn_ctx* ctx, float* norm) {
     KPRN_TRY(check_ctx(ctx));
+    KPRN_TRY(train_materialize_grads(ctx));   // dense view of a sparse step's entity gradient
     if (!norm) { set_error("null argument"); return KPRN_EINVAL; }
     return grad_norm_device(ctx, norm);
 }
 
 int kprn_grad_scale(kprn_ctx* ctx, float s) {
     KPRN_TRY(check_ctx(ctx));
+    KPRN_TRY(train_materialize_grads(ctx));   // dense view of a sparse step's entity gradient
     scale_kernel<<<1184, 256, 0, ctx->stream>>>(ctx->d_grads, ctx->lay.total, s);
     KPRN_LAUNCH_CHECK(ctx);
     return KPRN_OK;
@@ -663,6 +713,7 @@ int kprn_grad_scale(kprn_ctx* ctx, float s) {
 
 int kprn_grad_add_params(kprn_ctx* ctx, float l2) {
     KPRN_TRY(check_ctx(ctx));
+    KPRN_TRY(train_materialize_grads(ctx));   // dense view of a sparse step's entity gradient
     axpy_kernel<<<1184, 256, 0, ctx->stream>>>(ctx->d_grads, ctx->d_params, ctx->lay.total, l2);
     KPRN_LAUNCH_CHECK(ctx);
     return KPRN_OK;
@@ -671,6 +722,8 @@ int kprn_grad_add_params(kprn_ctx* ctx, float l2) {
 int kprn_adam_step(kprn_ctx* ctx, float lr, float b1, float b2, float eps) {
     KPRN_TRY(check_ctx(ctx));
     const int64_t n = ctx->lay.total;
+    KPRN_TRY(train_flush(ctx));               // the dense kernel assumes every row's (x, m, v) is current
+    KPRN_TRY(train_materialize_grads(ctx));
     if (!ctx->d_m || !ctx->d_v) {
         if (ctx->d_m) { cudaFree(ctx->d_m); ctx->d_m = nullptr; }
         if (ctx->d_v) { cudaFree(ctx->d_v); ctx->d_v = nullptr; }
@@ -689,30 +742,32 @@ int kprn_adam_step(kprn_ctx* ctx, float lr, float b1, float b2, float eps) {
     float step = (float)((double)lr * sqrt(bc2) / bc1);
     adam_kernel<<<1184, 256, 0, ctx->stream>>>(ctx->d_params, ctx->d_grads, ctx->d_m, ctx->d_v, n, step, b1, b2, eps);
     KPRN_LAUNCH_CHECK(ctx);
+    KPRN_TRY(train_note_dense_step(ctx, step));
     return params_changed(ctx);
+}
+
+static void batch_opts(kprn_train_opts& o, int loss, int32_t regularize, int32_t use_clip, float clip_norm, float l2, float lr, float b1,
+                       float b2, float eps) {
+    memset(&o, 0, sizeof(o));
+    o.loss = loss; o.regularize = regularize; o.use_clip = use_clip; o.clip_norm = clip_norm; o.l2 = l2;
+    o.lr = lr; o.beta1 = b1; o.beta2 = b2; o.eps = eps; o.grad_scale = 1.f;
 }
 
 int kprn_train_batch_bce(kprn_ctx* ctx, const int32_t* ids, const int32_t* seg, int64_t N, int64_t S, const float* labels,
                          const int64_t* pad3, int32_t regularize, int32_t use_clip, float clip_norm, float l2, float lr,
                          float b1, float b2, float eps, float* loss) {
-    KPRN_TRY(check_ctx(ctx));
-    if (!labels) { set_error("train_batch: null labels"); return KPRN_EINVAL; }
-    for (int t = 0; t < 3 && pad3; ++t) if (pad3[t] > 0) KPRN_TRY(kprn_zero_row(ctx, t, pad3[t]));
-    KPRN_TRY(kprn_zero_grad(ctx));
-    KPRN_TRY(kprn_forward(ctx, ids, seg, N, S, 0, 1, nullptr, nullptr));
-    KPRN_TRY(kprn_loss_bce(ctx, labels, S, loss));
-    KPRN_TRY(kprn_backward(ctx, nullptr, 1.f));
-    if (regularize) {
-        if (use_clip) {
-            float nrm = 0.f;
-            KPRN_TRY(kprn_grad_norm(ctx, &nrm));
-            if (nrm > clip_norm) KPRN_TRY(kprn_grad_scale(ctx, clip_norm / nrm));
-        }
-        if (l2 != 0.f) KPRN_TRY(kprn_grad_add_params(ctx, l2));
-    }
-    KPRN_TRY(kprn_adam_step(ctx, lr, b1, b2, eps));
-    for (int t = 0; t < 3 && pad3; ++t) if (pad3[t] > 0) KPRN_TRY(kprn_zero_row(ctx, t, pad3[t]));
-    return KPRN_OK;
+    kprn_train_opts o;
+    batch_opts(o, 0, regularize, use_clip, clip_norm, l2, lr, b1, b2, eps);
+    return kprn_train_step(ctx, ids, seg, N, S, labels, nullptr, nullptr, 0, pad3, &o, loss);
+}
+
+int kprn_train_batch_bpr(kprn_ctx* ctx, const int32_t* ids, const int32_t* seg, int64_t N, int64_t S, const int32_t* pos_seg,
+                         const int32_t* neg_seg, int64_t n_pairs, int32_t apply_to_logits, const int64_t* pad3, int32_t regularize,
+                         int32_t use_clip, float clip_norm, float l2, float lr, float b1, float b2, float eps, float* loss) {
+    kprn_train_opts o;
+    batch_opts(o, 1, regularize, use_clip, clip_norm, l2, lr, b1, b2, eps);
+    o.bpr_on_logits = apply_to_logits;
+    return kprn_train_step(ctx, ids, seg, N, S, nullptr, pos_seg, neg_seg, n_pairs, pad3, &o, loss);
 }
 
 int kprn_set_option(kprn_ctx* ctx, const char* key, int64_t value) {

@@ -1,5 +1,6 @@
 // common.cuh -- ctx layout and helpers shared by the kprn_b200 translation units.
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string>
@@ -21,7 +22,16 @@ struct DBuf {
     template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
-struct TcState;  // tensor-core path state (tc_path.cu)
+struct TcState;     // tensor-core path state (tc_path.cu)
+struct TrainState;  // sparse training state (train.cu)
+
+// Slot map of one batch (tc_path.cu dedup_build): pos[o] = hash-table position of the key read at index o (0xFFFFFFFF = none),
+// slot_of[pos] = slot of that key (slots numbered by first occurrence, blocks of 1024 indices placed atomically), ids = the
+// key of every slot (mode 0: the (type, entity, relation) triple, 3 ints; modes 1/2: one int), count[0] = number of slots.
+struct DedupBufs {
+    DBuf table, slot_of, pos, ids, count;
+    int64_t n_order = 0;
+};
 
 }  // namespace kprn
 
@@ -62,6 +72,20 @@ struct kprn_ctx {
     struct ProfSpan { cudaEvent_t e0, e1; int slot; };
     std::vector<ProfSpan> prof_pending;
     kprn::TcState* tc = nullptr;
+    kprn::TrainState* tr = nullptr;
+    uint64_t small_version = 1;    // bumped when only the SMALL dense parameters (everything but the entity table) changed
+    // multi-GPU (comm.cu): one process per GPU, communicator owned by the ctx
+    void* comm = nullptr;
+    int rank = 0, world = 1;
+    int64_t comm_bytes = 0, comm_calls = 0;
+    kprn::DBuf tmp_comm;
+    // sparse training step (train.cu): while set, the backward scatters entity-row gradients into the compact buffer
+    // sparse_gE[slot_of[pos[o]]] (o = read-order index of the step) instead of the dense table in d_grads
+    float* sparse_gE = nullptr;
+    const uint32_t* sparse_pos = nullptr;
+    const uint32_t* sparse_slot_of = nullptr;
+    bool in_train_step = false;
+    double* last_loss = nullptr;    // device scalar of the last training step's loss
     int opt_dedup = -1;                 // kprn_set_option("dedup"): -1 = KPRN_TC_DEDUP / default (on), 0 / 1 = forced
 };
 
@@ -117,5 +141,29 @@ bool tc_supported(const kprn_ctx* ctx);
 bool tc_validates_ids(const kprn_ctx* ctx, int64_t N);   // true when tc_forward(train = false) will flag out-of-range ids itself
 int tc_forward(kprn_ctx* ctx, const int32_t* d_ids, const int32_t* d_seg, int64_t N, int64_t S, bool train);
 void tc_destroy(kprn_ctx* ctx);
+int dedup_build(kprn_ctx* ctx, DedupBufs& b, int mode, const int32_t* ids, int64_t N, int T, int64_t n_keys);
+void dedup_free(DedupBufs& b);
+
+// ---- multi-GPU (comm.cu) ----
+int comm_allreduce_f32(kprn_ctx* ctx, float* buf, int64_t n, bool max_op);
+int comm_allreduce_f32_2(kprn_ctx* ctx, float* a, int64_t na, float* b, int64_t nb);
+int comm_allreduce_i64(kprn_ctx* ctx, int64_t* buf, int64_t n, bool max_op);
+int comm_allgather_bytes(kprn_ctx* ctx, const void* send, void* recv, int64_t bytes);
+int comm_broadcast_f32(kprn_ctx* ctx, float* buf, int64_t n, int root);
+
+// ---- pieces of the API layer the training step composes (api.cu) ----
+int forward_device_impl(kprn_ctx* ctx, const int32_t* d_ids, const int32_t* d_seg, int64_t N, int64_t S, bool train, bool want_logits,
+                        float* d_out_scores, float* d_out_logits);
+int loss_bce_device(kprn_ctx* ctx, const float* d_labels, int64_t S, double** d_loss_out);
+int loss_bpr_device(kprn_ctx* ctx, const int32_t* d_pos, const int32_t* d_neg, int64_t n_pairs, int on_logits, double** d_loss_out);
+int backward_device(kprn_ctx* ctx, float scale);
+int host_to_device(kprn_ctx* ctx, void* dst, const void* src, size_t bytes, size_t stage_off);
+void tc_packed_entity(kprn_ctx* ctx, __nv_bfloat16** hi, __nv_bfloat16** lo, int* KE);   // valid packed bf16 entity tables, or nulls
+
+// ---- sparse training step (train.cu) ----
+int train_note_dense_step(kprn_ctx* ctx, float step);
+int train_materialize_grads(kprn_ctx* ctx);
+int train_flush(kprn_ctx* ctx);          // brings every entity row up to date (lazy dense-equivalent Adam); no-op when nothing is pending
+void train_destroy(kprn_ctx* ctx);
 
 }  // namespace kprn

@@ -490,7 +490,8 @@ __global__ void rnn_cell_bwd_kernel(const float* __restrict__ act, int64_t ldact
 // shared memory per block first; entity rows go straight to global float atomics (RED.ADD).
 __global__ void scatter_embed_kernel(const float* __restrict__ dX, const int32_t* __restrict__ ids, Layout l,
                                      int d_t, int d_e, int d_r, int64_t V_t, int64_t V_e, int64_t V_r, int T, int64_t n0, int64_t CH,
-                                     int64_t rows, int rows_per_block, float* __restrict__ grads, int use_smem) {
+                                     int64_t rows, int rows_per_block, float* __restrict__ grads, int use_smem,
+                                     float* __restrict__ gE_compact, const uint32_t* __restrict__ sp_pos, const uint32_t* __restrict__ sp_slot_of) {
     extern __shared__ float sm[];   // [V_t*d_t + V_r*d_r] when use_smem
     const int n_small = (int)(V_t * d_t + V_r * d_r);
     if (use_smem) {
@@ -507,12 +508,19 @@ __global__ void scatter_embed_kernel(const float* __restrict__ dX, const int32_t
         int64_t it = id[0] - 1, ie = id[1] - 1, ir = id[2] - 1;
         if (it < 0 || it >= V_t || ie < 0 || ie >= V_e || ir < 0 || ir >= V_r) continue;
         const float* dx = dX + r * l.D;
+        // sparse training step (train.cu): the entity row's gradient goes to its slot of the compact buffer; the slot map is
+        // indexed in the recurrence's read order o = ((n/128)*T + t)*128 + n%128
+        float* ge = grads + l.E_e + ie * d_e;
+        if (gE_compact) {
+            const int64_t n = n0 + p;
+            ge = gE_compact + (int64_t)sp_slot_of[sp_pos[((n >> 7) * T + t) * 128 + (n & 127)]] * d_e;
+        }
         for (int k = threadIdx.x; k < l.D; k += blockDim.x) {
             float v = dx[k];
             if (k < d_t) {
                 if (use_smem) atomicAdd(&sm[it * d_t + k], v); else atomicAdd(grads + l.E_t + it * d_t + k, v);
             } else if (k < d_t + d_e) {
-                atomicAdd(grads + l.E_e + ie * d_e + (k - d_t), v);
+                atomicAdd(ge + (k - d_t), v);
             } else {
                 int kk = k - d_t - d_e;
                 if (use_smem) atomicAdd(&sm[V_t * d_t + ir * d_r + kk], v); else atomicAdd(grads + l.E_r + ir * d_r + kk, v);
@@ -619,7 +627,8 @@ int simple_backward(kprn_ctx* ctx, float scale) {
             size_t smem = sizeof(float) * (size_t)(c.V_t * c.d_t + c.V_r * c.d_r);
             int use_smem = smem <= 40 * 1024;
             scatter_embed_kernel<<<(unsigned)cdiv(rows, rpb), 256, use_smem ? smem : 0, ctx->stream>>>(
-                dX, ctx->d_ids, l, c.d_t, c.d_e, c.d_r, c.V_t, c.V_e, c.V_r, T, n0, nb, rows, rpb, gr, use_smem);
+                dX, ctx->d_ids, l, c.d_t, c.d_e, c.d_r, c.V_t, c.V_e, c.V_r, T, n0, nb, rows, rpb, gr, use_smem,
+                ctx->sparse_gE, ctx->sparse_pos, ctx->sparse_slot_of);
             KPRN_LAUNCH_CHECK(ctx);
         }
     }

@@ -50,13 +50,15 @@ constexpr int PROJ2_THREADS = 384 + 32 * (PROJ2_GW - 2);  // warps 2,3 + (PROJ2_
 constexpr int RECUR_THREADS = 608;    // recur: warps 0 TMA producer, 1 MMA issuer, 2 TMEM alloc + h loader, 3-18 epilogue (4 groups); 19 warps -> 104 registers per thread
 
 struct TcState {
-    uint64_t packed_version = 0;
+    uint64_t packed_version = 0;       // ctx->params_version the packed operands (entity tables included) were built from
+    uint64_t packed_small = 0;         // ctx->small_version the packed WEIGHTS were built from (a sparse training step leaves the
+                                       // entity tables current row by row and only bumps small_version)
     int Hp = 0, KE = 0, NCH = 0, KSh = 0, KSe = 0, G4 = 0, NOH = 0, NS = 0;
     bf16* E_hi = nullptr; bf16* E_lo = nullptr;
     bf16* WxE = nullptr; bf16* Wh = nullptr;
     float* Ptr = nullptr;
     DBuf xw, hT, hscratch, dbg, part4;
-    DBuf dd_table, dd_slot_of, dd_pos, dd_ids, dd_count;   // step-input deduplication
+    DedupBufs dd;              // step-input deduplication
     bool dedup = true;         // project each distinct (type, entity, relation) triple once (KPRN_TC_DEDUP=0: every step)
     bool debug = false;
     bool use_gather4 = true;   // TMA tile::gather4 for the entity rows (KPRN_TC_GATHER4=0 -> LDGSTS gather of proj2)
@@ -1371,21 +1373,27 @@ __device__ __forceinline__ int64_t dedup_step_of(int64_t o, int64_t N, int T) {
 
 // pos[o] = table position of the triple read at o; first[pos] = min o over its occurrences.  Equal triples inside a warp
 // (a pad column of a tile is one triple) elect one lane; a plain load before the CAS keeps hot keys from serialising.
+// mode 0: key = the (type, entity, relation) triple of ids[N,T,3], index o in READ ORDER (what the projection dedups);
+// mode 1: key = the entity row alone, same order (distinct rows of a training batch: compact gradient / sparse optimizer);
+// mode 2: key = keys[o] (a flat int32 list, negative = skip) -- the union of the row lists gathered from all ranks.
 __global__ void dedup_insert_kernel(const int32_t* __restrict__ ids, int64_t n_order, int64_t N, int T, int64_t V_t, int64_t V_e,
                                     int64_t V_r, unsigned long long* table, uint32_t* first, uint32_t mask, uint32_t* __restrict__ pos,
-                                    int32_t* err) {
+                                    int32_t* err, int mode) {
     const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t i = o < n_order ? dedup_step_of(o, N, T) : -1;
+    const int64_t i = o < n_order ? (mode == 2 ? (ids[o] >= 0 ? o : -1) : dedup_step_of(o, N, T)) : -1;
     const bool active = i >= 0;
     unsigned long long key = DEDUP_EMPTY;
-    if (active) {
+    if (active && mode == 2) {
+        key = (unsigned long long)ids[o];
+    } else if (active) {
         int64_t ta = (int64_t)ids[i * 3] - 1, en = (int64_t)ids[i * 3 + 1] - 1, rb = (int64_t)ids[i * 3 + 2] - 1;
         // a bad id raises in the reference (nn.LookupTable index out of range): flagged here, reported by the forward call
         if (ta < 0 || ta >= V_t || en < 0 || en >= V_e || rb < 0 || rb >= V_r) atomicExch(err, 1);
         ta = ta < 0 ? 0 : (ta >= V_t ? V_t - 1 : ta);
         en = en < 0 ? 0 : (en >= V_e ? V_e - 1 : en);
         rb = rb < 0 ? 0 : (rb >= V_r ? V_r - 1 : rb);
-        key = ((unsigned long long)en * (unsigned long long)V_t + (unsigned long long)ta) * (unsigned long long)V_r + (unsigned long long)rb;
+        key = mode == 1 ? (unsigned long long)en
+                        : ((unsigned long long)en * (unsigned long long)V_t + (unsigned long long)ta) * (unsigned long long)V_r + (unsigned long long)rb;
     }
     const unsigned peers = __match_any_sync(0xffffffffu, key);
     const int leader = __ffs(peers) - 1;           // lowest lane = lowest o of the group
@@ -1438,7 +1446,7 @@ __device__ __forceinline__ int dedup_flags(const uint32_t* __restrict__ pos, con
 // first-occurrence thread records the row for its key and writes the triple to the list the projection reads.
 __global__ void dedup_assign_kernel(const int32_t* __restrict__ ids, const uint32_t* __restrict__ pos, const uint32_t* __restrict__ first,
                                     int64_t n_order, int64_t N, int T, int32_t* count, uint32_t* __restrict__ slot_of,
-                                    int32_t* __restrict__ ids_d) {
+                                    int32_t* __restrict__ ids_d, int mode) {
     __shared__ int base_s;
     bool f[4];
     int tot;
@@ -1451,11 +1459,49 @@ __global__ void dedup_assign_kernel(const int32_t* __restrict__ ids, const uint3
 #pragma unroll
     for (int j = 0; j < 4; ++j)
         if (f[j]) {
-            const int64_t i = dedup_step_of(o0 + j, N, T);
             slot_of[pos[o0 + j]] = (uint32_t)row;
-            ids_d[(int64_t)row * 3] = ids[i * 3]; ids_d[(int64_t)row * 3 + 1] = ids[i * 3 + 1]; ids_d[(int64_t)row * 3 + 2] = ids[i * 3 + 2];
+            if (mode == 2) {
+                ids_d[row] = ids[o0 + j];
+            } else {
+                const int64_t i = dedup_step_of(o0 + j, N, T);
+                if (mode == 1) ids_d[row] = ids[i * 3 + 1];       // 1-based entity row of the slot
+                else { ids_d[(int64_t)row * 3] = ids[i * 3]; ids_d[(int64_t)row * 3 + 1] = ids[i * 3 + 1]; ids_d[(int64_t)row * 3 + 2] = ids[i * 3 + 2]; }
+            }
             ++row;
         }
+}
+
+// Builds the slot map of one batch (see DedupBufs in common.cuh).  No host round trip: the slot count stays on the device.
+int dedup_build(kprn_ctx* ctx, DedupBufs& b, int mode, const int32_t* ids, int64_t N, int T, int64_t n_keys) {
+    const kprn_config& c = ctx->cfg;
+    const int64_t ptiles = cdiv(N, TILE_M);
+    const int64_t n_order = mode == 2 ? n_keys : ptiles * T * TILE_M;
+    const int64_t n_max = mode == 2 ? n_keys : N * T;
+    if (n_order >= (1ll << 30)) { set_error("dedup: batch too large"); return KPRN_EINVAL; }
+    uint32_t M = 1024;
+    while ((int64_t)M < 2 * n_max) M <<= 1;
+    KPRN_TRY(ensure(b.table, (sizeof(unsigned long long) + sizeof(uint32_t)) * (size_t)M));     // keys, then first[]
+    KPRN_TRY(ensure(b.slot_of, sizeof(uint32_t) * (size_t)M));
+    KPRN_TRY(ensure(b.pos, sizeof(uint32_t) * (size_t)n_order));
+    KPRN_TRY(ensure(b.ids, sizeof(int32_t) * (mode == 0 ? 3 : 1) * (size_t)n_max));
+    KPRN_TRY(ensure(b.count, 256));
+    unsigned long long* table = b.table.as<unsigned long long>();
+    uint32_t* first = reinterpret_cast<uint32_t*>(table + M);
+    int32_t* count = b.count.as<int32_t>();
+    KPRN_CUDA(cudaMemsetAsync(table, 0xFF, (sizeof(unsigned long long) + sizeof(uint32_t)) * (size_t)M, ctx->stream));
+    KPRN_CUDA(cudaMemsetAsync(count, 0, sizeof(int32_t), ctx->stream));
+    dedup_insert_kernel<<<(unsigned)cdiv(n_order, 256), 256, 0, ctx->stream>>>(ids, n_order, N, T, c.V_t, c.V_e, c.V_r, table, first, M - 1,
+                                                                              b.pos.as<uint32_t>(), ctx->d_err, mode);
+    KPRN_LAUNCH_CHECK(ctx);
+    dedup_assign_kernel<<<(unsigned)cdiv(n_order, DEDUP_BLOCK), 256, 0, ctx->stream>>>(ids, b.pos.as<uint32_t>(), first, n_order, N, T, count,
+                                                                                      b.slot_of.as<uint32_t>(), b.ids.as<int32_t>(), mode);
+    KPRN_LAUNCH_CHECK(ctx);
+    b.n_order = n_order;
+    return KPRN_OK;
+}
+void dedup_free(DedupBufs& b) {
+    for (DBuf* d : {&b.table, &b.slot_of, &b.pos, &b.ids, &b.count})
+        if (d->p) { cudaFree(d->p); d->p = nullptr; d->cap = 0; }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1488,7 +1534,8 @@ static int tc_pack(kprn_ctx* ctx) {
     TcState* s = ctx->tc;
     const kprn_config& c = ctx->cfg;
     const Layout& l = ctx->lay;
-    if (s->packed_version == ctx->params_version) return KPRN_OK;
+    if (s->packed_version == ctx->params_version && s->packed_small == ctx->small_version) return KPRN_OK;
+    const bool full = s->packed_version != ctx->params_version;
     if (!s->E_hi || !s->E_lo || !s->WxE || !s->Wh || !s->Ptr) {
         // all or nothing: a failed allocation must not leave a half-built state that the next call takes for complete
         void** ptrs[5] = {(void**)&s->E_hi, (void**)&s->E_lo, (void**)&s->WxE, (void**)&s->Wh, (void**)&s->Ptr};
@@ -1505,9 +1552,11 @@ static int tc_pack(kprn_ctx* ctx) {
         }
         s->have_tmaps = make_entity_tensor_maps(s, c.V_e);
     }
-    int64_t ne = c.V_e * (int64_t)s->KE;
-    split_entity_kernel<<<(unsigned)cdiv(ne, 256), 256, 0, ctx->stream>>>(ctx->d_params + l.E_e, c.V_e, c.d_e, s->KE, s->E_hi, s->E_lo);
-    KPRN_LAUNCH_CHECK(ctx);
+    if (full) {
+        int64_t ne = c.V_e * (int64_t)s->KE;
+        split_entity_kernel<<<(unsigned)cdiv(ne, 256), 256, 0, ctx->stream>>>(ctx->d_params + l.E_e, c.V_e, c.d_e, s->KE, s->E_hi, s->E_lo);
+        KPRN_LAUNCH_CHECK(ctx);
+    }
     int64_t nh = (int64_t)s->NCH * s->KSh * B_SLAB_ELEMS;
     pack_wh_kernel<<<(unsigned)cdiv(nh, 256), 256, 0, ctx->stream>>>(ctx->d_params + l.Wh, c.H, s->NCH, s->KSh, s->recur_pairs ? 1 : 0, s->Wh);
     KPRN_LAUNCH_CHECK(ctx);
@@ -1518,7 +1567,16 @@ static int tc_pack(kprn_ctx* ctx) {
                                                                       s->KSe, s->NS, (int)(c.V_t * c.V_r), s->G4, s->WxE);
     KPRN_LAUNCH_CHECK(ctx);
     s->packed_version = ctx->params_version;
+    s->packed_small = ctx->small_version;
     return KPRN_OK;
+}
+
+// the packed bf16 copies of the entity table, when they mirror the fp32 table (the sparse optimizer keeps them in step row by row)
+void tc_packed_entity(kprn_ctx* ctx, bf16** hi, bf16** lo, int* KE) {
+    *hi = nullptr; *lo = nullptr; *KE = 0;
+    TcState* s = ctx->tc;
+    if (!s || !s->E_hi || !s->E_lo || s->packed_version != ctx->params_version) return;
+    *hi = s->E_hi; *lo = s->E_lo; *KE = s->KE;
 }
 
 static size_t proj_smem(int KE, int NOH) { return (size_t)(KE / 8 + 8 * NOH) * 2048 + (size_t)(KE / 8) * 2048 + PROJ_RING * B_SLAB_ELEMS * 2 + 512; }
@@ -1591,27 +1649,9 @@ int tc_forward(kprn_ctx* ctx, const int32_t* d_ids, const int32_t* d_seg, int64_
         KPRN_TRY(prof_begin(ctx, &e0));
         const int64_t n_steps = N * c.T, n_order = ptiles * c.T * TILE_M;       // n_order: read-order indices incl. the ragged tail
         if (s->dedup && n_order < (1ll << 30)) {
-            uint32_t M = 1024;
-            while ((int64_t)M < 2 * n_steps) M <<= 1;
-            const int nb = (int)cdiv(n_order, DEDUP_BLOCK);
-            KPRN_TRY(ensure(s->dd_table, (sizeof(unsigned long long) + sizeof(uint32_t)) * (size_t)M));     // keys, then first[]
-            KPRN_TRY(ensure(s->dd_slot_of, sizeof(uint32_t) * (size_t)M));
-            KPRN_TRY(ensure(s->dd_pos, sizeof(uint32_t) * (size_t)n_order));
-            KPRN_TRY(ensure(s->dd_ids, sizeof(int32_t) * 3 * (size_t)n_steps));
-            KPRN_TRY(ensure(s->dd_count, 256));
-            unsigned long long* table = s->dd_table.as<unsigned long long>();
-            uint32_t* first = reinterpret_cast<uint32_t*>(table + M);
-            int32_t* count = s->dd_count.as<int32_t>();
-            KPRN_CUDA(cudaMemsetAsync(table, 0xFF, (sizeof(unsigned long long) + sizeof(uint32_t)) * (size_t)M, ctx->stream));
-            KPRN_CUDA(cudaMemsetAsync(count, 0, sizeof(int32_t), ctx->stream));
-            dedup_insert_kernel<<<(unsigned)cdiv(n_order, 256), 256, 0, ctx->stream>>>(d_ids, n_order, N, c.T, c.V_t, c.V_e, c.V_r, table, first, M - 1,
-                                                                                      s->dd_pos.as<uint32_t>(), ctx->d_err);
-            KPRN_LAUNCH_CHECK(ctx);
-            dedup_assign_kernel<<<(unsigned)nb, 256, 0, ctx->stream>>>(d_ids, s->dd_pos.as<uint32_t>(), first, n_order, N, c.T, count,
-                                                                       s->dd_slot_of.as<uint32_t>(), s->dd_ids.as<int32_t>());
-            KPRN_LAUNCH_CHECK(ctx);
+            KPRN_TRY(dedup_build(ctx, s->dd, 0, d_ids, N, c.T, 0));
             // the projection sees a list of (at most n_steps) single-step "paths"; its real length is read on the device
-            a.ids = s->dd_ids.as<int32_t>(); a.N = n_steps; a.T = 1; a.num_tiles = cdiv(n_steps, TILE_M); a.n_dev = count;
+            a.ids = s->dd.ids.as<int32_t>(); a.N = n_steps; a.T = 1; a.num_tiles = cdiv(n_steps, TILE_M); a.n_dev = s->dd.count.as<int32_t>();
         }
         int64_t grid = a.num_tiles < s->num_sms ? a.num_tiles : s->num_sms;
         if (s->use_pairs && a.num_tiles >= 2) {
@@ -1637,7 +1677,7 @@ int tc_forward(kprn_ctx* ctx, const int32_t* d_ids, const int32_t* d_seg, int64_
         a.num_tiles = ptiles; a.passes = passes; a.dbg = dbg ? dbg + 16 : nullptr;
         a.wo = nullptr; a.part4 = nullptr; a.npad = ptiles * TILE_M;
         const bool dd = s->dedup && ptiles * c.T * TILE_M < (1ll << 30);
-        a.pos = dd ? s->dd_pos.as<uint32_t>() : nullptr; a.slot_of = dd ? s->dd_slot_of.as<uint32_t>() : nullptr;
+        a.pos = dd ? s->dd.pos.as<uint32_t>() : nullptr; a.slot_of = dd ? s->dd.slot_of.as<uint32_t>() : nullptr;
         ctx->head_part4 = nullptr;
         if (ctx->cls_only && c.pool == KPRN_POOL_LSE) {      // the pool kernel finishes the head: sum of 4 partials + bias
             KPRN_TRY(ensure(s->part4, sizeof(float) * 4 * (size_t)a.npad));
@@ -1694,8 +1734,9 @@ void tc_destroy(kprn_ctx* ctx) {
     if (s->WxE) cudaFree(s->WxE);
     if (s->Wh) cudaFree(s->Wh);
     if (s->Ptr) cudaFree(s->Ptr);
-    for (DBuf* b : {&s->xw, &s->hT, &s->hscratch, &s->dbg, &s->part4, &s->dd_table, &s->dd_slot_of, &s->dd_pos, &s->dd_ids, &s->dd_count})
+    for (DBuf* b : {&s->xw, &s->hT, &s->hscratch, &s->dbg, &s->part4})
         if (b->p) { cudaFree(b->p); b->p = nullptr; b->cap = 0; }
+    dedup_free(s->dd);
     delete s;
     ctx->tc = nullptr;
 }

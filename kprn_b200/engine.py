@@ -27,6 +27,12 @@ class KprnConfig(C.Structure):
                 ("device", C.c_int32), ("reserved", C.c_int32)]
 
 
+class KprnTrainOpts(C.Structure):
+    _fields_ = [("loss", C.c_int32), ("bpr_on_logits", C.c_int32), ("regularize", C.c_int32), ("use_clip", C.c_int32),
+                ("clip_norm", C.c_float), ("l2", C.c_float), ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float),
+                ("eps", C.c_float), ("grad_scale", C.c_float), ("dense", C.c_int32), ("reserved", C.c_int32 * 4)]
+
+
 class KprnError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__("kprn_b200 error %d: %s" % (code, msg))
@@ -73,6 +79,21 @@ ABI = {
     "kprn_adam_step": [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float],
     "kprn_train_batch_bce": [C.c_void_p, _I32P, _I32P, C.c_int64, C.c_int64, _F32P, _I64P, C.c_int32, C.c_int32,
                              C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _F32P],
+    "kprn_train_batch_bpr": [C.c_void_p, _I32P, _I32P, C.c_int64, C.c_int64, _I32P, _I32P, C.c_int64, C.c_int32, _I64P, C.c_int32,
+                             C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _F32P],
+    "kprn_train_step": [C.c_void_p, _I32P, _I32P, C.c_int64, C.c_int64, _F32P, _I32P, _I32P, C.c_int64, _I64P,
+                        C.POINTER(KprnTrainOpts), _F32P],
+    "kprn_train_step_device": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                               C.c_int64, _I64P, C.POINTER(KprnTrainOpts)],
+    "kprn_last_loss": [C.c_void_p, _F32P],
+    "kprn_train_info": [C.c_void_p, _I64P, _I64P, _I64P],
+    "kprn_comm_unique_id": [C.c_void_p],
+    "kprn_comm_init": [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p],
+    "kprn_comm_destroy": [C.c_void_p],
+    "kprn_comm_info": [C.c_void_p, _I32P, _I32P, _I64P, _I64P, C.c_int32],
+    "kprn_broadcast_params": [C.c_void_p, C.c_int32],
+    "kprn_allreduce_grads": [C.c_void_p, C.c_int32],
+    "kprn_allreduce_host_f64": [C.c_void_p, _F64P, C.c_int64, C.c_int32],
     "kprn_set_option": [C.c_void_p, C.c_char_p, C.c_int64],
     "kprn_launch_count": [C.c_void_p, _I64P, C.c_int32],
     "kprn_profile": [C.c_void_p, C.c_int32],
@@ -287,6 +308,91 @@ class Engine:
         _chk(self.lib.kprn_train_batch_bce(self.h, _i32p(ids), _i32p(seg), ids.shape[0], seg.shape[0] - 1, _f32p(labels),
                                            pads, int(regularize), int(use_clip), clip_norm, l2, lr, b1, b2, eps, C.byref(loss)))
         return float(loss.value)
+
+    def train_opts(self, loss="bce", bpr_on_logits=False, regularize=False, use_clip=False, clip_norm=5.0, l2=0.0, lr=1e-3,
+                   b1=0.9, b2=0.999, eps=1e-8, grad_scale=1.0, dense=False):
+        o = KprnTrainOpts()
+        o.loss = 0 if loss == "bce" else 1
+        o.bpr_on_logits, o.regularize, o.use_clip = int(bpr_on_logits), int(regularize), int(use_clip)
+        o.clip_norm, o.l2, o.lr, o.beta1, o.beta2, o.eps = clip_norm, l2, lr, b1, b2, eps
+        o.grad_scale, o.dense = grad_scale, int(dense)
+        return o
+
+    def train_step(self, ids, seg, labels=None, pos_seg=None, neg_seg=None, pad_rows=(0, 0, 0), **kw):
+        """One MyOptimizer:trainBatch (host buffers). BCE with labels[S], or BPR with (pos_seg, neg_seg) 0-based segment pairs."""
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        seg = np.ascontiguousarray(seg, dtype=np.int32)
+        if labels is None and pos_seg is not None:
+            kw.setdefault("loss", "bpr")
+        o = self.train_opts(**kw)
+        lab = None if labels is None else np.ascontiguousarray(labels, dtype=np.float32)
+        ps = None if pos_seg is None else np.ascontiguousarray(pos_seg, dtype=np.int32)
+        ns = None if neg_seg is None else np.ascontiguousarray(neg_seg, dtype=np.int32)
+        pads = (C.c_int64 * 3)(*[int(x) for x in pad_rows])
+        loss = C.c_float()
+        _chk(self.lib.kprn_train_step(self.h, _i32p(ids), _i32p(seg), ids.shape[0], seg.shape[0] - 1, _f32p(lab), _i32p(ps), _i32p(ns),
+                                      0 if ps is None else ps.size, pads, C.byref(o), C.byref(loss)))
+        return float(loss.value)
+
+    def train_step_device(self, d_ids, d_seg, N, S, d_labels=0, d_pos=0, d_neg=0, n_pairs=0, pad_rows=(0, 0, 0), opts=None):
+        """Raw device pointers (ints); the loss stays on the device (last_loss())."""
+        pads = (C.c_int64 * 3)(*[int(x) for x in pad_rows])
+        o = opts if opts is not None else self.train_opts()
+        _chk(self.lib.kprn_train_step_device(self.h, C.c_void_p(d_ids), C.c_void_p(d_seg), N, S, C.c_void_p(d_labels) if d_labels else None,
+                                             C.c_void_p(d_pos) if d_pos else None, C.c_void_p(d_neg) if d_neg else None, n_pairs, pads,
+                                             C.byref(o)))
+
+    def last_loss(self):
+        v = C.c_float()
+        _chk(self.lib.kprn_last_loss(self.h, C.byref(v)))
+        return float(v.value)
+
+    def train_info(self):
+        a, b, c_ = C.c_int64(), C.c_int64(), C.c_int64()
+        _chk(self.lib.kprn_train_info(self.h, C.byref(a), C.byref(b), C.byref(c_)))
+        return {"rows_local": int(a.value), "rows_union": int(b.value), "rows_gathered": int(c_.value)}
+
+    def train_batch_bpr(self, ids, seg, pos_seg, neg_seg, on_logits=False, pad_rows=(0, 0, 0), regularize=False, use_clip=False,
+                        clip_norm=5.0, l2=0.0, lr=1e-3, b1=0.9, b2=0.999, eps=1e-8):
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        seg = np.ascontiguousarray(seg, dtype=np.int32)
+        ps = np.ascontiguousarray(pos_seg, dtype=np.int32)
+        ns = np.ascontiguousarray(neg_seg, dtype=np.int32)
+        pads = (C.c_int64 * 3)(*[int(x) for x in pad_rows])
+        loss = C.c_float()
+        _chk(self.lib.kprn_train_batch_bpr(self.h, _i32p(ids), _i32p(seg), ids.shape[0], seg.shape[0] - 1, _i32p(ps), _i32p(ns), ps.size,
+                                           int(on_logits), pads, int(regularize), int(use_clip), clip_norm, l2, lr, b1, b2, eps, C.byref(loss)))
+        return float(loss.value)
+
+    # ---- multi-GPU (one process per GPU; NCCL communicator owned by the ctx) --------------------
+    @staticmethod
+    def comm_unique_id():
+        buf = (C.c_char * 128)()
+        _chk(load_library().kprn_comm_unique_id(buf))
+        return bytes(buf)
+
+    def comm_init(self, rank, world, id128):
+        buf = (C.c_char * 128).from_buffer_copy(id128)
+        _chk(self.lib.kprn_comm_init(self.h, rank, world, buf))
+
+    def comm_destroy(self):
+        _chk(self.lib.kprn_comm_destroy(self.h))
+
+    def comm_info(self, reset=False):
+        r, w, b, c_ = C.c_int32(), C.c_int32(), C.c_int64(), C.c_int64()
+        _chk(self.lib.kprn_comm_info(self.h, C.byref(r), C.byref(w), C.byref(b), C.byref(c_), int(reset)))
+        return {"rank": r.value, "world": w.value, "bytes": int(b.value), "calls": int(c_.value)}
+
+    def broadcast_params(self, root=0):
+        _chk(self.lib.kprn_broadcast_params(self.h, root))
+
+    def allreduce_grads(self, average=False):
+        _chk(self.lib.kprn_allreduce_grads(self.h, int(average)))
+
+    def allreduce_host(self, vals, op_max=False):
+        v = np.ascontiguousarray(vals, dtype=np.float64).copy()
+        _chk(self.lib.kprn_allreduce_host_f64(self.h, v.ctypes.data_as(_F64P), v.size, int(op_max)))
+        return v
 
     # ---- plumbing -----------------------------------------------------------------------------
     def set_stream(self, cuda_stream_ptr):

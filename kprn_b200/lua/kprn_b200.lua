@@ -62,6 +62,29 @@ int kprn_adam_step(kprn_ctx* ctx, float lr, float beta1, float beta2, float eps)
 int kprn_train_batch_bce(kprn_ctx* ctx, const int32_t* ids, const int32_t* seg_offsets, int64_t N, int64_t S,
                          const float* labels, const int64_t* pad_rows3, int32_t regularize, int32_t use_clip,
                          float clip_norm, float l2, float lr, float beta1, float beta2, float eps, float* loss);
+int kprn_train_batch_bpr(kprn_ctx* ctx, const int32_t* ids, const int32_t* seg_offsets, int64_t N, int64_t S,
+                         const int32_t* pos_seg, const int32_t* neg_seg, int64_t n_pairs, int32_t apply_to_logits,
+                         const int64_t* pad_rows3, int32_t regularize, int32_t use_clip, float clip_norm, float l2, float lr,
+                         float beta1, float beta2, float eps, float* loss);
+typedef struct kprn_train_opts {
+    int32_t loss; int32_t bpr_on_logits; int32_t regularize; int32_t use_clip; float clip_norm, l2;
+    float lr, beta1, beta2, eps; float grad_scale; int32_t dense; int32_t reserved[4];
+} kprn_train_opts;
+int kprn_train_step(kprn_ctx* ctx, const int32_t* ids, const int32_t* seg_offsets, int64_t N, int64_t S, const float* labels,
+                    const int32_t* pos_seg, const int32_t* neg_seg, int64_t n_pairs, const int64_t* pad_rows3,
+                    const kprn_train_opts* opts, float* loss);
+int kprn_train_step_device(kprn_ctx* ctx, const int32_t* d_ids, const int32_t* d_seg_offsets, int64_t N, int64_t S,
+                           const float* d_labels, const int32_t* d_pos_seg, const int32_t* d_neg_seg, int64_t n_pairs,
+                           const int64_t* pad_rows3, const kprn_train_opts* opts);
+int kprn_last_loss(kprn_ctx* ctx, float* loss);
+int kprn_train_info(kprn_ctx* ctx, int64_t* rows_local, int64_t* rows_union, int64_t* rows_gathered);
+int kprn_comm_unique_id(void* id128);
+int kprn_comm_init(kprn_ctx* ctx, int32_t rank, int32_t world, const void* id128);
+int kprn_comm_destroy(kprn_ctx* ctx);
+int kprn_comm_info(kprn_ctx* ctx, int32_t* rank, int32_t* world, int64_t* bytes_moved, int64_t* collective_calls, int32_t reset);
+int kprn_broadcast_params(kprn_ctx* ctx, int32_t root);
+int kprn_allreduce_grads(kprn_ctx* ctx, int32_t average);
+int kprn_allreduce_host_f64(kprn_ctx* ctx, double* vals, int64_t n, int32_t op_max);
 int kprn_set_option(kprn_ctx* ctx, const char* key, int64_t value);
 int kprn_launch_count(kprn_ctx* ctx, int64_t* n, int32_t reset);
 int kprn_profile(kprn_ctx* ctx, int32_t enable);

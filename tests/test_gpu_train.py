@@ -1,0 +1,168 @@
+"""GPU tests of the training step (kprn_train_step: MyOptimizer:trainBatch, SP/model/optimizer/MyOptimizer.lua:177-221):
+the row-sparse evaluation (compact entity gradient + lazily-replayed dense optim.adam) against the reference-literal dense
+flow and against the fp64 oracle's trainBatch, BCE and BPR, with the entity rows of successive batches overlapping only
+partly (so rows sit out several steps and are replayed)."""
+import numpy as np
+import pytest
+
+from kprn_b200 import synth
+from tests.util import assert_rel, engine_for, make_case
+
+pytestmark = pytest.mark.gpu
+
+
+def _batches(o, n_batches, N, seed, V_e):
+    c = o.cfg
+    out = []
+    for b in range(n_batches):
+        ids = synth.make_paths(N, T=c.T, V_e=V_e, seed=seed + 13 * b, length_mode="stress", V_t=c.V_t, V_r=c.V_r)
+        seg = synth.make_segments(N, seed=seed + 13 * b)
+        labels = synth.make_labels(len(seg) - 1, seed + 13 * b)
+        out.append((ids, seg, labels))
+    return out
+
+
+def _oracle_train(o, params, batches, pads, steps, loss="bce", lr=1e-3):
+    """MyOptimizer:trainBatch on the oracle: zero pads -> fwd -> loss -> bwd -> adam -> zero pads."""
+    x = params.copy()
+    m = np.zeros_like(x); v = np.zeros_like(x)
+    losses = []
+    for t in range(1, steps + 1):
+        ids, seg, labels = batches[(t - 1) % len(batches)]
+        for tbl, row in enumerate(pads):
+            o.zero_row(x, tbl, row)
+        fwd = o.forward(x, ids, seg, cache=True)
+        if loss == "bce":
+            lv, dsc = o.bce(fwd["scores"], labels.astype(np.float64))
+        else:
+            S = len(seg) - 1
+            pos = np.arange(0, S - 1, 2); neg = pos + 1
+            lv, dp, dn = o.bpr(fwd["scores"][pos], fwd["scores"][neg])
+            dsc = np.zeros(S); np.add.at(dsc, pos, dp); np.add.at(dsc, neg, dn)
+        losses.append(lv)
+        g = o.backward(x, ids, seg, fwd, dsc)
+        o.adam(x, g, m, v, t, lr=lr)
+        for tbl, row in enumerate(pads):
+            o.zero_row(x, tbl, row)
+    return x, losses
+
+
+@pytest.mark.parametrize("precision", [0, 3])
+def test_sparse_step_equals_dense_flow_and_oracle(precision):
+    """5 steps over 3 rotating batches drawn from a 4000-row table (most rows sit out some steps): parameters after the
+    last step -- read once, so every postponed update is replayed by the flush -- match the dense flow and the oracle."""
+    V_e = 4000
+    o, params, _, _, _ = make_case(N=64, seed=70, d_t=8, d_e=64, d_r=8, H=64, V_e=V_e)
+    c = o.cfg
+    pads = (c.V_t, c.V_e, c.V_r)
+    batches = _batches(o, 3, 600, 700, V_e)
+    steps = 5
+    ref, ref_losses = _oracle_train(o, params, batches, pads, steps)
+    outs = {}
+    for mode in ("sparse", "dense"):
+        e = engine_for(o, precision=precision)
+        e.set_params(params)
+        losses = []
+        for t in range(steps):
+            ids, seg, labels = batches[t % 3]
+            losses.append(e.train_step(ids, seg, labels, pad_rows=pads, dense=(mode == "dense")))
+        outs[mode] = e.get_params().astype(np.float64)
+        for a, b in zip(losses, ref_losses):
+            assert abs(a - b) <= 2e-4 * abs(b), (mode, losses, ref_losses)
+        e.close()
+    # sparse vs dense: same arithmetic per element; gradients differ only by float-atomic summation order
+    d = np.abs(outs["sparse"] - outs["dense"])
+    assert np.quantile(d, 0.999) <= 2e-6 and d.max() <= 2e-4, (np.quantile(d, 0.999), d.max())
+    # against the oracle: Adam divides by sqrt(v) ~ |g|, so the bar is on the update (tests/test_gpu_parity.py)
+    upd = ref - params
+    scale = np.sqrt(np.mean(upd[upd != 0] ** 2))
+    for mode in outs:
+        err = np.abs(outs[mode] - ref)
+        assert np.quantile(err, 0.999) <= 2e-3 * scale * 10 and np.mean(err) <= 2e-3 * scale, (mode, err.max(), scale)
+    # untouched rows did not move
+    touched = np.zeros(V_e, dtype=bool)
+    for ids, _, _ in batches:
+        touched[ids[:, :, 1].reshape(-1) - 1] = True
+    E0 = o.view(params, "E_e"); E1 = o.view(outs["sparse"], "E_e")
+    assert np.array_equal(E1[~touched], E0[~touched].astype(np.float32).astype(np.float64))
+
+
+def test_lazy_rows_survive_scoring_between_steps_and_param_io():
+    """A scoring forward / get_params between training steps flushes the postponed updates; training then continues."""
+    V_e = 3000
+    o, params, _, _, _ = make_case(N=64, seed=71, d_t=8, d_e=64, d_r=8, H=64, V_e=V_e)
+    c = o.cfg
+    pads = (c.V_t, c.V_e, c.V_r)
+    batches = _batches(o, 3, 500, 710, V_e)
+    ref, _ = _oracle_train(o, params, batches, pads, 4)
+    e = engine_for(o, precision=1)          # tensor-core scoring forward between the steps: packed bf16 rows must follow
+    d = engine_for(o, precision=1)
+    e.set_params(params); d.set_params(params)
+    for t in range(4):
+        ids, seg, labels = batches[t % 3]
+        e.train_step(ids, seg, labels, pad_rows=pads)
+        d.train_step(ids, seg, labels, pad_rows=pads, dense=True)
+        if t == 1:
+            ids2, seg2, _ = batches[2]
+            s_e, s_d = e.forward(ids2, seg2), d.forward(ids2, seg2)
+            assert_rel(s_e, s_d, rtol=2e-5, what="scores between steps: sparse vs dense engine")
+    ids2, seg2, _ = batches[0]
+    assert_rel(e.forward(ids2, seg2), o.forward(ref, ids2, seg2)["scores"], rtol=5e-4, what="scores after training vs oracle-trained")
+    assert_rel(e.forward(ids2, seg2), d.forward(ids2, seg2), rtol=2e-5, what="scores after training: sparse vs dense")
+    e.close(); d.close()
+
+
+@pytest.mark.parametrize("on_logits", [False, True])
+def test_bpr_train_step_matches_oracle(on_logits):
+    V_e = 2000
+    o, params, _, _, _ = make_case(N=64, seed=72, d_t=8, d_e=64, d_r=8, H=64, V_e=V_e)
+    c = o.cfg
+    pads = (c.V_t, c.V_e, c.V_r)
+    (ids, seg, labels), = _batches(o, 1, 700, 720, V_e)
+    S = len(seg) - 1
+    pos = np.arange(0, S - 1, 2, dtype=np.int32); neg = pos + 1
+    x = params.copy()
+    for tbl, row in enumerate(pads):
+        o.zero_row(x, tbl, row)
+    fwd = o.forward(x, ids, seg, cache=True)
+    if on_logits:
+        a, b = fwd["seg_logits"][pos, 0], fwd["seg_logits"][neg, 0]
+        lv, dp, dn = o.bpr(a, b)
+        dsl = np.zeros((S, c.L)); np.add.at(dsl[:, 0], pos, dp); np.add.at(dsl[:, 0], neg, dn)
+        g_ref = o.backward_logits(x, ids, seg, fwd, dsl)
+    else:
+        lv, dp, dn = o.bpr(fwd["scores"][pos], fwd["scores"][neg])
+        dsc = np.zeros(S); np.add.at(dsc, pos, dp); np.add.at(dsc, neg, dn)
+        g_ref = o.backward(x, ids, seg, fwd, dsc)
+    e = engine_for(o, precision=0)
+    e.set_params(params)
+    loss = e.train_step(ids, seg, None, pos, neg, pad_rows=pads, bpr_on_logits=on_logits)
+    assert abs(loss - lv) <= 1e-4 * abs(lv)
+    g = e.get_grads()                      # dense view of the sparse step's gradient
+    for name in o.shapes():
+        assert_rel(o.view(g, name), o.view(g_ref, name), what="grad " + name)
+    # kprn_train_batch_bpr is the same step
+    e2 = engine_for(o, precision=0)
+    e2.set_params(params)
+    loss2 = e2.train_batch_bpr(ids, seg, pos, neg, on_logits=on_logits, pad_rows=pads)
+    assert abs(loss2 - loss) <= 1e-6 * abs(loss)
+    e.close(); e2.close()
+
+
+def test_clip_in_sparse_step_matches_dense_flow():
+    V_e = 2000
+    o, params, _, _, _ = make_case(N=64, seed=73, d_t=8, d_e=64, d_r=8, H=64, V_e=V_e)
+    c = o.cfg
+    pads = (c.V_t, c.V_e, c.V_r)
+    batches = _batches(o, 2, 400, 730, V_e)
+    outs = []
+    for dense in (False, True):
+        e = engine_for(o, precision=0)
+        e.set_params(params)
+        for t in range(3):
+            ids, seg, labels = batches[t % 2]
+            e.train_step(ids, seg, labels, pad_rows=pads, regularize=True, use_clip=True, clip_norm=1e-3, dense=dense)   # clip active
+        outs.append(e.get_params().astype(np.float64))
+        e.close()
+    d = np.abs(outs[0] - outs[1])
+    assert np.quantile(d, 0.999) <= 2e-6 and d.max() <= 2e-4, (np.quantile(d, 0.999), d.max())
