@@ -422,7 +422,9 @@ def main():
                                 "note": "kprn_forward_f64ids: DoubleTensor[B=%d,P=%d,T,3] host buffer (144 B/path), dense buckets" % (Bb, Pb)}
         del f64
 
-    # ---- train: one MyOptimizer:trainBatch-equivalent step (pad rows -> zero grad -> forward -> BCE -> backward -> Adam) ----
+    # ---- train: MyOptimizer:trainBatch (pad rows -> zero grad -> forward -> BCE -> backward -> optim.adam -> pad rows), one
+    #      65 536-path batch per GPU per step (BASELINE configs[3] flavour); at N > 1 the step contains the collectives:
+    #      ncclAllReduce of the small tensors' gradients + ncclAllGather of (entity row ids, row gradients) ----
     train = None
     if not args.no_train:
         from kprn_b200 import synth
@@ -433,25 +435,65 @@ def main():
                 teng = engine.Engine(T=T, d_t=d_t, d_e=d_e, d_r=d_r, H=d, L=L, V_e=V_E, precision=tprec, device=local)
                 teng.init_uniform(0.1, 12345)
                 teng.set_stream(stream.cuda_stream)
+            if world > 1:
+                box = [engine.Engine.comm_unique_id() if rank == 0 else None]
+                dist.broadcast_object_list(box, src=0)
+                teng.comm_init(rank, world, box[0])
             labels = [synth.make_labels(len(seg) - 1, 12345 + b) for b, (_, seg) in enumerate(batches)]
+            d_lab = [torch.from_numpy(x).cuda() for x in labels]
+            s_loc = torch.tensor([float(len(x)) for x in labels], dtype=torch.float64, device="cuda")
+            s_glob = s_loc.clone()
+            if world > 1:
+                dist.all_reduce(s_glob)
+            gscale = (s_loc / s_glob).cpu().numpy()
             pads = (6, V_E, 9)
             ts = max(3, min(args.steps, 10))
+            topts = [teng.train_opts(grad_scale=float(gscale[b])) for b in range(NB)]
+
+            def step_train(i):
+                ids_t, seg_t, S = dev[i % NB]
+                teng.train_step_device(ids_t.data_ptr(), seg_t.data_ptr(), n_paths, S, d_labels=d_lab[i % NB].data_ptr(), pad_rows=pads,
+                                       opts=topts[i % NB])
             losses = []
+            for i in range(3):
+                step_train(i)
+                losses.append(teng.last_loss())
+            teng.launch_count(reset=True)
+            teng.comm_info(reset=True)
+            t_ms = time_device(teng, step_train, ts, stream, barrier)
+            tl = teng.launch_count(reset=True)
+            ci = teng.comm_info(reset=True)
+            losses.append(teng.last_loss())
+            info = teng.train_info()
+            tt = torch.tensor([t_ms], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            t_ms = float(tt.item())
+            # end to end: host buffers through kprn_train_step (H2D of ids / segments / labels and the loss read-back inside)
             for i in range(2):
-                losses.append(teng.train_batch_bce(host[i % NB][0], host[i % NB][1], labels[i % NB], pad_rows=pads))
+                teng.train_step(host[i % NB][0], host[i % NB][1], labels[i % NB], pad_rows=pads, grad_scale=float(gscale[i % NB]))
             barrier()
             t0 = time.perf_counter()
             for i in range(ts):
-                losses.append(teng.train_batch_bce(host[i % NB][0], host[i % NB][1], labels[i % NB], pad_rows=pads))
+                teng.train_step(host[i % NB][0], host[i % NB][1], labels[i % NB], pad_rows=pads, grad_scale=float(gscale[i % NB]))
             torch.cuda.synchronize()
-            tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+            te2 = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
             if world > 1:
-                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            t_ms = 1e3 * float(tt.item()) / ts
+                dist.all_reduce(te2, op=dist.ReduceOp.MAX)
+            e2e_ms = 1e3 * float(te2.item()) / ts
             train = {"ms_per_step": t_ms, "value": world * n_paths / (t_ms * 1e-3), "unit": "paths/s", "steps": ts,
-                     "mode": "kprn_train_batch_bce, precision %d, host ids (H2D inside), dense optim.adam over %d params" % (tprec, teng.n_params),
-                     "loss_first": losses[0], "loss_last": losses[-1],
-                     "fwd_bwd_flops_per_path": 3 * flops_per_path(d_t, d_e, d_r, d)}
+                     "e2e": {"value": world * n_paths / (e2e_ms * 1e-3), "unit": "paths/s", "ms_per_step": e2e_ms},
+                     "mode": "kprn_train_step_device, precision %d, BCE, row-sparse evaluation of dense optim.adam "
+                             "(%d params; %d distinct entity rows in the last batch)" % (tprec, teng.n_params, info["rows_local"]),
+                     "gpu_launches_per_step": tl / float(ts), "loss_first": losses[0], "loss_last": losses[-1],
+                     "fwd_bwd_flops_per_path": 3 * flops_per_path(d_t, d_e, d_r, d),
+                     "algorithmic_tflops": 3 * flops_per_path(d_t, d_e, d_r, d) * n_paths / (t_ms * 1e-3) / 1e12,
+                     "collectives": {"world": world, "bytes_per_step_per_rank": ci["bytes"] / float(ts), "calls_per_step": ci["calls"] / float(ts),
+                                     "rows_union": info["rows_union"], "rows_gathered": info["rows_gathered"],
+                                     "what": "ncclAllReduce(sum) of the small tensors' gradients (2 ranges) + ncclAllReduce(max) of the row "
+                                             "count + 2 x ncclAllGather (row ids, row gradients)" if world > 1 else "none (1 GPU)"}}
+            if world > 1:
+                teng.comm_destroy()
             if teng is not eng:
                 teng.close()
         except engine.KprnError as err:
