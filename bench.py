@@ -164,6 +164,30 @@ def cpu_port_throughput(d, budget_s=15.0, threads=None, dims=None, keep=False, p
     return n2 / dt2, n2, dt2, cores, out, sample
 
 
+def proxy_baseline(d, dims, conv):
+    """PyTorch-CPU fp64 proxy, timed in a fresh process (the C restatement's OpenMP pool spins in this one and would steal
+    its cores) at the best of a few thread counts."""
+    ncpu = len(os.sched_getaffinity(0))
+    best = None
+    for th in sorted({min(ncpu, x) for x in (16, 32, 64, ncpu)}):
+        code = ("import sys, json; sys.path.insert(0, %r); import bench; "
+                "v, n, dt, c, _, _ = bench.cpu_port_throughput(%d, budget_s=4.0, threads=%d, dims=%r, proxy=True); "
+                "print(json.dumps([v, n, dt]))" % (ROOT, d, th, tuple(dims)))
+        try:
+            out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120,
+                                 env=dict(os.environ, OMP_NUM_THREADS=str(th), MKL_NUM_THREADS=str(th)))
+            v, n, dt = json.loads(out.stdout.strip().splitlines()[-1])
+        except Exception:
+            continue
+        if best is None or v > best[0]:
+            best = (v, n, dt, th)
+    if best is None:
+        return {"error": "proxy run failed"}
+    return {"value": best[0], "unit": "paths/s", "cores": best[3], "kind": "proxy",
+            "sample": "first %d paths of batch 0, PyTorch-CPU fp64 (MKL/oneDNN addmm + elementwise ops), %.1f s, best of 16/32/64/all "
+                      "threads in a fresh process; stand-in for Torch7+MKL, never 'Torch7'" % (best[1], best[2])}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -570,10 +594,7 @@ def main():
             v, n_s, dt, cores, ref, (s_ids, s_seg) = cpu_port_throughput(d, budget_s=15.0, dims=(d_t, d_e, d_r), keep=True)
             line["cpu_baseline"] = {"value": v, "unit": "paths/s", "cores": cores, "kind": "port",
                                     "sample": "first %d paths of batch 0 (the batch the GPU arm times), fp64 C restatement + OpenMP, %.1f s" % (n_s, dt)}
-            vp, n_p, dtp, cp, _, _ = cpu_port_throughput(d, budget_s=8.0, dims=(d_t, d_e, d_r), proxy=True)
-            line["cpu_baseline_proxy"] = {"value": vp, "unit": "paths/s", "cores": cp, "kind": "proxy",
-                                          "sample": "first %d paths of batch 0, PyTorch-CPU fp64 (MKL/oneDNN addmm + elementwise), %.1f s; "
-                                                    "stand-in for Torch7+MKL, never 'Torch7'" % (n_p, dtp)}
+            line["cpu_baseline_proxy"] = proxy_baseline(d, (d_t, d_e, d_r), args.conv)
             # ---- parity: the GPU path against the oracle outputs of the sample just timed (same paths, same parameter values;
             #      outside every timed region; the oracle is the checker here) ----
             try:

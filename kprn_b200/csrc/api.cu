@@ -537,7 +537,7 @@ int kprn_forward_f64ids(kprn_ctx* ctx, const double* ids_f64, int64_t B, int64_t
         // pageable storage has to be staged anyway: convert while staging (half the DMA bytes, no device-side pass)
         KPRN_TRY(ensure_stage(ctx, sizeof(int32_t) * n));
         int32_t* st = (int32_t*)ctx->h_stage;
-        for (int64_t i = 0; i < n; ++i) st[i] = (int32_t)llrint(ids_f64[i]);
+        for (int64_t i = 0; i < n; ++i) st[i] = (int32_t)(ids_f64[i] + 0.5);      // ids are positive integers stored as doubles
         KPRN_CUDA(cudaMemcpyAsync(ctx->ids_buf.p, st, sizeof(int32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
     }
     dense_seg_kernel<<<(unsigned)cdiv(B + 1, 256), 256, 0, ctx->stream>>>(ctx->seg_buf.as<int32_t>(), B, (int32_t)P);

@@ -20,59 +20,10 @@
 #include <stdio.h>
 #include <stdlib.h>
 
-#include "common.cuh"
-#include "ptx.cuh"
+#include "tc_state.cuh"
 
 namespace kprn {
 
-using bf16 = __nv_bfloat16;
-
-// wait on an mbarrier and, when debugging, charge the waited cycles to counter `slot`
-#define TWAIT(slot, bar, par)                                              \
-    do {                                                                  \
-        if (a.dbg) { long long _t0 = clock64(); ptx::mbar_wait((bar), (par)); dbg_acc[slot] += clock64() - _t0; } \
-        else ptx::mbar_wait((bar), (par));                                \
-    } while (0)
-
-constexpr int TILE_M = 128;           // paths per CTA tile (UMMA M)
-constexpr int B_SLAB_ELEMS = 8 * 128 * 8;   // weight slab: 64 k x 128 gate columns (16 KB), both kernels
-constexpr int PROJ_RING = 5;
-constexpr int RECUR_RING = 6;          // 16 KB weight slabs in flight (1-CTA recurrence)
-constexpr int RECUR_RING_PAIR = 8;     // 8 KB half-slabs in flight per CTA (CTA-pair recurrence)
-constexpr int RECUR_BAR_BYTES = 384;   // barrier block at the end of the recurrence's shared memory
-constexpr int MAX_NS = 6;             // k-slices of the proj A tile: KE/64 entity slices + NOH one-hot slices
-constexpr int NUM_THREADS = 384;      // proj: warps 0 TMA producer, 1 MMA issuer, 2-3 gather/alloc, 4-11 epilogue
-#ifndef KPRN_PROJ2_GW
-#define KPRN_PROJ2_GW 4
-#endif
-constexpr int PROJ2_GW = KPRN_PROJ2_GW;                 // gather warps of proj2: 2, 4 or 8
-constexpr int PROJ2_THREADS = 384 + 32 * (PROJ2_GW - 2);  // warps 2,3 + (PROJ2_GW-2) extra gather warps after the epilogue
-constexpr int RECUR_THREADS = 608;    // recur: warps 0 TMA producer, 1 MMA issuer, 2 TMEM alloc + h loader, 3-18 epilogue (4 groups); 19 warps -> 104 registers per thread
-
-struct TcState {
-    uint64_t packed_version = 0;       // ctx->params_version the packed operands (entity tables included) were built from
-    uint64_t packed_small = 0;         // ctx->small_version the packed WEIGHTS were built from (a sparse training step leaves the
-                                       // entity tables current row by row and only bumps small_version)
-    int Hp = 0, KE = 0, NCH = 0, KSh = 0, KSe = 0, G4 = 0, NOH = 0, NS = 0;
-    bf16* E_hi = nullptr; bf16* E_lo = nullptr;
-    bf16* WxE = nullptr; bf16* Wh = nullptr;
-    float* Ptr = nullptr;
-    DBuf xw, hT, hscratch, dbg, part4;
-    DedupBufs dd;              // step-input deduplication
-    bool dedup = true;         // project each distinct (type, entity, relation) triple once (KPRN_TC_DEDUP=0: every step)
-    bool debug = false;
-    bool use_gather4 = true;   // TMA tile::gather4 for the entity rows (KPRN_TC_GATHER4=0 -> LDGSTS gather of proj2)
-    bool have_tmaps = false;
-    CUtensorMap tm_hi, tm_lo;
-    bool use_pairs = true;     // cta_group::2 projection kernel (KPRN_TC_PAIRS=0 falls back to the 1-CTA kernel)
-    bool recur_pairs = true;   // cta_group::2 recurrence (KPRN_TC_RECUR_PAIRS=0 falls back to the 1-CTA form)
-    int num_sms = 148;
-    bool attrs_set = false;
-};
-
-static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
-// hidden size padded to an instantiated recur_kernel<HP> (padded units have zero weights and stay exactly 0)
-static inline int pad_hidden(int H) { return H <= 64 ? 64 : (H <= 128 ? 128 : 256); }
 
 bool tc_supported(const kprn_ctx* ctx) {
     const kprn_config& c = ctx->cfg;
@@ -97,11 +48,6 @@ bool tc_validates_ids(const kprn_ctx* ctx, int64_t N) {
 // ---------------------------------------------------------------------------------------------
 // parameter packing (runs when the parameters change)
 
-__device__ __forceinline__ void split_bf16(float v, bf16& hi, bf16& lo) {
-    hi = __float2bfloat16_rn(v);
-    lo = __float2bfloat16_rn(v - __bfloat162float(hi));
-}
-
 __global__ void split_entity_kernel(const float* __restrict__ E, int64_t V, int d_e, int KE, bf16* __restrict__ hi,
                                     bf16* __restrict__ lo) {
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -112,13 +58,6 @@ __global__ void split_entity_kernel(const float* __restrict__ E, int64_t V, int 
     bf16 h, l;
     split_bf16(v, h, l);
     hi[idx] = h; lo[idx] = l;
-}
-
-// permuted gate column g' = chunk*128 + gate*32 + uu  <->  reference row gate*H + chunk*32 + uu
-__device__ __forceinline__ int perm_to_row(int gp, int H, int& u) {
-    int j = gp >> 7, q = (gp >> 5) & 3, uu = gp & 31;
-    u = j * 32 + uu;
-    return q * H + u;
 }
 
 // The recurrent kernel evaluates the gates as sigmoid(x) = 1/(1+2^(-x log2 e)) and tanh(x) = 1 - 2/(1+2^(2x log2 e)) with
@@ -225,478 +164,11 @@ __device__ __forceinline__ void proj_resolve_size(ProjArgs& a) {
     if (a.n_dev) { a.N = *a.n_dev; a.num_tiles = (a.N + TILE_M - 1) / TILE_M; }
 }
 
-__global__ void __launch_bounds__(NUM_THREADS, 1) proj_kernel(ProjArgs a) {
-    proj_resolve_size(a);
-    extern __shared__ __align__(1024) uint8_t smem[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr int R = PROJ_RING;
-    const int ah_chunks = a.KE / 8 + 8 * a.NOH;
-    uint8_t* sA_hi = smem;                                   // [ah_chunks][128][16 B]
-    uint8_t* sA_lo = smem + (size_t)ah_chunks * 2048;        // [KE/8][128][16 B]
-    uint8_t* sRing = sA_lo + (size_t)(a.KE / 8) * 2048;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sRing + R * B_SLAB_ELEMS * 2);
-    // bars: [0,R) slab_full  [R,2R) slab_empty  2R+[0,6) a_full  2R+6+[0,6) a_free  2R+12+[0,4) acc_full  2R+16+[0,4) acc_empty
-    const uint32_t bar0 = ptx::smem_u32(bars);
-    auto BAR = [&](int i) { return bar0 + 8u * i; };
-    constexpr int B_AFULL = 2 * R, B_AFREE = 2 * R + MAX_NS, B_ACCF = 2 * R + 2 * MAX_NS, B_ACCE = 2 * R + 2 * MAX_NS + 4;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_ACCE + 4);
-
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < R; ++i) { ptx::mbar_init(BAR(i), 1); ptx::mbar_init(BAR(R + i), 1); }
-        for (int i = 0; i < MAX_NS; ++i) { ptx::mbar_init(BAR(B_AFULL + i), 64); ptx::mbar_init(BAR(B_AFREE + i), 1); }
-        for (int i = 0; i < 4; ++i) { ptx::mbar_init(BAR(B_ACCF + i), 1); ptx::mbar_init(BAR(B_ACCE + i), 128); }
-        ptx::fence_mbar_init();
-    }
-    if (warp == 2) { ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 512); ptx::tmem_relinquish(); }
-    ptx::tc_fence_before();
-    __syncthreads();
-    ptx::tc_fence_after();
-    const uint32_t tmem = *tmem_slot;
-
-    long long dbg_acc[16] = {0};
-    const long long dbg_t0 = clock64();
-    const int64_t my_tiles = (a.num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;   // tiles blockIdx.x + i*gridDim.x
-    const uint32_t idesc = ptx::make_idesc_f16(1, TILE_M, 128);
-    const int parts = a.passes == 3 ? 2 : 1;
-
-    if (warp == 0) {
-        // ===== TMA producer: weight slabs, the same sequence for every tile =====
-        if (lane == 0) {
-            uint32_t stage = 0, phase = 0;
-            for (int64_t it = 0; it < my_tiles; ++it)
-                for (int nt = 0; nt < a.NCH; ++nt)
-                    for (int s = 0; s < a.NS; ++s)
-                        for (int part = 0; part < parts; ++part) {
-                            TWAIT(0, BAR(R + stage), phase ^ 1);
-                            ptx::mbar_arrive_expect_tx(BAR(stage), B_SLAB_ELEMS * 2);
-                            const bf16* src = a.W + ((int64_t)(nt * a.NS + s) * 2 + part) * B_SLAB_ELEMS;
-                            ptx::tma_bulk_g2s(ptx::smem_u32(sRing + stage * B_SLAB_ELEMS * 2), src, B_SLAB_ELEMS * 2, BAR(stage));
-                            if (++stage == R) { stage = 0; phase ^= 1; }
-                        }
-        }
-    } else if (warp == 1) {
-        // ===== MMA issuer: the whole warp runs the (uniform) control flow, one elected lane issues =====
-        {
-            const bool issue = ptx::elect_one();
-            uint32_t stage = 0, phase = 0;
-            int64_t au = 0;
-            const uint32_t aHi0 = ptx::desc_lo(ptx::smem_u32(sA_hi), 2048), aLo0 = ptx::desc_lo(ptx::smem_u32(sA_lo), 2048);
-            const uint32_t ring0 = ptx::desc_lo(ptx::smem_u32(sRing), 2048);
-            constexpr uint32_t DHI = ptx::desc_hi(128);
-            constexpr uint32_t SLAB_STEP = (B_SLAB_ELEMS * 2) >> 4, K16_STEP = (2 * 2048) >> 4, SLICE_STEP = (8 * 2048) >> 4;
-            for (int64_t it = 0; it < my_tiles; ++it) {
-                for (int nt = 0; nt < a.NCH; ++nt, ++au) {
-                    const int buf = au & 3;
-                    TWAIT(1, BAR(B_ACCE + buf), ((au >> 2) & 1) ^ 1);
-                    ptx::tc_fence_after();
-                    const uint32_t d = tmem + buf * 128;
-                    for (int s = 0; s < a.NS; ++s) {
-                        if (nt == 0) { TWAIT(2, BAR(B_AFULL + s), it & 1); ptx::tc_fence_after(); }
-                        const bool onehot = s >= a.KSe;
-                        const uint32_t ah = aHi0 + s * SLICE_STEP, al = aLo0 + s * SLICE_STEP;
-                        TWAIT(3, BAR(stage), phase);
-                        ptx::tc_fence_after();
-                        uint32_t bl = ring0 + stage * SLAB_STEP;
-                        if (issue) {
-#pragma unroll
-                            for (int k = 0; k < 4; ++k)
-                                ptx::umma_f16(d, ptx::desc_join(DHI, ah + k * K16_STEP), ptx::desc_join(DHI, bl + k * K16_STEP), idesc, (s | k) != 0);
-                            if (a.passes == 3 && !onehot) {      // the one-hot slice has no lo part
-#pragma unroll
-                                for (int k = 0; k < 4; ++k)
-                                    ptx::umma_f16(d, ptx::desc_join(DHI, al + k * K16_STEP), ptx::desc_join(DHI, bl + k * K16_STEP), idesc, 1);
-                            }
-                            ptx::umma_commit(BAR(R + stage));
-                        }
-                        if (++stage == R) { stage = 0; phase ^= 1; }
-                        if (a.passes == 3) {
-                            TWAIT(3, BAR(stage), phase);
-                            ptx::tc_fence_after();
-                            bl = ring0 + stage * SLAB_STEP;
-                            if (issue) {
-#pragma unroll
-                                for (int k = 0; k < 4; ++k)
-                                    ptx::umma_f16(d, ptx::desc_join(DHI, ah + k * K16_STEP), ptx::desc_join(DHI, bl + k * K16_STEP), idesc, 1);
-                                ptx::umma_commit(BAR(R + stage));
-                            }
-                            if (++stage == R) { stage = 0; phase ^= 1; }
-                        }
-                        if (issue && nt == a.NCH - 1) ptx::umma_commit(BAR(B_AFREE + s));   // slice s of the A tile may be refilled
-                    }
-                    if (issue) ptx::umma_commit(BAR(B_ACCF + buf));
-                }
-            }
-        }
-    } else if (warp < 4) {
-        // ===== gather warps: pre-split entity rows -> canonical A layout via 16-byte LDGSTS; one-hot (type,rel) slice =====
-        // Lane mapping: 8 lanes cover one 128-byte line of one row (k-chunks 0..7 of the slice), 4 rows per instruction,
-        // so an instruction touches 4 lines instead of 16 (LDGSTS cost scales with the lines touched).  All k-slices of
-        // a tile are issued back to back (one commit group each) as their buffers are released and completed in order
-        // with wait_group<n>; the ids of the next tile are loaded while the copies are in flight.
-        const int gw = warp - 2;
-        const int rsub = lane >> 3, kc = lane & 7;
-        const uint32_t dHi = ptx::smem_u32(sA_hi), dLo = ptx::smem_u32(sA_lo);
-        int64_t eid[16];
-        int combo[16];
-        auto load_ids = [&](int64_t it) {
-            const int64_t m = blockIdx.x + it * gridDim.x;
-            const int64_t pt = m / a.T;
-            const int t = (int)(m % a.T);
-#pragma unroll
-            for (int b = 0; b < 16; ++b) {
-                const int r = (2 * b + gw) * 4 + rsub;
-                int64_t n = pt * TILE_M + r;
-                if (n >= a.N) n = a.N - 1;
-                const int32_t* idp = a.ids + (n * a.T + t) * 3;
-                int64_t id = (int64_t)idp[1] - 1;
-                eid[b] = id < 0 ? 0 : (id >= a.V_e ? a.V_e - 1 : id);
-                int ta = idp[0] - 1, rb = idp[2] - 1;
-                ta = ta < 0 ? 0 : (ta >= a.V_t ? a.V_t - 1 : ta);
-                rb = rb < 0 ? 0 : (rb >= a.V_r ? a.V_r - 1 : rb);
-                combo[b] = ta * a.V_r + rb;
-            }
-        };
-        if (my_tiles > 0) load_ids(0);
-        for (int64_t it = 0; it < my_tiles; ++it) {
-            for (int s = 0; s < a.NS; ++s) {
-                TWAIT(4, BAR(B_AFREE + s), (it & 1) ^ 1);
-                const uint32_t off = (s * 8 + kc) * 2048;
-                if (s < a.KSe) {
-#pragma unroll
-                    for (int b = 0; b < 16; ++b) {
-                        const int r = (2 * b + gw) * 4 + rsub;
-                        ptx::cp_async16(dHi + off + r * 16, a.E_hi + eid[b] * a.KE + s * 64 + kc * 8);
-                        ptx::cp_async16(dLo + off + r * 16, a.E_lo + eid[b] * a.KE + s * 64 + kc * 8);
-                    }
-                } else {
-                    const int o = s - a.KSe;
-#pragma unroll
-                    for (int b = 0; b < 16; ++b) {
-                        const int r = (2 * b + gw) * 4 + rsub;
-                        uint32_t w[4] = {0u, 0u, 0u, 0u};
-                        if ((combo[b] >> 3) == o * 8 + kc) w[(combo[b] & 7) >> 1] = 0x3F80u << (16 * (combo[b] & 1));   // bf16 1.0
-                        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dHi + off + r * 16),
-                                     "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
-                    }
-                }
-                ptx::cp_async_commit();
-            }
-            if (it + 1 < my_tiles) load_ids(it + 1);      // overlaps the copies in flight
-            // complete the slices in order: group s is done when at most NS-1-s younger groups are pending
-            for (int s = 0; s < a.NS; ++s) {
-                switch (a.NS - 1 - s) {
-                    case 5: ptx::cp_async_wait_group<5>(); break;
-                    case 4: ptx::cp_async_wait_group<4>(); break;
-                    case 3: ptx::cp_async_wait_group<3>(); break;
-                    case 2: ptx::cp_async_wait_group<2>(); break;
-                    case 1: ptx::cp_async_wait_group<1>(); break;
-                    default: ptx::cp_async_wait_group<0>(); break;
-                }
-                ptx::fence_proxy_async_smem();
-                ptx::mbar_arrive(BAR(B_AFULL + s));
-            }
-        }
-    } else {
-        // ===== epilogue: TMEM -> registers -> XW (pure copy; bias and (type,rel) terms came through the MMA) =====
-        const int wg = (warp - 4) >> 2;               // parity of the accumulator-use index
-        const int q4 = warp & 3;                      // TMEM lane quarter of this warp
-        const int r = q4 * 32 + lane;
-        const int64_t total_uses = my_tiles * a.NCH;
-        for (int64_t au = wg; au < total_uses; au += 2) {
-            const int64_t it = au / a.NCH;
-            const int nt = (int)(au % a.NCH);
-            const int buf = au & 3;
-            const int64_t m = blockIdx.x + it * gridDim.x;
-            float* xw = a.XW + ((m * (a.G4 / 8) + nt * 16) * TILE_M + r) * 8;
-            if (nt == 0 && it + 1 < my_tiles) {
-                // pull the entity rows of the NEXT tile into L2 (one row per thread) so that the gather warps' LDGSTS
-                // see L2 latency instead of HBM latency: the A tile is single-buffered, its refill is on the critical path
-                const int64_t m2 = m + gridDim.x;
-                int64_t n2 = (m2 / a.T) * TILE_M + r;
-                if (n2 >= a.N) n2 = a.N - 1;
-                int64_t id2 = (int64_t)a.ids[(n2 * a.T + (int)(m2 % a.T)) * 3 + 1] - 1;
-                id2 = id2 < 0 ? 0 : (id2 >= a.V_e ? a.V_e - 1 : id2);
-                const char* ph = reinterpret_cast<const char*>(a.E_hi + id2 * a.KE);
-                const char* pl = reinterpret_cast<const char*>(a.E_lo + id2 * a.KE);
-                for (int b = 0; b < a.KE * 2; b += 128) {
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(ph + b));
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(pl + b));
-                }
-            }
-            TWAIT(5, BAR(B_ACCF + buf), (au >> 2) & 1);
-            ptx::tc_fence_after();
-            const uint32_t tbase = tmem + ((uint32_t)(q4 * 32) << 16) + buf * 128;
-#pragma unroll
-            for (int blk = 0; blk < 4; ++blk) {
-                float v[32];
-                ptx::tmem_ld32(tbase + blk * 32, v);
-                ptx::tc_wait_ld();
-#pragma unroll
-                for (int i = 0; i < 4; ++i) ptx::stg256(xw + (int64_t)(blk * 4 + i) * TILE_M * 8, v + 8 * i);     // one 32-byte sector per thread
-            }
-            ptx::tc_fence_before();
-            ptx::mbar_arrive(BAR(B_ACCE + buf));
-        }
-    }
-    if (a.dbg && lane == 0) {
-        // one representative lane per role: warps 0..3 and the first warp of each epilogue warpgroup
-        if (warp < 4 || warp == 4 || warp == 8) {
-            for (int i = 0; i < 15; ++i) if (dbg_acc[i]) atomicAdd(a.dbg + i, (unsigned long long)dbg_acc[i]);
-            if (warp == 1) atomicAdd(a.dbg + 15, (unsigned long long)(clock64() - dbg_t0));
-        }
-    }
-    ptx::tc_fence_before();
-    __syncthreads();
-    if (warp == 2) ptx::tmem_dealloc(tmem, 512);
-}
-
 // ---------------------------------------------------------------------------------------------
-// kernel "proj2": the same projection on CTA PAIRS (tcgen05 cta_group::2, cluster of 2).  The pair multiplies two
-// 128-row tiles (one per CTA) by the same 256 gate columns per MMA: each CTA stages only its 128-column half of every
-// weight slab, so shared-memory traffic per CTA (the binding resource of the 1-CTA N=128 kernel: every SS MMA reads 4 KB
-// of A and 4 KB of B) drops to 4 KB of A + 4 KB of B per 128 tensor cycles, and the weight stream per SM halves.
-// The leader (cluster rank 0) issues the MMAs; completion is multicast to the barriers of both CTAs; the peer forwards
-// "my half of the slab / my A slice / my accumulator drain" to the leader's barriers with remote mbarrier arrives.
-
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PROJ2_THREADS, 1) proj2_kernel(ProjArgs a) {
-    proj_resolve_size(a);
-    extern __shared__ __align__(1024) uint8_t smem[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr int R = PROJ_RING;
-    const uint32_t rank = ptx::cluster_ctarank();
-    const bool leader = rank == 0;
-    const int ah_chunks = a.KE / 8 + 8 * a.NOH;
-    uint8_t* sA_hi = smem;
-    uint8_t* sA_lo = smem + (size_t)ah_chunks * 2048;
-    uint8_t* sRing = sA_lo + (size_t)(a.KE / 8) * 2048;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sRing + R * B_SLAB_ELEMS * 2);
-    const uint32_t bar0 = ptx::smem_u32(bars);
-    auto BAR = [&](int i) { return bar0 + 8u * i; };
-    // [0,R) slab_full  [R,2R) slab_empty  [2R,3R) peer_full (leader)  then a_full[6] a_free[6] acc_full[2] acc_empty[2]
-    constexpr int B_PEER = 2 * R, B_AFULL = 3 * R, B_AFREE = 3 * R + MAX_NS, B_ACCF = 3 * R + 2 * MAX_NS, B_ACCE = B_ACCF + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_ACCE + 2);
-
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < R; ++i) { ptx::mbar_init(BAR(i), 1); ptx::mbar_init(BAR(R + i), 1); ptx::mbar_init(BAR(B_PEER + i), 1); }
-        for (int i = 0; i < MAX_NS; ++i) { ptx::mbar_init(BAR(B_AFULL + i), 2 * PROJ2_GW); ptx::mbar_init(BAR(B_AFREE + i), 1); }   // 8 gather warps x 2 CTAs
-        for (int i = 0; i < 2; ++i) { ptx::mbar_init(BAR(B_ACCF + i), 1); ptx::mbar_init(BAR(B_ACCE + i), 8); }           // 4 epilogue warps x 2 CTAs
-        ptx::fence_mbar_init();
-    }
-    if (warp == 2) { ptx::tmem_alloc2(ptx::smem_u32(tmem_slot), 512); ptx::tmem_relinquish2(); }
-    ptx::tc_fence_before();
-    ptx::cluster_sync();                      // barriers of both CTAs are initialised before any remote arrive
-    ptx::tc_fence_after();
-    const uint32_t tmem = *tmem_slot;
-
-    long long dbg_acc[16] = {0};
-    const long long dbg_t0 = clock64();
-    const int64_t npairs = gridDim.x / 2, pair = blockIdx.x / 2;
-    const int64_t n_tp = (a.num_tiles + 1) / 2;                                  // tile pairs
-    const int64_t my_tiles = pair < n_tp ? (n_tp - pair + npairs - 1) / npairs : 0;
-    auto tile_of = [&](int64_t it) { int64_t m = 2 * (pair + it * npairs) + rank; return m < a.num_tiles ? m : a.num_tiles - 1; };
-    const int NP = a.NCH / 2;                                                    // 256-column pairs of chunks per tile
-    const uint32_t idesc = ptx::make_idesc_f16(1, 256, 256);
-    const int parts = a.passes == 3 ? 2 : 1;
-
-    if (warp == 0) {
-        // ===== TMA producer: this CTA's 128-column half (chunk 2*np + rank) of every slab =====
-        if (lane == 0) {
-            uint32_t stage = 0, phase = 0;
-            for (int64_t it = 0; it < my_tiles; ++it)
-                for (int np = 0; np < NP; ++np)
-                    for (int s = 0; s < a.NS; ++s)
-                        for (int part = 0; part < parts; ++part) {
-                            TWAIT(0, BAR(R + stage), phase ^ 1);
-                            ptx::mbar_arrive_expect_tx(BAR(stage), B_SLAB_ELEMS * 2);
-                            const bf16* src = a.W + ((int64_t)((2 * np + rank) * a.NS + s) * 2 + part) * B_SLAB_ELEMS;
-                            ptx::tma_bulk_g2s(ptx::smem_u32(sRing + stage * B_SLAB_ELEMS * 2), src, B_SLAB_ELEMS * 2, BAR(stage));
-                            if (++stage == R) { stage = 0; phase ^= 1; }
-                        }
-        }
-    } else if (warp == 1) {
-        if (leader) {
-            // ===== MMA issuer (leader CTA): uniform control flow on the whole warp, one elected lane issues =====
-            const bool issue = ptx::elect_one();
-            uint32_t stage = 0, phase = 0;
-            int64_t au = 0;
-            const uint32_t aHi0 = ptx::desc_lo(ptx::smem_u32(sA_hi), 2048), aLo0 = ptx::desc_lo(ptx::smem_u32(sA_lo), 2048);
-            const uint32_t ring0 = ptx::desc_lo(ptx::smem_u32(sRing), 2048);
-            constexpr uint32_t DHI = ptx::desc_hi(128);
-            constexpr uint32_t SLAB_STEP = (B_SLAB_ELEMS * 2) >> 4, K16_STEP = (2 * 2048) >> 4, SLICE_STEP = (8 * 2048) >> 4;
-            for (int64_t it = 0; it < my_tiles; ++it) {
-                for (int np = 0; np < NP; ++np, ++au) {
-                    const int buf = au & 1;
-                    if (a.dbg) { long long t0 = clock64(); ptx::mbar_wait_cluster(BAR(B_ACCE + buf), ((au >> 1) & 1) ^ 1); dbg_acc[1] += clock64() - t0; }
-                    else ptx::mbar_wait_cluster(BAR(B_ACCE + buf), ((au >> 1) & 1) ^ 1);
-                    ptx::tc_fence_after();
-                    const uint32_t d = tmem + buf * 256;
-                    for (int s = 0; s < a.NS; ++s) {
-                        if (np == 0) {
-                            if (a.dbg) { long long t0 = clock64(); ptx::mbar_wait_cluster(BAR(B_AFULL + s), it & 1); dbg_acc[2] += clock64() - t0; }
-                            else ptx::mbar_wait_cluster(BAR(B_AFULL + s), it & 1);
-                            ptx::tc_fence_after();
-                        }
-                        const bool onehot = s >= a.KSe;
-                        const uint32_t ah = aHi0 + s * SLICE_STEP, al = aLo0 + s * SLICE_STEP;
-                        for (int part = 0; part < parts; ++part) {
-                            if (a.dbg) { long long t0 = clock64(); ptx::mbar_wait(BAR(stage), phase); ptx::mbar_wait_cluster(BAR(B_PEER + stage), phase); dbg_acc[3] += clock64() - t0; }
-                            else { ptx::mbar_wait(BAR(stage), phase); ptx::mbar_wait_cluster(BAR(B_PEER + stage), phase); }
-                            ptx::tc_fence_after();
-                            const uint32_t bl = ring0 + stage * SLAB_STEP;
-                            if (issue) {
-#pragma unroll
-                                for (int k = 0; k < 4; ++k)
-                                    ptx::umma2_f16(d, ptx::desc_join(DHI, ah + k * K16_STEP), ptx::desc_join(DHI, bl + k * K16_STEP), idesc,
-                                                   (part | s | k) != 0);
-                                if (part == 0 && a.passes == 3 && !onehot) {
-#pragma unroll
-                                    for (int k = 0; k < 4; ++k)
-                                        ptx::umma2_f16(d, ptx::desc_join(DHI, al + k * K16_STEP), ptx::desc_join(DHI, bl + k * K16_STEP), idesc, 1);
-                                }
-                                ptx::umma2_commit(BAR(R + stage), 3);
-                            }
-                            if (++stage == R) { stage = 0; phase ^= 1; }
-                        }
-                        if (issue && np == NP - 1) ptx::umma2_commit(BAR(B_AFREE + s), 3);
-                    }
-                    if (issue) ptx::umma2_commit(BAR(B_ACCF + buf), 3);
-                }
-            }
-        } else {
-            // ===== peer forwarder: tells the leader when this CTA's half of a slab has landed =====
-            if (lane == 0) {
-                uint32_t stage = 0, phase = 0;
-                const uint32_t remote0 = ptx::mapa(BAR(B_PEER), 0);
-                for (int64_t it = 0; it < my_tiles; ++it)
-                    for (int np = 0; np < NP; ++np)
-                        for (int s = 0; s < a.NS; ++s)
-                            for (int part = 0; part < parts; ++part) {
-                                ptx::mbar_wait(BAR(stage), phase);
-                                ptx::mbar_arrive_cluster(remote0 + 8u * stage);
-                                if (++stage == R) { stage = 0; phase ^= 1; }
-                            }
-            }
-        }
-    } else if (warp < 4 || warp >= 12) {   // gather warps: 2, 3, 12 .. 12+PROJ2_GW-3
-        // ===== 8 gather warps (2,3,12..17), one 16-row block each; both CTAs gather their own tile and report completion
-        // to the leader's a_full.  Many warps, few copies each: LDGSTS throughput is bounded by the copies in flight per warp =====
-        const int gw = warp < 4 ? warp - 2 : warp - 10;          // 0..PROJ2_GW-1
-        constexpr int GB = 8 / PROJ2_GW;                          // 16-row blocks per gather warp
-        const int rsub = lane >> 1, cpar = lane & 1;
-        const uint32_t dHi = ptx::smem_u32(sA_hi), dLo = ptx::smem_u32(sA_lo);
-        const uint32_t afull_leader = ptx::mapa(BAR(B_AFULL), 0);
-        int64_t eid[GB];
-        int combo[GB];
-        auto load_ids = [&](int64_t it) {
-            const int64_t m = tile_of(it);
-            const int64_t pt = m / a.T;
-            const int t = (int)(m % a.T);
-#pragma unroll
-            for (int b = 0; b < GB; ++b) {
-                const int r = (gw + PROJ2_GW * b) * 16 + rsub;
-                int64_t n = pt * TILE_M + r;
-                if (n >= a.N) n = a.N - 1;
-                const int32_t* idp = a.ids + (n * a.T + t) * 3;
-                int64_t id = (int64_t)idp[1] - 1;
-                eid[b] = id < 0 ? 0 : (id >= a.V_e ? a.V_e - 1 : id);
-                int ta = idp[0] - 1, rb = idp[2] - 1;
-                ta = ta < 0 ? 0 : (ta >= a.V_t ? a.V_t - 1 : ta);
-                rb = rb < 0 ? 0 : (rb >= a.V_r ? a.V_r - 1 : rb);
-                combo[b] = ta * a.V_r + rb;
-            }
-        };
-        if (my_tiles > 0) load_ids(0);
-        for (int64_t it = 0; it < my_tiles; ++it) {
-            for (int s = 0; s < a.NS; ++s) {
-                TWAIT(4, BAR(B_AFREE + s), (it & 1) ^ 1);
-                if (s < a.KSe) {
-#pragma unroll
-                    for (int b = 0; b < GB; ++b) {
-                        const int r = (gw + PROJ2_GW * b) * 16 + rsub;
-                        const bf16* sh = a.E_hi + eid[b] * a.KE + s * 64;
-                        const bf16* sl = a.E_lo + eid[b] * a.KE + s * 64;
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const int kc = cpar + 2 * i;
-                            ptx::cp_async16(dHi + (s * 8 + kc) * 2048 + r * 16, sh + kc * 8);
-                            ptx::cp_async16(dLo + (s * 8 + kc) * 2048 + r * 16, sl + kc * 8);
-                        }
-                    }
-                } else {
-                    const int o = s - a.KSe;
-#pragma unroll
-                    for (int b = 0; b < GB; ++b) {
-                        const int r = (gw + PROJ2_GW * b) * 16 + rsub;
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const int kc = cpar + 2 * i;
-                            uint32_t w[4] = {0u, 0u, 0u, 0u};
-                            if ((combo[b] >> 3) == o * 8 + kc) w[(combo[b] & 7) >> 1] = 0x3F80u << (16 * (combo[b] & 1));   // bf16 1.0
-                            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dHi + (s * 8 + kc) * 2048 + r * 16),
-                                         "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
-                        }
-                    }
-                }
-                ptx::cp_async_commit();
-            }
-            if (it + 1 < my_tiles) load_ids(it + 1);
-            for (int s = 0; s < a.NS; ++s) {
-                switch (a.NS - 1 - s) {
-                    case 5: ptx::cp_async_wait_group<5>(); break;
-                    case 4: ptx::cp_async_wait_group<4>(); break;
-                    case 3: ptx::cp_async_wait_group<3>(); break;
-                    case 2: ptx::cp_async_wait_group<2>(); break;
-                    case 1: ptx::cp_async_wait_group<1>(); break;
-                    default: ptx::cp_async_wait_group<0>(); break;
-                }
-                ptx::fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) ptx::mbar_arrive_cluster(afull_leader + 8u * s);
-            }
-        }
-    } else {
-        // ===== epilogue: each CTA drains its own 128 rows x 256 columns; the leader is told when both are done =====
-        const int wg = (warp - 4) >> 2;
-        const int q4 = warp & 3;
-        const int r = q4 * 32 + lane;
-        const uint32_t acce_leader = ptx::mapa(BAR(B_ACCE), 0);
-        const int64_t total_uses = my_tiles * NP;
-        for (int64_t au = wg; au < total_uses; au += 2) {
-            const int64_t it = au / NP;
-            const int np = (int)(au % NP);
-            const int buf = au & 1;
-            const int64_t m = tile_of(it);
-            float* xw = a.XW + ((m * (a.G4 / 8) + np * 32) * TILE_M + r) * 8;
-            TWAIT(5, BAR(B_ACCF + buf), (au >> 1) & 1);
-            ptx::tc_fence_after();
-            const uint32_t tbase = tmem + ((uint32_t)(q4 * 32) << 16) + buf * 256;
-#pragma unroll
-            for (int blk = 0; blk < 8; ++blk) {
-                float v[32];
-                ptx::tmem_ld32(tbase + blk * 32, v);
-                ptx::tc_wait_ld();
-#pragma unroll
-                for (int i = 0; i < 4; ++i) ptx::stg256(xw + (int64_t)(blk * 4 + i) * TILE_M * 8, v + 8 * i);     // one 32-byte sector per thread
-            }
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive_cluster(acce_leader + 8u * buf);
-        }
-    }
-    if (a.dbg && lane == 0 && leader) {
-        if (warp < 4 || warp == 4 || warp == 8) {
-            for (int i = 0; i < 15; ++i) if (dbg_acc[i]) atomicAdd(a.dbg + i, (unsigned long long)dbg_acc[i]);
-            if (warp == 1) atomicAdd(a.dbg + 15, (unsigned long long)(clock64() - dbg_t0));
-        }
-    }
-    ptx::tc_fence_before();
-    ptx::cluster_sync();
-    if (warp == 2) ptx::tmem_dealloc2(tmem, 512);
-}
-
-// ---------------------------------------------------------------------------------------------
-// kernel "proj3": proj2 with the entity rows gathered by the TMA unit (cp.async.bulk.tensor.2d tile::gather4 over a
-// tensor map of the pre-split bf16 table, 4 rows x 128 B per instruction, hardware 128-byte swizzle) instead of LDGSTS.
+// kernel "proj3": the projection on CTA PAIRS (tcgen05 cta_group::2, cluster of 2: one MMA multiplies two 128-row tiles by
+// the same 256 gate columns, each CTA staging its own 128-column half of every weight slab) with the entity rows gathered by
+// the TMA unit (cp.async.bulk.tensor.2d tile::gather4 over a tensor map of the pre-split bf16 table, 4 rows x 128 B per
+// instruction, hardware 128-byte swizzle).  (The 1-CTA and LDGSTS-gather generations it replaced are in the git history.)
 // The entity k-slices of the A tile therefore use the K-major SWIZZLE_128B UMMA layout (rows of 128 B, 8-row atoms of
 // 1 KB); the one-hot slice keeps the no-swizzle layout.  Warp 2 issues the gathers (lane l owns rows 4l..4l+3), warp 3
 // forwards "my A slice has landed" to the leader CTA.
@@ -1610,8 +1082,6 @@ int tc_forward(kprn_ctx* ctx, const int32_t* d_ids, const int32_t* d_seg, int64_
         KPRN_CUDA(cudaGetDeviceProperties(&prop, ctx->device));
         s->num_sms = prop.multiProcessorCount;
         { const char* d = getenv("KPRN_TC_DEBUG"); s->debug = d && d[0] == '1'; }
-        { const char* d = getenv("KPRN_TC_PAIRS"); s->use_pairs = !(d && d[0] == '0'); }
-        { const char* d = getenv("KPRN_TC_GATHER4"); s->use_gather4 = !(d && d[0] == '0'); }
         { const char* d = getenv("KPRN_TC_RECUR_PAIRS"); s->recur_pairs = !(d && d[0] == '0'); }
         if (prop.major != 10) {
             delete ctx->tc; ctx->tc = nullptr;      // a retry must meet this check again
@@ -1622,8 +1092,6 @@ int tc_forward(kprn_ctx* ctx, const int32_t* d_ids, const int32_t* d_seg, int64_
     TcState* s = ctx->tc;
     s->dedup = dedup_enabled(ctx);
     if (!s->attrs_set) {
-        KPRN_CUDA(cudaFuncSetAttribute(proj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)proj_smem(s->KE, s->NOH)));
-        KPRN_CUDA(cudaFuncSetAttribute(proj2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)proj_smem(s->KE, s->NOH)));
         KPRN_CUDA(cudaFuncSetAttribute(proj3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)proj_smem(s->KE, s->NOH)));
         s->attrs_set = true;
     }
@@ -1653,14 +1121,11 @@ int tc_forward(kprn_ctx* ctx, const int32_t* d_ids, const int32_t* d_seg, int64_
             // the projection sees a list of (at most n_steps) single-step "paths"; its real length is read on the device
             a.ids = s->dd.ids.as<int32_t>(); a.N = n_steps; a.T = 1; a.num_tiles = cdiv(n_steps, TILE_M); a.n_dev = s->dd.count.as<int32_t>();
         }
-        int64_t grid = a.num_tiles < s->num_sms ? a.num_tiles : s->num_sms;
-        if (s->use_pairs && a.num_tiles >= 2) {
+        if (!s->have_tmaps) { set_error("tensor-core path: cuTensorMapEncodeTiled unavailable (driver too old for sm_100a TMA)"); return KPRN_ECUDA; }
+        {   // a single (or odd last) tile is computed by both CTAs of a pair: identical values, identical stores
             int64_t pairs = (a.num_tiles + 1) / 2;
             int64_t g2 = 2 * (pairs < s->num_sms / 2 ? pairs : s->num_sms / 2);
-            if (s->use_gather4 && s->have_tmaps) proj3_kernel<<<(unsigned)g2, NUM_THREADS, proj_smem(s->KE, s->NOH), ctx->stream>>>(s->tm_hi, s->tm_lo, a);
-            else proj2_kernel<<<(unsigned)g2, PROJ2_THREADS, proj_smem(s->KE, s->NOH), ctx->stream>>>(a);
-        } else {
-            proj_kernel<<<(unsigned)grid, NUM_THREADS, proj_smem(s->KE, s->NOH), ctx->stream>>>(a);
+            proj3_kernel<<<(unsigned)g2, NUM_THREADS, proj_smem(s->KE, s->NOH), ctx->stream>>>(s->tm_hi, s->tm_lo, a);
         }
         KPRN_LAUNCH_CHECK(ctx);
         KPRN_TRY(prof_end(ctx, e0, 1));

@@ -65,9 +65,12 @@ def test_bench_config_matches_oracle(case):
     assert_rel(s2, ref["scores"], what="scores, scores-only path")
     cls = e.forward(ids, seg, want_logits=True)[1][:, 0]
     assert_rel(cls, ref["seg_logits"][:, 0], what="class logit")
-    # %.5f strings as test_from_checkpoint.lua:112 prints them
+    # %.5f strings as test_from_checkpoint.lua:112 prints them.  A float32 score near 0.5 is itself only known to 3e-8, so
+    # ~0.3 % of the strings sit within that distance of a rounding boundary and print the other neighbour than the fp64
+    # oracle's does (the reference's own fp32 GPU run would too); more than 1 % would mean a real error.
     mism = sum(1 for a, b in zip(s2, ref["scores"]) if "%.5f" % a != "%.5f" % b)
-    assert mism <= max(1, len(s2) // 2000), "%d of %d five-decimal score strings differ" % (mism, len(s2))
+    assert mism <= max(2, len(s2) // 100), "%d of %d five-decimal score strings differ" % (mism, len(s2))
+    assert max(abs(float("%.5f" % a) - float("%.5f" % b)) for a, b in zip(s2, ref["scores"])) <= 1.01e-5
     e.close()
 
 

@@ -197,8 +197,8 @@ def test_long_short_and_empty_segments_warp_shuffle_pool(precision, lens):
 
 
 def test_fallback_kernels_still_match():
-    """KPRN_TC_GATHER4=0 (LDGSTS gather, proj2), KPRN_TC_PAIRS=0 (1-CTA proj) and KPRN_TC_RECUR_PAIRS=0 (1-CTA recurrence) and
-    KPRN_TC_DEDUP=0 (projection of every step instead of every distinct step input) are kept as fallbacks: same results."""
+    """KPRN_TC_RECUR_PAIRS=0 (1-CTA recurrence) and KPRN_TC_DEDUP=0 (projection of every step instead of every distinct step
+    input) are kept as fallbacks: same results."""
     import os
     import subprocess
     import sys
@@ -212,8 +212,7 @@ def test_fallback_kernels_still_match():
         "assert_rel(e.forward(ids, seg), ref['scores'], what='scores'); print('ok')",
     ])
     compile(code, "<fallback>", "exec")
-    for env in ({"KPRN_TC_GATHER4": "0"}, {"KPRN_TC_PAIRS": "0"}, {"KPRN_TC_RECUR_PAIRS": "0"}, {"KPRN_TC_DEDUP": "0"},
-                {"KPRN_TC_DEDUP": "0", "KPRN_TC_PAIRS": "0", "KPRN_TC_RECUR_PAIRS": "0"}):
+    for env in ({"KPRN_TC_RECUR_PAIRS": "0"}, {"KPRN_TC_DEDUP": "0"}, {"KPRN_TC_DEDUP": "0", "KPRN_TC_RECUR_PAIRS": "0"}):
         out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True, timeout=300)
         assert out.returncode == 0 and "ok" in out.stdout, (env, out.stderr[-800:])
 
