@@ -235,7 +235,7 @@ int forward_device_impl(kprn_ctx* ctx, const int32_t* d_ids, const int32_t* d_se
     ctx->N = N; ctx->S = S; ctx->d_ids = d_ids; ctx->d_seg = d_seg;
     ctx->have_loss_grad = false;
     // scores-only fast path: nothing downstream of nn.Select(2,classId) needs the other L-1 columns
-    ctx->cls_only = !train && !want_logits && c.head_layers == 1;
+    ctx->cls_only = (!train || ctx->in_train_step) && !want_logits && c.head_layers == 1;
     ctx->head_part4 = nullptr;      // set by the fused tensor-core forward when it leaves the head to the pool kernel
     bool use_tc = c.precision != KPRN_PREC_FP32 && tc_supported(ctx);
     // shapes the fused kernels do not cover (H or d_e > 256, Elman cell, large type x relation product): the generic
@@ -243,6 +243,7 @@ int forward_device_impl(kprn_ctx* ctx, const int32_t* d_ids, const int32_t* d_se
     ctx->gemm_on_tc = c.precision != KPRN_PREC_FP32 && !use_tc && !train;
     cudaEvent_t e0;
     KPRN_TRY(prof_begin(ctx, &e0));
+    ctx->tc_train_fwd = false;
     if (use_tc) KPRN_TRY(tc_forward(ctx, d_ids, d_seg, N, S, train));
     else KPRN_TRY(simple_forward(ctx, d_ids, d_seg, N, S, train));
     KPRN_TRY(prof_end(ctx, e0, 0));
@@ -618,7 +619,7 @@ int loss_bpr_device(kprn_ctx* ctx, const int32_t* d_pos, const int32_t* d_neg, i
 int backward_device(kprn_ctx* ctx, float scale) {
     if (!ctx->have_fwd || !ctx->have_train_cache) { set_error("backward: needs a forward with train=1 first"); return KPRN_ESTATE; }
     if (!ctx->have_loss_grad) { set_error("backward: no loss gradient (call kprn_loss_* first or pass grad_scores)"); return KPRN_ESTATE; }
-    return simple_backward(ctx, scale);
+    return ctx->tc_train_fwd ? tc_backward(ctx, scale) : simple_backward(ctx, scale);
 }
 }  // namespace kprn
 extern "C" {

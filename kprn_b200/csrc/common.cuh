@@ -54,6 +54,7 @@ struct kprn_ctx {
     bool cls_only = false;          // last forward materialised only the class column (scores-only fast path)
     const float* head_part4 = nullptr;   // scores-only tensor-core forward: [4][head_npad] partial head dot products (else null)
     int64_t head_npad = 0;
+    bool tc_train_fwd = false;      // the last training forward ran on the fused tensor-core kernels (backward: tc_backward)
     bool gemm_on_tc = false;        // scoring forward of a shape the fused tensor-core kernels do not cover: products via tc_gemm
     const int32_t* d_ids = nullptr;      // ids of the last forward (ctx-owned copy or caller's device ptr)
     const int32_t* d_seg = nullptr;
@@ -141,6 +142,10 @@ bool tc_supported(const kprn_ctx* ctx);
 bool tc_validates_ids(const kprn_ctx* ctx, int64_t N);   // true when tc_forward(train = false) will flag out-of-range ids itself
 int tc_forward(kprn_ctx* ctx, const int32_t* d_ids, const int32_t* d_seg, int64_t N, int64_t S, bool train);
 void tc_destroy(kprn_ctx* ctx);
+bool tc_train_supported(const kprn_ctx* ctx);             // training forward + backward on the fused tensor-core kernels (tc_train.cu)
+int tc_backward(kprn_ctx* ctx, float scale);
+// pool + head backward for the live class column on the fp32 kernels: leaves ds_c[N] in ctx->ws_ds, adds gbo[c] and gWo[c,:]
+int head_backward_cls(kprn_ctx* ctx, float scale, const float* hT, int64_t ldh);
 int dedup_build(kprn_ctx* ctx, DedupBufs& b, int mode, const int32_t* ids, int64_t N, int T, int64_t n_keys);
 void dedup_free(DedupBufs& b);
 

@@ -539,6 +539,28 @@ __global__ void scatter_embed_kernel(const float* __restrict__ dX, const int32_t
     }
 }
 
+// pool backward + the head's gradients for the one live output column (head_layers == 1): ds_c[p] into ctx->ws_ds,
+// gbo[c] += sum ds_c, gWo[c,:] += sum_p ds_c[p] h_T[p,:].  Shared by the fused tensor-core backward (tc_train.cu).
+int head_backward_cls(kprn_ctx* ctx, float scale, const float* hT, int64_t ldh) {
+    const kprn_config& c = ctx->cfg;
+    const Layout& l = ctx->lay;
+    const int cls = c.class_id - 1;
+    const int64_t N = ctx->N, S = ctx->S;
+    float* gr = ctx->d_grads;
+    KPRN_TRY(ensure(ctx->ws_ds, sizeof(float) * N));
+    float ig = c.inv_gamma == 0.f ? 1.f : c.inv_gamma;
+    float* ds_c = ctx->ws_ds.as<float>();
+    KPRN_CUDA(cudaMemsetAsync(ds_c, 0, sizeof(float) * N, ctx->stream));
+    pool_bwd_kernel<<<(unsigned)cdiv(S, 128), 128, 0, ctx->stream>>>(
+        ctx->path_logits.as<float>(), ctx->seg_logits.as<float>(), ctx->d_seg, S, c.L, c.pool, c.topk, ig, cls,
+        ctx->dscores.as<float>(), scale, ds_c);
+    KPRN_LAUNCH_CHECK(ctx);
+    sum_kernel<<<296, 256, 0, ctx->stream>>>(ds_c, N, gr + l.bo + cls);
+    KPRN_LAUNCH_CHECK(ctx);
+    KPRN_TRY(wcolsum(ctx, hT, ldh, ds_c, N, c.H, gr + l.Wo + (int64_t)cls * c.H));
+    return KPRN_OK;
+}
+
 int simple_backward(kprn_ctx* ctx, float scale) {
     const kprn_config& c = ctx->cfg;
     const Layout& l = ctx->lay;

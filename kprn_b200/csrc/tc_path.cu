@@ -423,6 +423,11 @@ struct RecurArgs {
     // XW row of (path tile, t, r) = slot_of[pos[(tile*T + t)*128 + r]] (a row of the projection of the DISTINCT step inputs,
     // see the dedup kernels); null = its own row (tile tile*T + t, row r)
     const uint32_t* pos; const uint32_t* slot_of;
+    // training forward (TRAIN = true): the activations the backward needs, written by the epilogue as it computes them
+    //   cache  [tile][t][chunk j][sub-block sb][i,g,f,o,c][pair p 4][row 128][2] fp32: each st.global.v2 of a warp is 256 contiguous bytes
+    //   hcache [tile][t][hi|lo][kc Hp/8][row 128][8] bf16: h_t in the UMMA operand layout (what the next step's MMAs read, and the
+    //          B operand of the weight-gradient product dG^T h_{t-1}); replaces the per-CTA scratch
+    float* cache; bf16* hcache;
 };
 
 __device__ __forceinline__ float ex2f(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -446,14 +451,14 @@ __device__ __forceinline__ void pack_split8(const float* v, uint4& hi, uint4& lo
     lo = make_uint4(wl[0], wl[1], wl[2], wl[3]);
 }
 
-// recur_kernel<HP, PAIR>.  PAIR = true: launched as clusters of two CTAs (cta_group::2).  Each CTA still owns one 128-path
+// recur_kernel<HP, PAIR, TRAIN>.  PAIR = true: launched as clusters of two CTAs (cta_group::2).  Each CTA still owns one 128-path
 // tile (its own h in shared memory, c and accumulators in its own TMEM, its own epilogue), but one MMA multiplies both
 // tiles (M = 256) by the same 128 gate columns, and each CTA stages only ITS 64-column half of every weight slab: the
 // L2 -> SM weight stream -- more than half of this kernel's L2 traffic, which runs at ~85 % of the chip's measured L2
 // throughput in the 1-CTA form -- is halved.  The leader CTA's warp 1 issues the MMAs; the peer's warp 1 forwards
 // "my half-slab landed" / "my h slice landed" to the leader; both epilogues hand accumulators back to the leader;
 // MMA completion is multicast to both CTAs (tcgen05.commit ... multicast::cluster).
-template <int HP, bool PAIR>
+template <int HP, bool PAIR, bool TRAIN>
 __global__ void __launch_bounds__(RECUR_THREADS, 1) recur_kernel(RecurArgs a) {
     constexpr int NCH = HP / 32;        // 128-column chunks per step
     constexpr int KS = HP / 64;         // 64-wide k slices of h
@@ -516,7 +521,11 @@ __global__ void __launch_bounds__(RECUR_THREADS, 1) recur_kernel(RecurArgs a) {
     const int T = a.T;
     const uint32_t idesc = ptx::make_idesc_f16(1, PAIR ? 2 * TILE_M : TILE_M, 128);
     const int slabs_per_k = a.passes == 3 ? 2 : 1;
-    uint8_t* scratch = reinterpret_cast<uint8_t*>(a.hscratch) + (size_t)blockIdx.x * 2 * H_BYTES;   // [hi | lo] image of sH
+    uint8_t* const scratch0 = reinterpret_cast<uint8_t*>(a.hscratch) + (size_t)blockIdx.x * 2 * H_BYTES;   // [hi | lo] image of sH
+    // where h_t of (tile, t) lives in global memory: the per-CTA L2-resident scratch, or (training) its slot of the h cache
+    auto h_image = [&](int64_t tile, int t) -> uint8_t* {
+        return TRAIN ? reinterpret_cast<uint8_t*>(a.hcache) + (size_t)(tile * T + t) * 2 * H_BYTES : scratch0;
+    };
 
     if (warp == 0) {
         // ===== TMA producer: Wh slabs (this CTA's columns); the sequence is identical for every MMA step (t >= 1) =====
@@ -633,6 +642,7 @@ __global__ void __launch_bounds__(RECUR_THREADS, 1) recur_kernel(RecurArgs a) {
             for (int64_t it = 0; it < my_tiles; ++it) {
                 for (int t = 0; t < T - 1; ++t) {
                     ++idx;
+                    const uint8_t* scratch = h_image(tile_of(it), t);
                     // all MMAs that read the previous contents of sH must have retired: that is MMA step idx-1
                     if (idx >= 2) TWAIT(12, BAR(B_STEP), (idx - 2) & 1);
                     for (int s = 0; s < KS; ++s) {
@@ -684,6 +694,8 @@ __global__ void __launch_bounds__(RECUR_THREADS, 1) recur_kernel(RecurArgs a) {
                 const float* xw_t = a.pos ? a.XW + (int64_t)(slot >> 7) * tile_xw + (slot & 127) * 8
                                            : a.XW + (pt * T + t) * tile_xw + r * 8;
                 const bool last = (t == T - 1);
+                uint8_t* const scratch = h_image(pt, t);
+                float* const cache_t = TRAIN ? a.cache + (size_t)(pt * T + t) * NCH * 20480 + r * 2 : nullptr;
                 float xa[32], xb[32];                 // XW of the current / next chunk, ping-pong (no register copies)
                 float dot = 0.f;                      // last step, scores-only: this thread's share of h_T . wo
                 KPRN_LOAD_XW(xa, xw_t, 0)
@@ -754,6 +766,14 @@ __global__ void __launch_bounds__(RECUR_THREADS, 1) recur_kernel(RecurArgs a) {
                             const uint64_t h2 = ptx::mul2(o_, th);
                             cn[e] = ptx::lo2(c2); cn[e + 1] = ptx::hi2(c2);
                             hv[e] = ptx::lo2(h2); hv[e + 1] = ptx::hi2(h2);
+                            if (TRAIN) {
+                                float* cc = cache_t + (size_t)(j * 4 + sb) * 5120 + p * 256;
+                                asm volatile("st.global.v2.f32 [%0], {%1, %2};" ::"l"(cc), "f"(ptx::lo2(i_)), "f"(ptx::hi2(i_)) : "memory");
+                                asm volatile("st.global.v2.f32 [%0], {%1, %2};" ::"l"(cc + 1024), "f"(ptx::lo2(g_)), "f"(ptx::hi2(g_)) : "memory");
+                                asm volatile("st.global.v2.f32 [%0], {%1, %2};" ::"l"(cc + 2048), "f"(ptx::lo2(f_)), "f"(ptx::hi2(f_)) : "memory");
+                                asm volatile("st.global.v2.f32 [%0], {%1, %2};" ::"l"(cc + 3072), "f"(ptx::lo2(o_)), "f"(ptx::hi2(o_)) : "memory");
+                                asm volatile("st.global.v2.f32 [%0], {%1, %2};" ::"l"(cc + 4096), "f"(ptx::lo2(c2)), "f"(ptx::hi2(c2)) : "memory");
+                            }
                         }
                     }
                     ptx::tmem_st8(cst + sb * 8, cn);
@@ -765,7 +785,8 @@ __global__ void __launch_bounds__(RECUR_THREADS, 1) recur_kernel(RecurArgs a) {
                         *reinterpret_cast<uint4*>(scratch + H_BYTES + kc * 2048 + r * 16) = lo;
                         // publication of these writes (proxy fence + arrive) is deferred by one chunk: by then the
                         // stores have drained and the fence costs nothing (see the top of the lambda / after the loop)
-                    } else if (a.part4) {
+                    } else {
+                      if (a.part4) {
                         // A5 fused (nn.Linear row classId on SelectTable(-1)): partial dot product over this thread's 8 units;
                         // padded units (>= H) hold h = 0 exactly, their weights are not read
                         const int u0 = j * 32 + sb * 8;
@@ -778,7 +799,8 @@ __global__ void __launch_bounds__(RECUR_THREADS, 1) recur_kernel(RecurArgs a) {
                             for (int e = 0; e < 8; ++e)
                                 if (u0 + e < a.H) dot = fmaf(hv[e], a.wo[u0 + e], dot);
                         }
-                    } else if (n < a.N) {
+                      }
+                      if ((TRAIN || !a.part4) && n < a.N) {
                         // SelectTable(-1): last hidden state, standard [N,H] layout for the head
                         float* dst = a.hT + n * a.H + j * 32 + sb * 8;
                         if (h_vec4 && j * 32 + sb * 8 + 8 <= a.H) {      // full-sector stores (scalar stores cost 8 partial sectors)
@@ -789,6 +811,7 @@ __global__ void __launch_bounds__(RECUR_THREADS, 1) recur_kernel(RecurArgs a) {
                             for (int e = 0; e < 8; ++e)
                                 if (j * 32 + sb * 8 + e < a.H) dst[e] = hv[e];
                         }
+                      }
                     }
                 };
 #pragma unroll 1
@@ -1055,10 +1078,10 @@ static size_t proj_smem(int KE, int NOH) { return (size_t)(KE / 8 + 8 * NOH) * 2
 static size_t recur_smem(int Hp, bool pair) {
     return (size_t)2 * TILE_M * Hp * 2 + (pair ? (size_t)RECUR_RING_PAIR * B_SLAB_ELEMS : (size_t)RECUR_RING * B_SLAB_ELEMS * 2) + RECUR_BAR_BYTES;
 }
-template <int HP, bool PAIR>
+template <int HP, bool PAIR, bool TRAIN>
 static cudaError_t launch_recur(const RecurArgs& a, int64_t grid, cudaStream_t stream) {
     {   // the opt-in is per device (a process may hold ctxs on several): set it on every launch, it costs nothing
-        cudaError_t e = cudaFuncSetAttribute(recur_kernel<HP, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)recur_smem(HP, PAIR));
+        cudaError_t e = cudaFuncSetAttribute(recur_kernel<HP, PAIR, TRAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)recur_smem(HP, PAIR));
         if (e != cudaSuccess) return e;
     }
     cudaLaunchConfig_t cfg = {};
@@ -1066,12 +1089,15 @@ static cudaError_t launch_recur(const RecurArgs& a, int64_t grid, cudaStream_t s
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = PAIR ? 2 : 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, recur_kernel<HP, PAIR>, a);
+    return cudaLaunchKernelEx(&cfg, recur_kernel<HP, PAIR, TRAIN>, a);
 }
 
 int tc_forward(kprn_ctx* ctx, const int32_t* d_ids, const int32_t* d_seg, int64_t N, int64_t S, bool train) {
     const kprn_config& c = ctx->cfg;
-    if (train) return simple_forward(ctx, d_ids, d_seg, N, S, true);   // training caches come from the fp32 kernels
+    // training: the fused kernels with activation caches (KPRN_PREC_TC_ALL, shapes of tc_train_supported), else the generic engine
+    const bool tc_train = train && tc_train_supported(ctx);
+    ctx->tc_train_fwd = false;
+    if (train && !tc_train) return simple_forward(ctx, d_ids, d_seg, N, S, true);
     if (!ctx->tc) {
         ctx->tc = new TcState();
         TcState* s = ctx->tc;
@@ -1144,6 +1170,8 @@ int tc_forward(kprn_ctx* ctx, const int32_t* d_ids, const int32_t* d_seg, int64_
         const bool dd = s->dedup && ptiles * c.T * TILE_M < (1ll << 30);
         a.pos = dd ? s->dd.pos.as<uint32_t>() : nullptr; a.slot_of = dd ? s->dd.slot_of.as<uint32_t>() : nullptr;
         ctx->head_part4 = nullptr;
+        a.cache = nullptr; a.hcache = nullptr;
+        if (tc_train) KPRN_TRY(tc_train_buffers(ctx, N, &a.cache, &a.hcache));
         if (ctx->cls_only && c.pool == KPRN_POOL_LSE) {      // the pool kernel finishes the head: sum of 4 partials + bias
             KPRN_TRY(ensure(s->part4, sizeof(float) * 4 * (size_t)a.npad));
             a.part4 = s->part4.as<float>();
@@ -1153,14 +1181,19 @@ int tc_forward(kprn_ctx* ctx, const int32_t* d_ids, const int32_t* d_seg, int64_
 
         cudaEvent_t e0;
         KPRN_TRY(prof_begin(ctx, &e0));
-        if (s->recur_pairs) {     // a single tile is computed by both CTAs of the one pair
-            if (s->Hp == 64) KPRN_CUDA((launch_recur<64, true>(a, grid_r, ctx->stream)));
-            else if (s->Hp == 128) KPRN_CUDA((launch_recur<128, true>(a, grid_r, ctx->stream)));
-            else KPRN_CUDA((launch_recur<256, true>(a, grid_r, ctx->stream)));
+        if (tc_train) {           // CTA pairs, epilogue also writes the activation caches of the backward
+            grid_r = 2 * ((ptiles + 1) / 2 < s->num_sms / 2 ? (ptiles + 1) / 2 : s->num_sms / 2);
+            if (s->Hp == 64) KPRN_CUDA((launch_recur<64, true, true>(a, grid_r, ctx->stream)));
+            else if (s->Hp == 128) KPRN_CUDA((launch_recur<128, true, true>(a, grid_r, ctx->stream)));
+            else KPRN_CUDA((launch_recur<256, true, true>(a, grid_r, ctx->stream)));
+        } else if (s->recur_pairs) {     // a single tile is computed by both CTAs of the one pair
+            if (s->Hp == 64) KPRN_CUDA((launch_recur<64, true, false>(a, grid_r, ctx->stream)));
+            else if (s->Hp == 128) KPRN_CUDA((launch_recur<128, true, false>(a, grid_r, ctx->stream)));
+            else KPRN_CUDA((launch_recur<256, true, false>(a, grid_r, ctx->stream)));
         } else {
-            if (s->Hp == 64) KPRN_CUDA((launch_recur<64, false>(a, grid_r, ctx->stream)));
-            else if (s->Hp == 128) KPRN_CUDA((launch_recur<128, false>(a, grid_r, ctx->stream)));
-            else KPRN_CUDA((launch_recur<256, false>(a, grid_r, ctx->stream)));
+            if (s->Hp == 64) KPRN_CUDA((launch_recur<64, false, false>(a, grid_r, ctx->stream)));
+            else if (s->Hp == 128) KPRN_CUDA((launch_recur<128, false, false>(a, grid_r, ctx->stream)));
+            else KPRN_CUDA((launch_recur<256, false, false>(a, grid_r, ctx->stream)));
         }
         KPRN_LAUNCH_CHECK(ctx);
         KPRN_TRY(prof_end(ctx, e0, 2));
@@ -1188,12 +1221,14 @@ int tc_forward(kprn_ctx* ctx, const int32_t* d_ids, const int32_t* d_seg, int64_
         KPRN_TRY(head_forward(ctx, s->hT.as<float>(), c.H, 0, N, z1));
     }
     (void)S; (void)d_seg;
+    ctx->tc_train_fwd = tc_train;
     return KPRN_OK;
 }
 
 void tc_destroy(kprn_ctx* ctx) {
     TcState* s = ctx->tc;
     if (!s) return;
+    tc_train_destroy(ctx);
     if (s->E_hi) cudaFree(s->E_hi);
     if (s->E_lo) cudaFree(s->E_lo);
     if (s->WxE) cudaFree(s->WxE);

@@ -28,7 +28,10 @@ constexpr int MAX_NS = 6;             // k-slices of the proj A tile: KE/64 enti
 constexpr int NUM_THREADS = 384;      // proj: warps 0 TMA producer, 1 MMA issuer, 2-3 gather/alloc, 4-11 epilogue
 constexpr int RECUR_THREADS = 608;    // recur: warps 0 TMA producer, 1 MMA issuer, 2 TMEM alloc + h loader, 3-18 epilogue (4 groups); 19 warps -> 104 registers per thread
 
+struct TcTrain;   // tc_train.cu
+
 struct TcState {
+    TcTrain* tt = nullptr;             // training-side buffers and packed operands
     uint64_t packed_version = 0;       // ctx->params_version the packed operands (entity tables included) were built from
     uint64_t packed_small = 0;         // ctx->small_version the packed WEIGHTS were built from (a sparse training step leaves the
                                        // entity tables current row by row and only bumps small_version)
@@ -65,6 +68,7 @@ __device__ __forceinline__ void split_bf16(float v, bf16& hi, bf16& lo) {
 
 // training side (tc_train.cu)
 int tc_train_pack(kprn_ctx* ctx);
+int tc_train_buffers(kprn_ctx* ctx, int64_t N, float** cache, bf16** hcache);
 void tc_train_destroy(kprn_ctx* ctx);
 
 }  // namespace kprn

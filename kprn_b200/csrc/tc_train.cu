@@ -1,0 +1,838 @@
+// tc_train.cu -- the training products of the FastLSTM path on tcgen05 (A10 of SURVEY.md 8a; math: SURVEY App. A.7;
+// reference call site SP/model/optimizer/MyOptimizer.lua:184-217, modules SP/model/module/MapReduce.lua:74-85 + FastLSTM BPTT).
+//
+//   forward (tc_path.cu, recur_kernel<.., TRAIN>) leaves   cache  = i, g, f, o, c of every (path, step, unit)   (fp32)
+//                                                          hcache = h_t as bf16 hi/lo in the UMMA operand layout
+//   for t = T-1 .. 0:
+//     cell_bwd_kernel   dG_t from (cache_t, c_{t-1}, dh_t, dc)           -> dgop[tile][t] = dG_t as bf16 hi/lo, operand layout
+//     bgemm_kernel      [dh_{t-1} | dX_t] = dG_t [Wh | Wx_e]             (M = paths, N = Hp + KE, K = 4Hp; cta_group::2, bf16x3)
+//                       dh -> fp32 buffer for the next cell_bwd;  dX rows are added (red.global.add.v4.f32) to the entity
+//                       gradient: the compact per-slot buffer of a sparse training step or the dense table
+//   wgrad_kernel        gWh += dG^T h_{t-1}, gWx_e += dG^T x_e, gP += dG^T onehot(type,relation)   (M = 4Hp gate columns,
+//                       K = all path-steps: the SAME bytes of dgop read as an MN-major operand; split-K over CTA pairs)
+//   wgrad_reduce_kernel fixed-order sum of the K-split partials into the flat gradient; ptr_grad_kernel turns gP (the
+//                       gradient of the hoisted (type,relation) table) into gE_type, gE_relation, gWx[:, type|relation], gbx.
+// The head / pool / loss gradients stay on the fp32 kernels of kernels_simple.cu (0.2 % of the flops).
+#include "tc_state.cuh"
+
+namespace kprn {
+
+constexpr int BG_THREADS = 384;       // bgemm: warp 0 TMA producer, 1 MMA issuer / peer forwarder, 2 TMEM alloc, 3 idle, 4-11 epilogue
+constexpr int BG_STAGES = 2;
+constexpr int WG_THREADS = 256;       // wgrad: warp 0 TMA producer, 1 issuer / forwarder, 2 gather + one-hot writer, 3 forwarder, 4-7 epilogue
+constexpr int WG_STAGES = 3;
+constexpr int WG_ROWS = 64;           // path-step rows (K) per pipeline stage
+
+struct TcTrain {
+    uint64_t packed_small = 0;
+    bf16* WT = nullptr;               // bgemm B operand: [part 2][ks G4/64][hi|lo][half 2][kc 8][n Nh][8]
+    DBuf cache, hcache, dgop, dh, dc, wpart, gP, cls;
+    CUtensorMap tm_dg, tm_hc;         // 2-D maps over dgop / hcache (uint32 view): box = 64 rows x 16 k-chunks
+    void* tm_dg_base = nullptr; void* tm_hc_base = nullptr; int64_t tm_dg_rows = 0, tm_hc_rows = 0;
+};
+
+// ---------------------------------------------------------------------------------------------
+// packing of the backward's weight operands (unscaled: the gradients are w.r.t. the true pre-activations)
+
+// part 0: Wh^T as B of dh = dG Wh     -> element (n = hidden unit k, K index gp) = Wh[row(gp)][n]
+// part 1: Wx_e^T as B of dX = dG Wx_e -> element (n = entity column,  K index gp) = Wx[row(gp)][d_t + n]
+__global__ void pack_wt_kernel(const float* __restrict__ Wh, const float* __restrict__ Wx, int H, int D, int d_t, int d_e, int G4,
+                               int N0, int N1, bf16* __restrict__ out) {
+    const int KSg = G4 / 64;
+    const int64_t per0 = (int64_t)KSg * 2 * 8 * N0 * 8, per1 = (int64_t)KSg * 2 * 8 * N1 * 8;     // elements of a part (hi + lo)
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (per0 + per1) / 2) return;                                                          // one thread per (hi, lo) pair
+    const int part = idx < per0 / 2 ? 0 : 1;
+    const int64_t li = part ? idx - per0 / 2 : idx;
+    const int N = part ? N1 : N0, Nh = N / 2;
+    // li indexes [ks][half][kc 8][n Nh][8]
+    const int e = (int)(li & 7);
+    int64_t r = li >> 3;
+    const int n = (int)(r % Nh); r /= Nh;
+    const int kc = (int)(r & 7); r >>= 3;
+    const int half = (int)(r & 1); r >>= 1;
+    const int ks = (int)r;
+    const int gp = ks * 64 + kc * 8 + e, nn = half * Nh + n;
+    int u;
+    const int row = perm_to_row(gp, H, u);
+    float v = 0.f;
+    if (u < H) {
+        if (part == 0) { if (nn < H) v = Wh[(int64_t)row * H + nn]; }
+        else if (nn < d_e) v = Wx[(int64_t)row * D + d_t + nn];
+    }
+    bf16 h, l;
+    split_bf16(v, h, l);
+    bf16* base = out + (part ? per0 : 0) + (((int64_t)ks * 2 + 0) * 2 + half) * (8 * Nh * 8) + ((int64_t)kc * Nh + n) * 8 + e;
+    base[0] = h;
+    base[(int64_t)2 * 8 * Nh * 8] = l;          // the lo block follows the two halves of hi
+}
+
+// ---------------------------------------------------------------------------------------------
+// cell backward: one thread = one path row x 8 hidden units (the recurrence epilogue's mapping).
+// grid (tiles, NCH), block (128 rows, 4 sub-blocks)
+
+struct CellBwdArgs {
+    const float* cache; int T; int t; int NCH; int H; int64_t N;
+    const float* dh;          // [tile][Hp/8][row 128][8] from bgemm (t < T-1) or null (t = T-1: dh = ds_c[n] * wo[u])
+    const float* ds_c; const float* wo;
+    float* dc;                // [tile][Hp/8][row 128][8] in/out (first step: treated as 0)
+    bf16* dgop;               // [tile][t][hi|lo][kc G4/8][row 128][8]
+    int G4;
+};
+
+__device__ __forceinline__ void split8_store(const float* v, bf16* hi, bf16* lo) {
+    uint32_t wh[4], wl[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h2);
+        const float r0 = v[2 * i] - __uint_as_float(hb << 16), r1 = v[2 * i + 1] - __uint_as_float(hb & 0xFFFF0000u);
+        const __nv_bfloat162 l2 = __floats2bfloat162_rn(r0, r1);
+        wh[i] = hb; wl[i] = *reinterpret_cast<const uint32_t*>(&l2);
+    }
+    *reinterpret_cast<uint4*>(hi) = make_uint4(wh[0], wh[1], wh[2], wh[3]);
+    *reinterpret_cast<uint4*>(lo) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+}
+
+__global__ void __launch_bounds__(512) cell_bwd_kernel(CellBwdArgs a) {
+    const int64_t m = blockIdx.x;
+    const int j = blockIdx.y, r = threadIdx.x, sb = threadIdx.y;
+    const int64_t n = m * TILE_M + r;
+    const bool live = n < a.N;
+    const size_t step_floats = (size_t)a.NCH * 20480;
+    const float* ct = a.cache + (size_t)(m * a.T + a.t) * step_floats + (size_t)(j * 4 + sb) * 5120 + r * 2;
+    const float* cprev = a.t > 0 ? ct - step_floats + 4096 : nullptr;
+    float gi[8], gg[8], gf[8], go[8], cc[8], cp[8];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const float2 vi = *reinterpret_cast<const float2*>(ct + p * 256), vg = *reinterpret_cast<const float2*>(ct + 1024 + p * 256);
+        const float2 vf = *reinterpret_cast<const float2*>(ct + 2048 + p * 256), vo = *reinterpret_cast<const float2*>(ct + 3072 + p * 256);
+        const float2 vc = *reinterpret_cast<const float2*>(ct + 4096 + p * 256);
+        gi[2 * p] = vi.x; gi[2 * p + 1] = vi.y; gg[2 * p] = vg.x; gg[2 * p + 1] = vg.y; gf[2 * p] = vf.x; gf[2 * p + 1] = vf.y;
+        go[2 * p] = vo.x; go[2 * p + 1] = vo.y; cc[2 * p] = vc.x; cc[2 * p + 1] = vc.y;
+        float2 vp = make_float2(0.f, 0.f);
+        if (cprev) vp = *reinterpret_cast<const float2*>(cprev + p * 256);
+        cp[2 * p] = vp.x; cp[2 * p + 1] = vp.y;
+    }
+    const int grp = j * 4 + sb;                                 // 8-unit group of this thread
+    const size_t gi8 = ((size_t)(m * (a.G4 / 32) + grp) * TILE_M + r) * 8;      // G4/32 = Hp/8 groups per tile
+    float dh[8], dc[8];
+    if (a.dh) {
+        const float4 x0 = *reinterpret_cast<const float4*>(a.dh + gi8), x1 = *reinterpret_cast<const float4*>(a.dh + gi8 + 4);
+        dh[0] = x0.x; dh[1] = x0.y; dh[2] = x0.z; dh[3] = x0.w; dh[4] = x1.x; dh[5] = x1.y; dh[6] = x1.z; dh[7] = x1.w;
+        const float4 y0 = *reinterpret_cast<const float4*>(a.dc + gi8), y1 = *reinterpret_cast<const float4*>(a.dc + gi8 + 4);
+        dc[0] = y0.x; dc[1] = y0.y; dc[2] = y0.z; dc[3] = y0.w; dc[4] = y1.x; dc[5] = y1.y; dc[6] = y1.z; dc[7] = y1.w;
+    } else {
+        // t = T-1: dh = ds_c * Wo[classId, :]   (nn.Linear backward for the one live output column), dc = 0
+        const float s = live ? a.ds_c[n] : 0.f;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { const int u = grp * 8 + e; dh[e] = u < a.H ? s * a.wo[u] : 0.f; dc[e] = 0.f; }
+    }
+    float di[8], dg[8], df[8], dO[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const float tc = tanhf(cc[e]);
+        const float d_o = dh[e] * tc;
+        const float dcu = dc[e] + dh[e] * go[e] * (1.f - tc * tc);
+        dc[e] = dcu * gf[e];
+        di[e] = live ? dcu * gg[e] * gi[e] * (1.f - gi[e]) : 0.f;
+        dg[e] = live ? dcu * gi[e] * (1.f - gg[e] * gg[e]) : 0.f;
+        df[e] = live ? dcu * cp[e] * gf[e] * (1.f - gf[e]) : 0.f;
+        dO[e] = live ? d_o * go[e] * (1.f - go[e]) : 0.f;
+    }
+    *reinterpret_cast<float4*>(a.dc + gi8) = make_float4(dc[0], dc[1], dc[2], dc[3]);
+    *reinterpret_cast<float4*>(a.dc + gi8 + 4) = make_float4(dc[4], dc[5], dc[6], dc[7]);
+    // operand layout: k-chunk kc = j*16 + gate*4 + sb (8 permuted gate columns), row r
+    const size_t hl = (size_t)(a.G4 / 8) * TILE_M * 8;                       // elements of one of hi / lo
+    bf16* base = a.dgop + (size_t)(m * a.T + a.t) * 2 * hl + ((size_t)(j * 16 + sb) * TILE_M + r) * 8;
+    const size_t gstep = (size_t)4 * TILE_M * 8;                              // next gate = 4 k-chunks further
+    split8_store(di, base, base + hl);
+    split8_store(dg, base + gstep, base + gstep + hl);
+    split8_store(df, base + 2 * gstep, base + 2 * gstep + hl);
+    split8_store(dO, base + 3 * gstep, base + 3 * gstep + hl);
+}
+
+// ---------------------------------------------------------------------------------------------
+// bgemm: [dh | dX] (128 paths per CTA, 256 per pair) = dG_t (K = G4) x [Wh^T | Wx_e^T], bf16x3, cta_group::2.
+
+struct BgArgs {
+    const bf16* dgop; const bf16* WT; int T; int t; int G4; int N0, N1; int64_t num_tiles; int64_t N;
+    int part_begin;           // 1 at t = 0 (no dh needed)
+    float* dh;                // [tile][N0/8][row 128][8]
+    // dX rows: += into gE (dense: row = entity id - 1; compact: slot_of[pos[o]])
+    float* gE; int d_e; const int32_t* ids; const uint32_t* pos; const uint32_t* slot_of; int64_t V_e;
+};
+
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BG_THREADS, 1) bgemm_kernel(BgArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = ptx::cluster_ctarank();
+    const bool leader = rank == 0;
+    constexpr int S = BG_STAGES;
+    const int Nh0 = a.N0 / 2, Nh1 = a.N1 / 2;
+    const uint32_t A_BYTES = 16384;                                   // one of hi / lo of a 64-wide k-slice: [kc 8][row 128][16 B]
+    const uint32_t B0_BYTES = 8u * Nh0 * 16, B1_BYTES = 8u * Nh1 * 16;
+    const uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B0_BYTES + 2 * B1_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * STAGE_BYTES);
+    const uint32_t bar0 = ptx::smem_u32(bars);
+    auto BAR = [&](int i) { return bar0 + 8u * i; };
+    // [0,S) full  [S,2S) empty  [2S,3S) peer_full (leader)  3S acc_full  3S+1 acc_empty (leader)
+    constexpr int B_PEER = 2 * S, B_ACCF = 3 * S, B_ACCE = 3 * S + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_ACCE + 1);
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < S; ++i) { ptx::mbar_init(BAR(i), 1); ptx::mbar_init(BAR(S + i), 1); ptx::mbar_init(BAR(B_PEER + i), 1); }
+        ptx::mbar_init(BAR(B_ACCF), 1); ptx::mbar_init(BAR(B_ACCE), 16);
+        ptx::fence_mbar_init();
+    }
+    if (warp == 2) { ptx::tmem_alloc2(ptx::smem_u32(tmem_slot), 512); ptx::tmem_relinquish2(); }
+    ptx::tc_fence_before();
+    ptx::cluster_sync();
+    ptx::tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    const int64_t npairs = gridDim.x / 2, pair = blockIdx.x / 2, n_tp = (a.num_tiles + 1) / 2;
+    const int64_t my_tiles = pair < n_tp ? (n_tp - pair + npairs - 1) / npairs : 0;
+    auto tile_of = [&](int64_t it) -> int64_t { const int64_t m = 2 * (pair + it * npairs) + rank; return m < a.num_tiles ? m : a.num_tiles - 1; };
+    const int KSg = a.G4 / 64;
+    const size_t hl = (size_t)(a.G4 / 8) * TILE_M * 8;               // elements of one of hi / lo of a dgop tile
+    const int64_t per0 = (int64_t)KSg * 2 * 8 * a.N0 * 8;            // elements of part 0 of WT
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int64_t it = 0; it < my_tiles; ++it) {
+                const bf16* A = a.dgop + (size_t)(tile_of(it) * a.T + a.t) * 2 * hl;
+                for (int ks = 0; ks < KSg; ++ks) {
+                    ptx::mbar_wait(BAR(S + stage), phase ^ 1);
+                    const uint32_t tx = 2 * A_BYTES + (a.part_begin == 0 ? 2 * B0_BYTES : 0) + 2 * B1_BYTES;
+                    ptx::mbar_arrive_expect_tx(BAR(stage), tx);
+                    const uint32_t sb0 = ptx::smem_u32(smem + stage * STAGE_BYTES);
+                    ptx::tma_bulk_g2s(sb0, A + (size_t)ks * 8 * TILE_M * 8, A_BYTES, BAR(stage));
+                    ptx::tma_bulk_g2s(sb0 + A_BYTES, A + hl + (size_t)ks * 8 * TILE_M * 8, A_BYTES, BAR(stage));
+                    if (a.part_begin == 0) {
+                        const bf16* W0 = a.WT + (((int64_t)ks * 2 + 0) * 2 + rank) * (8 * Nh0 * 8);
+                        ptx::tma_bulk_g2s(sb0 + 2 * A_BYTES, W0, B0_BYTES, BAR(stage));
+                        ptx::tma_bulk_g2s(sb0 + 2 * A_BYTES + B0_BYTES, W0 + (int64_t)2 * 8 * Nh0 * 8, B0_BYTES, BAR(stage));
+                    }
+                    const bf16* W1 = a.WT + per0 + (((int64_t)ks * 2 + 0) * 2 + rank) * (8 * Nh1 * 8);
+                    ptx::tma_bulk_g2s(sb0 + 2 * A_BYTES + 2 * B0_BYTES, W1, B1_BYTES, BAR(stage));
+                    ptx::tma_bulk_g2s(sb0 + 2 * A_BYTES + 2 * B0_BYTES + B1_BYTES, W1 + (int64_t)2 * 8 * Nh1 * 8, B1_BYTES, BAR(stage));
+                    if (++stage == S) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (leader) {
+            const bool issue = ptx::elect_one();
+            uint32_t stage = 0, phase = 0;
+            constexpr uint32_t DHI = ptx::desc_hi(128);
+            const uint32_t idesc0 = ptx::make_idesc_f16(1, 256, a.N0), idesc1 = ptx::make_idesc_f16(1, 256, a.N1);
+            for (int64_t it = 0; it < my_tiles; ++it) {
+                ptx::mbar_wait_cluster(BAR(B_ACCE), (it & 1) ^ 1);
+                ptx::tc_fence_after();
+                for (int ks = 0; ks < KSg; ++ks) {
+                    ptx::mbar_wait(BAR(stage), phase);
+                    ptx::mbar_wait_cluster(BAR(B_PEER + stage), phase);
+                    ptx::tc_fence_after();
+                    const uint32_t sb0 = ptx::smem_u32(smem + stage * STAGE_BYTES);
+                    const uint32_t ah = ptx::desc_lo(sb0, 2048), al = ptx::desc_lo(sb0 + A_BYTES, 2048);
+                    if (issue) {
+                        for (int part = a.part_begin; part < 2; ++part) {
+                            const uint32_t Nh = part ? Nh1 : Nh0;
+                            const uint32_t boff = 2 * A_BYTES + (part ? 2 * B0_BYTES : 0), bbytes = part ? B1_BYTES : B0_BYTES;
+                            const uint32_t bh = ptx::desc_lo(sb0 + boff, Nh * 16), bl = ptx::desc_lo(sb0 + boff + bbytes, Nh * 16);
+                            const uint32_t k16b = (2 * Nh * 16) >> 4;
+                            const uint32_t d = tmem + part * 256;
+                            const uint32_t idesc = part ? idesc1 : idesc0;
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                ptx::umma2_f16(d, ptx::desc_join(DHI, ah + k * 256u), ptx::desc_join(DHI, bh + k * k16b), idesc, (ks | k) != 0);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                ptx::umma2_f16(d, ptx::desc_join(DHI, al + k * 256u), ptx::desc_join(DHI, bh + k * k16b), idesc, 1);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                ptx::umma2_f16(d, ptx::desc_join(DHI, ah + k * 256u), ptx::desc_join(DHI, bl + k * k16b), idesc, 1);
+                        }
+                        ptx::umma2_commit(BAR(S + stage), 3);
+                    }
+                    if (++stage == S) { stage = 0; phase ^= 1; }
+                }
+                if (issue) ptx::umma2_commit(BAR(B_ACCF), 3);
+            }
+        } else if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            const uint32_t remote = ptx::mapa(BAR(B_PEER), 0);
+            for (int64_t it = 0; it < my_tiles; ++it)
+                for (int ks = 0; ks < KSg; ++ks) {
+                    ptx::mbar_wait(BAR(stage), phase);
+                    ptx::mbar_arrive_cluster(remote + 8u * stage);
+                    if (++stage == S) { stage = 0; phase ^= 1; }
+                }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue: warps 4-7 drain part 0 (dh), warps 8-11 part 1 (dX); a warp owns the 32 rows of its TMEM lane quarter =====
+        const int part = (warp - 4) >> 2, q4 = warp & 3, r = q4 * 32 + lane;
+        const uint32_t acce_leader = ptx::mapa(BAR(B_ACCE), 0);
+        for (int64_t it = 0; it < my_tiles; ++it) {
+            const int64_t m = tile_of(it);
+            ptx::mbar_wait(BAR(B_ACCF), it & 1);
+            ptx::tc_fence_after();
+            const uint32_t tb = tmem + ((uint32_t)(q4 * 32) << 16) + part * 256;
+            if (part == 0) {
+                if (a.part_begin == 0) {
+                    float* dst = a.dh + ((size_t)m * (a.N0 / 8) * TILE_M + r) * 8;
+                    for (int blk = 0; blk < a.N0 / 32; ++blk) {
+                        float v[32];
+                        ptx::tmem_ld32(tb + blk * 32, v);
+                        ptx::tc_wait_ld();
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) ptx::stg256(dst + (size_t)(blk * 4 + i) * TILE_M * 8, v + 8 * i);
+                    }
+                }
+            } else {
+                const int64_t n = m * TILE_M + r;
+                float* ge = nullptr;
+                // an odd tail tile is computed by both CTAs of the last pair: only rank 0 adds it
+                const bool dup = (2 * (pair + it * npairs) + rank) >= a.num_tiles;
+                if (n < a.N && !dup) {
+                    if (a.pos) {
+                        const uint32_t p = a.pos[(m * a.T + a.t) * TILE_M + r];
+                        if (p != 0xFFFFFFFFu) ge = a.gE + (size_t)a.slot_of[p] * a.d_e;
+                    } else {
+                        int64_t ie = (int64_t)a.ids[(n * a.T + a.t) * 3 + 1] - 1;
+                        if (ie >= 0 && ie < a.V_e) ge = a.gE + (size_t)ie * a.d_e;
+                    }
+                }
+                for (int blk = 0; blk < a.N1 / 32; ++blk) {
+                    float v[32];
+                    ptx::tmem_ld32(tb + blk * 32, v);
+                    ptx::tc_wait_ld();
+                    if (ge) {
+                        if ((a.d_e & 3) == 0 && blk * 32 + 32 <= a.d_e) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) red_add_v4(ge + blk * 32 + 4 * i, v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) if (blk * 32 + i < a.d_e) atomicAdd(ge + blk * 32 + i, v[i]);
+                        }
+                    }
+                }
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive_cluster(acce_leader);
+        }
+    }
+    ptx::tc_fence_before();
+    ptx::cluster_sync();
+    if (warp == 2) ptx::tmem_dealloc2(tmem, 512);
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// wgrad: G[gp, n] = sum over path-steps of dG[step, gp] * B[step, n]  for one 256-row block of gate columns (128 per CTA of a
+// pair) and one operand family:
+//   part 0: B = [h_{t-1} (Hp columns) | onehot(type,relation) (64 columns)]   -> gWh and gP (two accumulators)
+//   part 1: B = x_e (KE columns, gathered with TMA tile::gather4 from the pre-split entity table) -> gWx[:, entity columns]
+// A = dgop read as an MN-major operand (M = gate column, K = path row): the bytes [kc][row][8] that bgemm reads K-major.
+// K is split over gridDim.y CTA pairs; each writes its partial tile, wgrad_reduce_kernel sums them in a fixed order.
+
+struct WgArgs {
+    const int32_t* ids; int64_t N; int T; int64_t num_tiles; int V_r; int64_t V_e; int V_t;
+    int G4, N0, KE, NOH;
+    int64_t blocks_per_split;       // (tile, t) blocks per K-split
+    int hc_box;                     // k-chunk rows per TMA box of the h map: min(16, N0/16)
+    float* part;                    // [split][part 2][gp G4][n 320] fp32
+    int H_BYTES;                    // bytes of one of hi / lo of an hcache step
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WG_THREADS, 1)
+wgrad_kernel(const __grid_constant__ CUtensorMap tm_dg, const __grid_constant__ CUtensorMap tm_hc, const __grid_constant__ CUtensorMap tm_hi,
+             const __grid_constant__ CUtensorMap tm_lo, WgArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = ptx::cluster_ctarank();
+    const bool leader = rank == 0;
+    constexpr int S = WG_STAGES;
+    // work item: blockIdx.x / 2 = (mp, part) ; blockIdx.y = K split
+    const int item = blockIdx.x / 2, part = item & 1, mp = item >> 1;
+    const int split = blockIdx.y;
+    const int Nmain = part ? a.KE : a.N0, Nh = Nmain / 2;
+    constexpr uint32_t A_BYTES = 16 * WG_ROWS * 16;                  // [kc 16][row 64][16 B] = 16 KB per hi / lo
+    const uint32_t B_BYTES = (uint32_t)Nh * WG_ROWS * 2;             // per hi / lo: part 0 [kc Nh/8][row 64][16 B]; part 1 [panel Nh/64][row 64][128 B]
+    constexpr uint32_t OH_BYTES = 4 * WG_ROWS * 16;                  // one-hot: this CTA's 32 combos x 64 rows (hi only)
+    const uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * 8192 * (uint32_t)((Nh + 63) / 64) + OH_BYTES;   // B region rounded to 8 KB panels (1024-aligned)
+    const uint32_t B_OFF = 2 * A_BYTES, B_LO_OFF = B_OFF + 8192 * (uint32_t)((Nh + 63) / 64), OH_OFF = STAGE_BYTES - OH_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * STAGE_BYTES);
+    const uint32_t bar0 = ptx::smem_u32(bars);
+    auto BAR = [&](int i) { return bar0 + 8u * i; };
+    // [0,S) full (TMA tx + one-hot writer)  [S,2S) empty  [2S,3S) peer_full (leader)  3S acc_full
+    constexpr int B_PEER = 2 * S, B_ACCF = 3 * S;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_ACCF + 1);
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < S; ++i) { ptx::mbar_init(BAR(i), 2); ptx::mbar_init(BAR(S + i), 1); ptx::mbar_init(BAR(B_PEER + i), 1); }
+        ptx::mbar_init(BAR(B_ACCF), 1);
+        ptx::fence_mbar_init();
+        ptx::prefetch_tensormap(&tm_dg); ptx::prefetch_tensormap(&tm_hc); ptx::prefetch_tensormap(&tm_hi); ptx::prefetch_tensormap(&tm_lo);
+    }
+    if (warp == 2) { ptx::tmem_alloc2(ptx::smem_u32(tmem_slot), 512); ptx::tmem_relinquish2(); }
+    ptx::tc_fence_before();
+    ptx::cluster_sync();
+    ptx::tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    const int64_t nblocks = a.num_tiles * a.T;
+    const int64_t b0 = split * a.blocks_per_split, b1 = (b0 + a.blocks_per_split < nblocks) ? b0 + a.blocks_per_split : nblocks;
+    const int kc_rows = a.G4 / 8;                                    // k-chunk rows of one of hi / lo of a dgop step
+    const int hc_rows = a.N0 / 8;
+    const int kcA = (mp * 2 + (int)rank) * 16;                       // first k-chunk of this CTA's 128 gate columns
+    // stage sequence: for b in [b0, b1): for half in {0, 1} (64 rows each)
+
+    if (warp == 0) {
+        // ===== TMA producer: A (dG, hi + lo) and, part 0, this CTA's half of h_{t-1} (hi + lo); 2-D maps, one op each =====
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int64_t b = b0; b < b1; ++b) {
+                const int t = (int)(b % a.T);
+                const int64_t m = b / a.T;
+                const bool has_h = part == 0 && t > 0;
+                for (int half = 0; half < 2; ++half) {
+                    ptx::mbar_wait(BAR(S + stage), phase ^ 1);
+                    uint32_t tx = 2 * A_BYTES;
+                    if (has_h) tx += 2 * B_BYTES;
+                    if (part == 1) tx += 2 * B_BYTES;                // the gathers of warp 2 count on the same barrier
+                    ptx::mbar_arrive_expect_tx(BAR(stage), tx);
+                    const uint32_t sb0 = ptx::smem_u32(smem + stage * STAGE_BYTES);
+                    const int32_t col = half * (WG_ROWS * 4);        // uint32 column: 64 rows x 16 B
+                    const int32_t rowA = (int32_t)((b * 2) * kc_rows + kcA);
+                    asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                                 ::"r"(sb0), "l"(&tm_dg), "r"(col), "r"(rowA), "r"(BAR(stage)) : "memory");
+                    asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                                 ::"r"(sb0 + A_BYTES), "l"(&tm_dg), "r"(col), "r"(rowA + kc_rows), "r"(BAR(stage)) : "memory");
+                    if (has_h) {
+                        const int32_t rowH = (int32_t)(((m * a.T + (t - 1)) * 2) * hc_rows + (int)rank * (Nh / 8));
+                        for (int c = 0; c < Nh / 8; c += a.hc_box) {
+                            asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                                         ::"r"(sb0 + B_OFF + c * 1024), "l"(&tm_hc), "r"(col), "r"(rowH + c), "r"(BAR(stage)) : "memory");
+                            asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                                         ::"r"(sb0 + B_LO_OFF + c * 1024), "l"(&tm_hc), "r"(col), "r"(rowH + hc_rows + c), "r"(BAR(stage)) : "memory");
+                        }
+                    }
+                    if (++stage == S) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (leader) {
+            // ===== MMA issuer =====
+            const bool issue = ptx::elect_one();
+            uint32_t stage = 0, phase = 0;
+            // MN-major no-swizzle operand [k-chunk (8 mn)][row (k)][16 B]: LBO = 128 B between 8-row k groups, SBO = 1024 B
+            // between 8-element mn groups (tools/umma_probe.cu); a K=16 step = 16 rows = 256 B
+            constexpr uint32_t DHI_MN = ptx::desc_hi(1024);
+            // MN-major SWIZZLE_128B operand (TMA gather image): panels of 64 mn [row (k)][128 B]: LBO = 8192 B panel stride,
+            // SBO = 1024 B between 8-row k groups; a K=16 step = 16 rows = 2048 B
+            constexpr uint32_t DHI_SW = ((1024u >> 4) & 0x3FFF) | (1u << 14) | (2u << 29);
+            const uint32_t idesc_main = ptx::make_idesc_f16(1, 256, Nmain) | (1u << 15) | (1u << 16);
+            const uint32_t idesc_oh = ptx::make_idesc_f16(1, 256, 64) | (1u << 15) | (1u << 16);
+            bool first_main = true, first_oh = true;
+            for (int64_t b = b0; b < b1; ++b) {
+                const int t = (int)(b % a.T);
+                const bool has_main = part == 1 || t > 0;
+                for (int half = 0; half < 2; ++half) {
+                    ptx::mbar_wait(BAR(stage), phase);
+                    ptx::mbar_wait_cluster(BAR(B_PEER + stage), phase);
+                    ptx::tc_fence_after();
+                    const uint32_t sb0 = ptx::smem_u32(smem + stage * STAGE_BYTES);
+                    const uint32_t ah = ptx::desc_lo(sb0, 128), al = ptx::desc_lo(sb0 + A_BYTES, 128);
+                    if (issue) {
+                        if (has_main) {
+                            uint32_t bh, bl, bk16, bhi;
+                            if (part == 0) { bh = ptx::desc_lo(sb0 + B_OFF, 128); bl = ptx::desc_lo(sb0 + B_LO_OFF, 128); bk16 = 256u >> 4; bhi = DHI_MN; }
+                            else { bh = ptx::desc_lo(sb0 + B_OFF, 8192); bl = ptx::desc_lo(sb0 + B_LO_OFF, 8192); bk16 = 2048u >> 4; bhi = DHI_SW; }
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                ptx::umma2_f16(tmem, ptx::desc_join(DHI_MN, ah + k * 16u), ptx::desc_join(bhi, bh + k * bk16), idesc_main, !(first_main && k == 0));
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                ptx::umma2_f16(tmem, ptx::desc_join(DHI_MN, al + k * 16u), ptx::desc_join(bhi, bh + k * bk16), idesc_main, 1);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                ptx::umma2_f16(tmem, ptx::desc_join(DHI_MN, ah + k * 16u), ptx::desc_join(bhi, bl + k * bk16), idesc_main, 1);
+                            first_main = false;
+                        }
+                        if (part == 0) {
+                            const uint32_t oh = ptx::desc_lo(sb0 + OH_OFF, 128);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                ptx::umma2_f16(tmem + 256, ptx::desc_join(DHI_MN, ah + k * 16u), ptx::desc_join(DHI_MN, oh + k * 16u), idesc_oh, !(first_oh && k == 0));
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                ptx::umma2_f16(tmem + 256, ptx::desc_join(DHI_MN, al + k * 16u), ptx::desc_join(DHI_MN, oh + k * 16u), idesc_oh, 1);
+                            first_oh = false;
+                        }
+                        ptx::umma2_commit(BAR(S + stage), 3);
+                    }
+                    if (++stage == S) { stage = 0; phase ^= 1; }
+                }
+            }
+            if (issue) ptx::umma2_commit(BAR(B_ACCF), 3);
+        } else if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            const uint32_t remote = ptx::mapa(BAR(B_PEER), 0);
+            for (int64_t b = b0; b < b1; ++b)
+                for (int half = 0; half < 2; ++half) {
+                    ptx::mbar_wait(BAR(stage), phase);
+                    ptx::mbar_arrive_cluster(remote + 8u * stage);
+                    if (++stage == S) { stage = 0; phase ^= 1; }
+                }
+        }
+    } else if (warp == 2) {
+        // ===== part 1: TMA gather of the entity rows (lane l owns rows 2l, 2l+1 of the 64-row stage ... as 16 row quads: lanes 0-15)
+        //       part 0: writer of the one-hot (type,relation) slice (this CTA's 32 combos) =====
+        uint32_t stage = 0, phase = 0;
+        for (int64_t b = b0; b < b1; ++b) {
+            const int t = (int)(b % a.T);
+            const int64_t m = b / a.T;
+            for (int half = 0; half < 2; ++half) {
+                ptx::mbar_wait(BAR(S + stage), phase ^ 1);
+                const uint32_t sb0 = ptx::smem_u32(smem + stage * STAGE_BYTES);
+                if (part == 1) {
+                    if (lane < 16) {
+                        int32_t eid[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            int64_t n = m * TILE_M + half * WG_ROWS + lane * 4 + q;
+                            if (n >= a.N) n = a.N - 1;               // its dG row is zero
+                            int64_t id = (int64_t)a.ids[(n * a.T + t) * 3 + 1] - 1;
+                            eid[q] = (int32_t)(id < 0 ? 0 : (id >= a.V_e ? a.V_e - 1 : id));
+                        }
+                        for (int pnl = 0; pnl < Nh / 64; ++pnl) {
+                            const int32_t col = ((int)rank * (Nh / 64) + pnl) * 64;
+                            const uint32_t off = pnl * 8192 + lane * 512;      // 4 rows x 128 B
+                            ptx::tma_gather4(sb0 + B_OFF + off, &tm_hi, col, eid[0], eid[1], eid[2], eid[3], BAR(stage));
+                            ptx::tma_gather4(sb0 + B_LO_OFF + off, &tm_lo, col, eid[0], eid[1], eid[2], eid[3], BAR(stage));
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(BAR(stage));
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        const int rr = lane * 2 + q;
+                        int64_t n = m * TILE_M + half * WG_ROWS + rr;
+                        int combo = -1;
+                        if (n < a.N) {
+                            const int32_t* idp = a.ids + (n * a.T + t) * 3;
+                            int ta = idp[0] - 1, rb = idp[2] - 1;
+                            ta = ta < 0 ? 0 : (ta >= a.V_t ? a.V_t - 1 : ta);
+                            rb = rb < 0 ? 0 : (rb >= a.V_r ? a.V_r - 1 : rb);
+                            combo = ta * a.V_r + rb - (int)rank * 32 - 0;
+                        }
+                        // this CTA holds combos [rank*32, rank*32+32) of the 64-column slice (NOH = 1) as 4 k-chunks of 8
+#pragma unroll
+                        for (int kc = 0; kc < 4; ++kc) {
+                            uint32_t w[4] = {0u, 0u, 0u, 0u};
+                            if (combo >= 0 && combo < 32 && (combo >> 3) == kc) w[(combo & 7) >> 1] = 0x3F80u << (16 * (combo & 1));
+                            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(sb0 + OH_OFF + kc * (WG_ROWS * 16) + rr * 16),
+                                         "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+                        }
+                    }
+                    ptx::fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(BAR(stage));
+                }
+                if (++stage == S) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue: this CTA's 128 gate columns x (Nmain [+ 64]) -> partial buffer [split][part][gp][320] =====
+        const int q4 = warp & 3, r = q4 * 32 + lane;
+        ptx::mbar_wait(BAR(B_ACCF), 0);
+        ptx::tc_fence_after();
+        const int gp = mp * 256 + (int)rank * 128 + r;
+        float* dst = a.part + (((size_t)split * 2 + part) * a.G4 + gp) * 320;
+        const uint32_t tb = tmem + ((uint32_t)(q4 * 32) << 16);
+        const bool any_main = b1 > b0 && (part == 1 || (a.T > 1 && (b1 - b0 > 1 || (b0 % a.T) != 0)));
+        for (int blk = 0; blk < Nmain / 32; ++blk) {
+            float v[32];
+            if (any_main) { ptx::tmem_ld32(tb + blk * 32, v); ptx::tc_wait_ld(); }
+            else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) *reinterpret_cast<float4*>(dst + blk * 32 + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        }
+        if (part == 0) {
+            for (int blk = 0; blk < 2; ++blk) {
+                float v[32];
+                if (b1 > b0) { ptx::tmem_ld32(tb + 256 + blk * 32, v); ptx::tc_wait_ld(); }
+                else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = 0.f;
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) *reinterpret_cast<float4*>(dst + 256 + blk * 32 + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            }
+        }
+        ptx::tc_fence_before();
+    }
+    ptx::tc_fence_before();
+    ptx::cluster_sync();
+    if (warp == 2) ptx::tmem_dealloc2(tmem, 512);
+}
+
+
+// fixed-order sum of the K-split partials into the flat gradient (accumulating, as accGradParameters does):
+//   part 0, n < N0        -> gWh[row(gp)][n]          part 0, n in [256, 320) -> gP[n - 256][gp] (temporary, overwritten)
+//   part 1, n < KE        -> gWx[row(gp)][d_t + n]
+__global__ void wgrad_reduce_kernel(const float* __restrict__ part, int splits, int G4, int H, int D, int d_t, int d_e, int N0, int KE,
+                                    float* __restrict__ gWh, float* __restrict__ gWx, float* __restrict__ gP) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)2 * G4 * 320) return;
+    const int n = (int)(idx % 320);
+    const int gp = (int)((idx / 320) % G4);
+    const int pt = (int)(idx / ((int64_t)320 * G4));
+    if (pt == 0 && n >= N0 && n < 256) return;
+    if (pt == 1 && n >= KE) return;
+    float acc = 0.f;
+    for (int sp = 0; sp < splits; ++sp) acc += part[(((size_t)sp * 2 + pt) * G4 + gp) * 320 + n];
+    int u;
+    const int row = perm_to_row(gp, H, u);
+    if (pt == 0 && n >= 256) { gP[(size_t)(n - 256) * G4 + gp] = acc; return; }
+    if (u >= H) return;
+    if (pt == 0) { if (n < H) gWh[(size_t)row * H + n] += acc; }
+    else if (n < d_e) gWx[(size_t)row * D + d_t + n] += acc;
+}
+
+// gradient of the hoisted (type,relation) table -> bias, per-type / per-relation sums
+__global__ void ptr_sums_kernel(const float* __restrict__ gP, int G4, int H, int V_t, int V_r, float* __restrict__ Tsum, float* __restrict__ Rsum,
+                                float* __restrict__ gbx) {
+    const int gp = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gp >= G4) return;
+    int u;
+    const int row = perm_to_row(gp, H, u);
+    float all = 0.f;
+    for (int a = 0; a < V_t; ++a) {
+        float s = 0.f;
+        for (int b = 0; b < V_r; ++b) s += gP[(size_t)(a * V_r + b) * G4 + gp];
+        Tsum[(size_t)a * G4 + gp] = s;
+        all += s;
+    }
+    for (int b = 0; b < V_r; ++b) {
+        float s = 0.f;
+        for (int a = 0; a < V_t; ++a) s += gP[(size_t)(a * V_r + b) * G4 + gp];
+        Rsum[(size_t)b * G4 + gp] = s;
+    }
+    if (u < H) gbx[row] += all;
+}
+// gE_type[a][k] += sum_gp Tsum[a][gp] Wx[row(gp)][k];  gE_rel[b][k] += sum_gp Rsum[b][gp] Wx[row(gp)][d_t + d_e + k]
+__global__ void ptr_embed_kernel(const float* __restrict__ Tsum, const float* __restrict__ Rsum, const float* __restrict__ Wx, int G4, int H,
+                                 int D, int d_t, int d_e, int d_r, int V_t, float* __restrict__ gEt, float* __restrict__ gEr) {
+    const int which = blockIdx.x;                // [0, V_t): type rows; then relation rows
+    const bool is_t = which < V_t;
+    const int rowi = is_t ? which : which - V_t;
+    const int width = is_t ? d_t : d_r, coff = is_t ? 0 : d_t + d_e;
+    const float* S = (is_t ? Tsum : Rsum) + (size_t)rowi * G4;
+    for (int k = threadIdx.x; k < width; k += blockDim.x) {
+        float acc = 0.f;
+        for (int gp = 0; gp < G4; ++gp) {
+            int u;
+            const int row = perm_to_row(gp, H, u);
+            if (u < H) acc = fmaf(S[gp], Wx[(size_t)row * D + coff + k], acc);
+        }
+        (is_t ? gEt : gEr)[(size_t)rowi * width + k] += acc;
+    }
+}
+// gWx[row(gp)][k] += sum_a Tsum[a][gp] E_t[a][k]  (type columns)  and the same with Rsum / E_r for the relation columns
+__global__ void ptr_wx_kernel(const float* __restrict__ Tsum, const float* __restrict__ Rsum, const float* __restrict__ Et, const float* __restrict__ Er,
+                              int G4, int H, int D, int d_t, int d_e, int d_r, int V_t, int V_r, float* __restrict__ gWx) {
+    const int gp = blockIdx.x;
+    int u;
+    const int row = perm_to_row(gp, H, u);
+    if (u >= H) return;
+    for (int k = threadIdx.x; k < d_t + d_r; k += blockDim.x) {
+        float acc = 0.f;
+        if (k < d_t) { for (int a = 0; a < V_t; ++a) acc = fmaf(Tsum[(size_t)a * G4 + gp], Et[(size_t)a * d_t + k], acc); }
+        else { const int kk = k - d_t; for (int b = 0; b < V_r; ++b) acc = fmaf(Rsum[(size_t)b * G4 + gp], Er[(size_t)b * d_r + kk], acc); }
+        gWx[(size_t)row * D + (k < d_t ? k : d_e + k)] += acc;
+    }
+}
+// class logit of every path from the fused head partials (what pool_bwd_kernel reads): s[p*L + cls] = sum of 4 partials + bias
+__global__ void cls_logit_kernel(const float* __restrict__ part4, int64_t npad, const float* __restrict__ bias, int64_t N, int L, int cls,
+                                 float* __restrict__ path_logits) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < N) path_logits[p * L + cls] = ((part4[p] + part4[npad + p]) + (part4[2 * npad + p] + part4[3 * npad + p])) + *bias;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+
+static TcTrain* tt_get(kprn_ctx* ctx) {
+    TcState* s = ctx->tc;
+    if (!s->tt) s->tt = new TcTrain();
+    return s->tt;
+}
+
+bool tc_train_supported(const kprn_ctx* ctx) {
+    const kprn_config& c = ctx->cfg;
+    if (!tc_supported(ctx) || c.precision != KPRN_PREC_TC_ALL || c.head_layers != 1) return false;
+    const int KE = round_up(c.d_e, 64);
+    if (KE != 128 && KE != 256) return false;            // the entity operand of wgrad is staged in 64-column swizzled panels per CTA
+    if (c.V_t * c.V_r > 64) return false;                // one one-hot slice
+    { const char* d = getenv("KPRN_TC_TRAIN"); if (d && d[0] == '0') return false; }
+    return true;
+}
+
+static bool encode_2d_u32(CUtensorMap* tm, void* base, uint64_t rows, uint32_t box_rows) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) { cudaGetLastError(); return false; }
+    const cuuint64_t gdim[2] = {512, rows};                 // a k-chunk row = 128 path rows x 16 B = 512 uint32
+    const cuuint64_t gstride[1] = {2048};
+    const cuuint32_t box[2] = {256, box_rows};              // 64 path rows x box_rows k-chunks
+    const cuuint32_t estr[2] = {1, 1};
+    return reinterpret_cast<EncodeFn>(fn)(tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+int tc_train_pack(kprn_ctx* ctx) {
+    TcState* s = ctx->tc;
+    TcTrain* tt = tt_get(ctx);
+    const kprn_config& c = ctx->cfg;
+    const Layout& l = ctx->lay;
+    const int KSg = s->G4 / 64;
+    const int64_t elems = (int64_t)KSg * 2 * 8 * (s->Hp + s->KE) * 8;
+    if (!tt->WT) KPRN_CUDA(cudaMalloc(&tt->WT, sizeof(bf16) * (size_t)elems));
+    if (tt->packed_small == ctx->small_version + ctx->params_version * 1000003ull) return KPRN_OK;
+    pack_wt_kernel<<<(unsigned)cdiv(elems / 2, 256), 256, 0, ctx->stream>>>(ctx->d_params + l.Wh, ctx->d_params + l.Wx, c.H, l.D, c.d_t, c.d_e,
+                                                                           s->G4, s->Hp, s->KE, tt->WT);
+    KPRN_LAUNCH_CHECK(ctx);
+    tt->packed_small = ctx->small_version + ctx->params_version * 1000003ull;
+    return KPRN_OK;
+}
+
+// buffers the TRAIN forward writes (called by tc_forward before the recurrence)
+int tc_train_buffers(kprn_ctx* ctx, int64_t N, float** cache, bf16** hcache) {
+    TcState* s = ctx->tc;
+    TcTrain* tt = tt_get(ctx);
+    const int T = ctx->cfg.T;
+    const int64_t ptiles = cdiv(N, TILE_M);
+    KPRN_TRY(ensure(tt->cache, sizeof(float) * (size_t)ptiles * T * s->NCH * 20480));
+    KPRN_TRY(ensure(tt->hcache, (size_t)ptiles * T * 2 * TILE_M * s->Hp * 2));
+    *cache = tt->cache.as<float>(); *hcache = tt->hcache.as<bf16>();
+    return KPRN_OK;
+}
+
+int tc_backward(kprn_ctx* ctx, float scale) {
+    TcState* s = ctx->tc;
+    TcTrain* tt = tt_get(ctx);
+    const kprn_config& c = ctx->cfg;
+    const Layout& l = ctx->lay;
+    const int T = c.T, G4 = s->G4, Hp = s->Hp, KE = s->KE;
+    const int64_t N = ctx->N, ptiles = cdiv(N, TILE_M);
+    float* gr = ctx->d_grads;
+    const float* P = ctx->d_params;
+    KPRN_TRY(tc_train_pack(ctx));
+    // ---- pool / head gradients on the fp32 kernels (kernels_simple.cu): ds_c[p], gbo[c], gWo[c,:] ----
+    if (ctx->head_part4) {
+        cls_logit_kernel<<<(unsigned)cdiv(N, 256), 256, 0, ctx->stream>>>(ctx->head_part4, ctx->head_npad, P + l.bo + (c.class_id - 1), N, c.L,
+                                                                        c.class_id - 1, ctx->path_logits.as<float>());
+        KPRN_LAUNCH_CHECK(ctx);
+    }
+    KPRN_TRY(head_backward_cls(ctx, scale, s->hT.as<float>(), c.H));
+    const float* ds_c = ctx->ws_ds.as<float>();
+    // ---- buffers ----
+    const size_t dg_bytes = (size_t)ptiles * T * 2 * (G4 / 8) * 2048;
+    KPRN_TRY(ensure(tt->dgop, dg_bytes));
+    KPRN_TRY(ensure(tt->dh, sizeof(float) * (size_t)ptiles * Hp * TILE_M));
+    KPRN_TRY(ensure(tt->dc, sizeof(float) * (size_t)ptiles * Hp * TILE_M));
+    const int items = (G4 / 256) * 2;
+    int splits = (s->num_sms / 2) / items;
+    if (splits < 1) splits = 1;
+    const int64_t nblocks = ptiles * T;
+    if (splits > nblocks) splits = (int)nblocks;
+    const int64_t bps = cdiv(nblocks, splits);
+    splits = (int)cdiv(nblocks, bps);
+    KPRN_TRY(ensure(tt->wpart, sizeof(float) * (size_t)splits * 2 * G4 * 320));
+    KPRN_TRY(ensure(tt->gP, sizeof(float) * (size_t)(64 + c.V_t + c.V_r) * G4));
+    // entity-row gradient target: the compact buffer of a sparse training step, or the dense table
+    float* gE = ctx->sparse_gE ? ctx->sparse_gE : gr + l.E_e;
+    const size_t bg_smem = BG_STAGES * (2 * 16384 + 2 * 8 * (Hp / 2) * 16 + 2 * 8 * (KE / 2) * 16) + 256;
+    KPRN_CUDA(cudaFuncSetAttribute(bgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bg_smem));
+    const int64_t n_tp = (ptiles + 1) / 2;
+    const unsigned bg_grid = (unsigned)(2 * (n_tp < s->num_sms / 2 ? n_tp : s->num_sms / 2));
+    for (int t = T - 1; t >= 0; --t) {
+        CellBwdArgs ca;
+        ca.cache = tt->cache.as<float>(); ca.T = T; ca.t = t; ca.NCH = s->NCH; ca.H = c.H; ca.N = N;
+        ca.dh = t == T - 1 ? nullptr : tt->dh.as<float>(); ca.ds_c = ds_c; ca.wo = P + l.Wo + (int64_t)(c.class_id - 1) * c.H;
+        ca.dc = tt->dc.as<float>(); ca.dgop = tt->dgop.as<bf16>(); ca.G4 = G4;
+        cell_bwd_kernel<<<dim3((unsigned)ptiles, (unsigned)s->NCH), dim3(TILE_M, 4), 0, ctx->stream>>>(ca);
+        KPRN_LAUNCH_CHECK(ctx);
+        BgArgs ba;
+        ba.dgop = tt->dgop.as<bf16>(); ba.WT = tt->WT; ba.T = T; ba.t = t; ba.G4 = G4; ba.N0 = Hp; ba.N1 = KE; ba.num_tiles = ptiles; ba.N = N;
+        ba.part_begin = t == 0 ? 1 : 0; ba.dh = tt->dh.as<float>();
+        ba.gE = gE; ba.d_e = c.d_e; ba.ids = ctx->d_ids; ba.pos = ctx->sparse_gE ? ctx->sparse_pos : nullptr;
+        ba.slot_of = ctx->sparse_gE ? ctx->sparse_slot_of : nullptr; ba.V_e = c.V_e;
+        bgemm_kernel<<<bg_grid, BG_THREADS, bg_smem, ctx->stream>>>(ba);
+        KPRN_LAUNCH_CHECK(ctx);
+    }
+    // ---- weight gradients ----
+    const int64_t dg_rows = ptiles * T * 2 * (G4 / 8), hc_rows = ptiles * T * 2 * (Hp / 8);
+    const int hc_box = (Hp / 16) < 16 ? (Hp / 16) : 16;
+    if (tt->tm_dg_base != tt->dgop.p || tt->tm_dg_rows != dg_rows) {
+        if (!encode_2d_u32(&tt->tm_dg, tt->dgop.p, (uint64_t)dg_rows, 16)) { set_error("tc backward: tensor map (dG) failed"); return KPRN_ECUDA; }
+        tt->tm_dg_base = tt->dgop.p; tt->tm_dg_rows = dg_rows;
+    }
+    if (tt->tm_hc_base != tt->hcache.p || tt->tm_hc_rows != hc_rows) {
+        if (!encode_2d_u32(&tt->tm_hc, tt->hcache.p, (uint64_t)hc_rows, (uint32_t)hc_box)) { set_error("tc backward: tensor map (h) failed"); return KPRN_ECUDA; }
+        tt->tm_hc_base = tt->hcache.p; tt->tm_hc_rows = hc_rows;
+    }
+    {
+        WgArgs wa;
+        wa.ids = ctx->d_ids; wa.N = N; wa.T = T; wa.num_tiles = ptiles; wa.V_r = (int)c.V_r; wa.V_e = c.V_e; wa.V_t = (int)c.V_t;
+        wa.G4 = G4; wa.N0 = Hp; wa.KE = KE; wa.NOH = 1; wa.blocks_per_split = bps; wa.part = tt->wpart.as<float>(); wa.H_BYTES = TILE_M * Hp * 2;
+        wa.hc_box = hc_box;
+        const size_t wg_smem = (size_t)WG_STAGES * (2 * 16384 + 2 * 8192 * 2 + 4096) + 256;
+        KPRN_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wg_smem));
+        wgrad_kernel<<<dim3((unsigned)(items * 2), (unsigned)splits), WG_THREADS, wg_smem, ctx->stream>>>(tt->tm_dg, tt->tm_hc, s->tm_hi, s->tm_lo, wa);
+        KPRN_LAUNCH_CHECK(ctx);
+    }
+    float* gP = tt->gP.as<float>();
+    float* Tsum = gP + (size_t)64 * G4;
+    float* Rsum = Tsum + (size_t)c.V_t * G4;
+    wgrad_reduce_kernel<<<(unsigned)cdiv((int64_t)2 * G4 * 320, 256), 256, 0, ctx->stream>>>(tt->wpart.as<float>(), splits, G4, c.H, l.D, c.d_t, c.d_e,
+                                                                                          Hp, KE, gr + l.Wh, gr + l.Wx, gP);
+    KPRN_LAUNCH_CHECK(ctx);
+    ptr_sums_kernel<<<(unsigned)cdiv(G4, 128), 128, 0, ctx->stream>>>(gP, G4, c.H, (int)c.V_t, (int)c.V_r, Tsum, Rsum, gr + l.bx);
+    KPRN_LAUNCH_CHECK(ctx);
+    ptr_embed_kernel<<<(unsigned)(c.V_t + c.V_r), 256, 0, ctx->stream>>>(Tsum, Rsum, P + l.Wx, G4, c.H, l.D, c.d_t, c.d_e, c.d_r, (int)c.V_t,
+                                                                        gr + l.E_t, gr + l.E_r);
+    KPRN_LAUNCH_CHECK(ctx);
+    ptr_wx_kernel<<<(unsigned)G4, 256, 0, ctx->stream>>>(Tsum, Rsum, P + l.E_t, P + l.E_r, G4, c.H, l.D, c.d_t, c.d_e, c.d_r, (int)c.V_t, (int)c.V_r,
+                                                        gr + l.Wx);
+    KPRN_LAUNCH_CHECK(ctx);
+    return KPRN_OK;
+}
+
+void tc_train_destroy(kprn_ctx* ctx) {
+    TcState* s = ctx->tc;
+    if (!s || !s->tt) return;
+    TcTrain* tt = s->tt;
+    if (tt->WT) cudaFree(tt->WT);
+    for (DBuf* b : {&tt->cache, &tt->hcache, &tt->dgop, &tt->dh, &tt->dc, &tt->wpart, &tt->gP, &tt->cls})
+        if (b->p) { cudaFree(b->p); b->p = nullptr; b->cap = 0; }
+    delete tt;
+    s->tt = nullptr;
+}
+
+}  // namespace kprn

@@ -47,12 +47,12 @@ def _oracle_train(o, params, batches, pads, steps, loss="bce", lr=1e-3):
     return x, losses
 
 
-@pytest.mark.parametrize("precision", [0, 3])
-def test_sparse_step_equals_dense_flow_and_oracle(precision):
+@pytest.mark.parametrize("precision,dims", [(0, (64, 64)), (3, (64, 64)), (3, (128, 128))])
+def test_sparse_step_equals_dense_flow_and_oracle(precision, dims):
     """5 steps over 3 rotating batches drawn from a 4000-row table (most rows sit out some steps): parameters after the
     last step -- read once, so every postponed update is replayed by the flush -- match the dense flow and the oracle."""
     V_e = 4000
-    o, params, _, _, _ = make_case(N=64, seed=70, d_t=8, d_e=64, d_r=8, H=64, V_e=V_e)
+    o, params, _, _, _ = make_case(N=64, seed=70, d_t=8, d_e=dims[0], d_r=8, H=dims[1], V_e=V_e)      # (128, 128): the fused tensor-core training kernels
     c = o.cfg
     pads = (c.V_t, c.V_e, c.V_r)
     batches = _batches(o, 3, 600, 700, V_e)
@@ -140,7 +140,11 @@ def test_bpr_train_step_matches_oracle(on_logits):
     assert abs(loss - lv) <= 1e-4 * abs(lv)
     g = e.get_grads()                      # dense view of the sparse step's gradient
     for name in o.shapes():
-        assert_rel(o.view(g, name), o.view(g_ref, name), what="grad " + name)
+        r = o.view(g_ref, name)
+        if np.sqrt(np.mean(r * r)) < 1e-12:       # BPR on logits: every pair adds +s and -s to the class bias -> exactly zero
+            assert np.abs(o.view(g, name)).max() < 1e-5, name
+            continue
+        assert_rel(o.view(g, name), r, what="grad " + name)
     # kprn_train_batch_bpr is the same step
     e2 = engine_for(o, precision=0)
     e2.set_params(params)

@@ -4,7 +4,7 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from tests.util import make_case, engine_for
 
-for kw in (dict(N=333, seed=33, d_t=50, d_e=100, d_r=50, H=250, V_e=3000), dict(N=900, seed=34, d_t=32, d_e=256, d_r=32, H=256, V_e=5000)):
+for kw in (dict(N=1500, seed=32, d_t=16, d_e=128, d_r=16, H=128, V_e=2000), dict(N=333, seed=33, d_t=50, d_e=100, d_r=50, H=250, V_e=3000), dict(N=900, seed=34, d_t=32, d_e=256, d_r=32, H=256, V_e=5000)):
     o, params, ids, seg, labels = make_case(**kw)
     ref = o.forward(params, ids, seg, cache=True)
     loss_ref, dsc = o.bce(ref["scores"], labels)
