@@ -32,9 +32,9 @@ struct TrainState {
     bool pending = false;         // some rows are behind ctx->adam_t
     bool sparse_grads = false;    // the last backward left the entity gradient in gE (kprn_get_grads materialises it)
     int64_t sparse_N = 0;         // paths of the batch gE belongs to
-    std::vector<float> steps_h;   // step size of optimizer step k at [k] (k = 1..adam_t)
-    DBuf steps;                   // device copy
-    int64_t steps_on_dev = 0;
+    float* steps_pinned = nullptr; // step size of optimizer step k at [k] (k = 1..adam_t), page-locked mirror
+    DBuf steps;                   // device copy read by the replay
+    int64_t steps_cap = 0;
     float b1 = 0.f, b2 = 0.f, eps = 0.f;
     // multi-GPU exchange
     DBuf send_ids, recv_ids, recv_g, contrib, norm2;
@@ -242,24 +242,28 @@ static float adam_step_size(float lr, float b1, float b2, int64_t t) {
     return (float)((double)lr * sqrt(bc2) / bc1);
 }
 
-// records the step size of optimizer step ctx->adam_t (already incremented) on host and device
+// records the step size of optimizer step ctx->adam_t (already incremented): steps[t] on the device, without a host sync
+// (the value travels from a page-locked mirror that lives as long as the ctx)
 static int steps_push(kprn_ctx* ctx, TrainState* tr, float step) {
     const int64_t t = ctx->adam_t;
-    if ((int64_t)tr->steps_h.size() < t + 1) tr->steps_h.resize(t + 1, 0.f);
-    tr->steps_h[t] = step;
-    if (tr->steps.cap < sizeof(float) * (size_t)(t + 1)) {
+    if (tr->steps_cap < t + 1) {
+        const int64_t ncap = 2 * t + 1024;
+        float* nh = nullptr;
+        KPRN_CUDA(cudaMallocHost(&nh, sizeof(float) * (size_t)ncap));
         DBuf nb;
-        KPRN_TRY(ensure(nb, sizeof(float) * (size_t)(2 * t + 1024)));
-        if (tr->steps.p) { KPRN_CUDA(cudaStreamSynchronize(ctx->stream)); cudaFree(tr->steps.p); }
-        tr->steps = nb;
-        tr->steps_on_dev = 0;
+        if (ensure(nb, sizeof(float) * (size_t)ncap) != KPRN_OK) { cudaFreeHost(nh); return KPRN_ENOMEM; }
+        KPRN_CUDA(cudaStreamSynchronize(ctx->stream));            // rare (capacity doubles): in-flight copies read the old mirror
+        if (tr->steps_pinned) { memcpy(nh, tr->steps_pinned, sizeof(float) * (size_t)tr->steps_cap); cudaFreeHost(tr->steps_pinned); }
+        else nh[0] = 0.f;
+        if (tr->steps.p) {
+            KPRN_CUDA(cudaMemcpyAsync(nb.p, tr->steps.p, sizeof(float) * (size_t)tr->steps_cap, cudaMemcpyDeviceToDevice, ctx->stream));
+            KPRN_CUDA(cudaStreamSynchronize(ctx->stream));
+            cudaFree(tr->steps.p);
+        }
+        tr->steps = nb; tr->steps_pinned = nh; tr->steps_cap = ncap;
     }
-    // (re)upload what the device copy lacks; steps_h lives as long as the ctx and the copy is issued from a stable address
-    const int64_t from = tr->steps_on_dev;
-    KPRN_CUDA(cudaMemcpyAsync(tr->steps.as<float>() + from, tr->steps_h.data() + from, sizeof(float) * (size_t)(t + 1 - from),
-                              cudaMemcpyHostToDevice, ctx->stream));
-    KPRN_CUDA(cudaStreamSynchronize(ctx->stream));     // pageable source: the vector may be reallocated by the next push
-    tr->steps_on_dev = t + 1;
+    tr->steps_pinned[t] = step;
+    KPRN_CUDA(cudaMemcpyAsync(tr->steps.as<float>() + t, tr->steps_pinned + t, sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     return KPRN_OK;
 }
 
@@ -299,6 +303,7 @@ void train_destroy(kprn_ctx* ctx) {
     for (DBuf* b : {&tr->gE, &tr->steps, &tr->send_ids, &tr->recv_ids, &tr->recv_g, &tr->contrib, &tr->norm2})
         if (b->p) { cudaFree(b->p); b->p = nullptr; b->cap = 0; }
     if (tr->last_t) cudaFree(tr->last_t);
+    if (tr->steps_pinned) cudaFreeHost(tr->steps_pinned);
     delete tr;
     ctx->tr = nullptr;
 }
