@@ -31,7 +31,7 @@ bool tc_supported(const kprn_ctx* ctx) {
     int KE = round_up(c.d_e, 64);
     if (c.H > 256 || KE > 256) return false;
     int noh = (int)((c.V_t * c.V_r + 63) / 64);
-    if (noh > 2 || KE / 64 + noh > MAX_NS) return false;   // (type,relation) combos ride the MMA as a one-hot k-slice
+    if (noh > 2 || KE / 64 + noh > MAX_NS || c.V_t + c.V_r > 160) return false;   // (type,relation) combos ride the MMA as a one-hot k-slice
     return true;
 }
 
@@ -121,25 +121,29 @@ __global__ void pack_wh_kernel(const float* __restrict__ Wh, int H, int NCH, int
     out[base + B_SLAB_ELEMS] = l;
 }
 
-// hoisted small-vocabulary projection: P_tr[a*V_r+b][g'] = bx + E_t[a] Wx_t^T + E_r[b] Wx_r^T  (fp32 FFMA)
-__global__ void ptr_table_kernel(const float* __restrict__ P, Layout l, int d_t, int d_e, int d_r, int H, int V_r,
+// hoisted small-vocabulary projection: P_tr[a*V_r+b][g'] = bx + E_t[a] Wx_t^T + E_r[b] Wx_r^T  (fp32 FFMA).
+// One block per gate column: the V_t + V_r dot products of that column's weight row (each warp takes some of them, lanes
+// stride over k, shuffle reduction), then the V_t*V_r sums -- 15 dot products per column instead of 54 x 2.
+__global__ void ptr_table_kernel(const float* __restrict__ P, Layout l, int d_t, int d_e, int d_r, int H, int V_t, int V_r,
                                  int G4, float* __restrict__ out) {
-    int combo = blockIdx.x;
-    int a = combo / V_r, b = combo % V_r;
-    const float* et = P + l.E_t + (int64_t)a * d_t;
-    const float* er = P + l.E_r + (int64_t)b * d_r;
-    for (int gp = threadIdx.x; gp < G4; gp += blockDim.x) {
-        int u;
-        int row = perm_to_row(gp, H, u);
-        float acc = 0.f;
-        if (u < H) {
-            const float* w = P + l.Wx + (int64_t)row * l.D;
-            acc = P[l.bx + row];
-            for (int k = 0; k < d_t; ++k) acc = fmaf(et[k], w[k], acc);
-            for (int k = 0; k < d_r; ++k) acc = fmaf(er[k], w[d_t + d_e + k], acc);
+    __shared__ float dots[160];
+    const int gp = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    int u;
+    const int row = perm_to_row(gp, H, u);
+    if (u < H) {
+        const float* w = P + l.Wx + (int64_t)row * l.D;
+        for (int q = warp; q < V_t + V_r; q += nw) {
+            float acc = 0.f;
+            if (q < V_t) { const float* e = P + l.E_t + (int64_t)q * d_t; for (int k = lane; k < d_t; k += 32) acc = fmaf(e[k], w[k], acc); }
+            else { const float* e = P + l.E_r + (int64_t)(q - V_t) * d_r; for (int k = lane; k < d_r; k += 32) acc = fmaf(e[k], w[d_t + d_e + k], acc); }
+            for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (lane == 0) dots[q] = acc;
         }
-        out[(int64_t)combo * G4 + gp] = acc;
     }
+    __syncthreads();
+    const float b = u < H ? P[l.bx + row] : 0.f;
+    for (int combo = threadIdx.x; combo < V_t * V_r; combo += blockDim.x)
+        out[(int64_t)combo * G4 + gp] = u < H ? (b + dots[combo / V_r]) + dots[V_t + combo % V_r] : 0.f;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1055,7 +1059,7 @@ static int tc_pack(kprn_ctx* ctx) {
     int64_t nh = (int64_t)s->NCH * s->KSh * B_SLAB_ELEMS;
     pack_wh_kernel<<<(unsigned)cdiv(nh, 256), 256, 0, ctx->stream>>>(ctx->d_params + l.Wh, c.H, s->NCH, s->KSh, s->recur_pairs ? 1 : 0, s->Wh);
     KPRN_LAUNCH_CHECK(ctx);
-    ptr_table_kernel<<<(unsigned)(c.V_t * c.V_r), 256, 0, ctx->stream>>>(ctx->d_params, l, c.d_t, c.d_e, c.d_r, c.H, (int)c.V_r, s->G4, s->Ptr);
+    ptr_table_kernel<<<(unsigned)s->G4, 128, 0, ctx->stream>>>(ctx->d_params, l, c.d_t, c.d_e, c.d_r, c.H, (int)c.V_t, (int)c.V_r, s->G4, s->Ptr);
     KPRN_LAUNCH_CHECK(ctx);
     int64_t nw = (int64_t)s->NCH * s->NS * B_SLAB_ELEMS;
     pack_wxe_kernel<<<(unsigned)cdiv(nw, 256), 256, 0, ctx->stream>>>(ctx->d_params + l.Wx, s->Ptr, c.H, l.D, c.d_t, c.d_e, s->NCH,

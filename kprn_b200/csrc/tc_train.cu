@@ -13,6 +13,8 @@
 //   wgrad_reduce_kernel fixed-order sum of the K-split partials into the flat gradient; ptr_grad_kernel turns gP (the
 //                       gradient of the hoisted (type,relation) table) into gE_type, gE_relation, gWx[:, type|relation], gbx.
 // The head / pool / loss gradients stay on the fp32 kernels of kernels_simple.cu (0.2 % of the flops).
+#include <cub/device/device_radix_sort.cuh>
+
 #include "tc_state.cuh"
 
 namespace kprn {
@@ -27,6 +29,8 @@ struct TcTrain {
     uint64_t packed_small = 0;
     bf16* WT = nullptr;               // bgemm B operand: [part 2][ks G4/64][hi|lo][half 2][kc 8][n Nh][8]
     DBuf cache, hcache, dgop, dh, dc, wpart, gP, cls;
+    DBuf dX, eg_keys, eg_vals, eg_tmp, eg_part, eg_flags;     // entity-gradient staging + sorted segment reduce
+    DedupBufs es;                     // distinct entity rows of the batch when the caller (a sparse training step) did not build them
     CUtensorMap tm_dg, tm_hc;         // 2-D maps over dgop / hcache (uint32 view): box = 64 rows x 16 k-chunks
     void* tm_dg_base = nullptr; void* tm_hc_base = nullptr; int64_t tm_dg_rows = 0, tm_hc_rows = 0;
 };
@@ -159,13 +163,9 @@ struct BgArgs {
     const bf16* dgop; const bf16* WT; int T; int t; int G4; int N0, N1; int64_t num_tiles; int64_t N;
     int part_begin;           // 1 at t = 0 (no dh needed)
     float* dh;                // [tile][N0/8][row 128][8]
-    // dX rows: += into gE (dense: row = entity id - 1; compact: slot_of[pos[o]])
-    float* gE; int d_e; const int32_t* ids; const uint32_t* pos; const uint32_t* slot_of; int64_t V_e;
+    float* dX;                // [(tile*T + t)*128 + row][N1] fp32: the entity-slice input gradient of every path-step (row index =
+                              // the read-order index o of the slot maps); summed per entity row by the sorted segment reduce below
 };
-
-__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BG_THREADS, 1) bgemm_kernel(BgArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -295,32 +295,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BG_THREADS, 1) bgemm
                     }
                 }
             } else {
-                const int64_t n = m * TILE_M + r;
-                float* ge = nullptr;
-                // an odd tail tile is computed by both CTAs of the last pair: only rank 0 adds it
-                const bool dup = (2 * (pair + it * npairs) + rank) >= a.num_tiles;
-                if (n < a.N && !dup) {
-                    if (a.pos) {
-                        const uint32_t p = a.pos[(m * a.T + a.t) * TILE_M + r];
-                        if (p != 0xFFFFFFFFu) ge = a.gE + (size_t)a.slot_of[p] * a.d_e;
-                    } else {
-                        int64_t ie = (int64_t)a.ids[(n * a.T + a.t) * 3 + 1] - 1;
-                        if (ie >= 0 && ie < a.V_e) ge = a.gE + (size_t)ie * a.d_e;
-                    }
-                }
+                float* dst = a.dX + ((size_t)(m * a.T + a.t) * TILE_M + r) * a.N1;
                 for (int blk = 0; blk < a.N1 / 32; ++blk) {
                     float v[32];
                     ptx::tmem_ld32(tb + blk * 32, v);
                     ptx::tc_wait_ld();
-                    if (ge) {
-                        if ((a.d_e & 3) == 0 && blk * 32 + 32 <= a.d_e) {
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) red_add_v4(ge + blk * 32 + 4 * i, v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) if (blk * 32 + i < a.d_e) atomicAdd(ge + blk * 32 + i, v[i]);
-                        }
-                    }
+                    for (int i = 0; i < 4; ++i) ptx::stg256(dst + blk * 32 + 8 * i, v + 8 * i);     // one full 32-byte sector per store
                 }
             }
             ptx::tc_fence_before();
@@ -633,6 +614,7 @@ __global__ void ptr_sums_kernel(const float* __restrict__ gP, int G4, int H, int
     if (u < H) gbx[row] += all;
 }
 // gE_type[a][k] += sum_gp Tsum[a][gp] Wx[row(gp)][k];  gE_rel[b][k] += sum_gp Rsum[b][gp] Wx[row(gp)][d_t + d_e + k]
+// grid (V_t + V_r, column chunks of 64, 8 gate-column ranges): threads = columns (coalesced weight reads), one atomicAdd per range
 __global__ void ptr_embed_kernel(const float* __restrict__ Tsum, const float* __restrict__ Rsum, const float* __restrict__ Wx, int G4, int H,
                                  int D, int d_t, int d_e, int d_r, int V_t, float* __restrict__ gEt, float* __restrict__ gEr) {
     const int which = blockIdx.x;                // [0, V_t): type rows; then relation rows
@@ -640,15 +622,16 @@ __global__ void ptr_embed_kernel(const float* __restrict__ Tsum, const float* __
     const int rowi = is_t ? which : which - V_t;
     const int width = is_t ? d_t : d_r, coff = is_t ? 0 : d_t + d_e;
     const float* S = (is_t ? Tsum : Rsum) + (size_t)rowi * G4;
-    for (int k = threadIdx.x; k < width; k += blockDim.x) {
-        float acc = 0.f;
-        for (int gp = 0; gp < G4; ++gp) {
-            int u;
-            const int row = perm_to_row(gp, H, u);
-            if (u < H) acc = fmaf(S[gp], Wx[(size_t)row * D + coff + k], acc);
-        }
-        (is_t ? gEt : gEr)[(size_t)rowi * width + k] += acc;
+    const int k = blockIdx.y * 64 + threadIdx.x;
+    if (k >= width) return;
+    const int g0 = blockIdx.z * (G4 / 8), g1 = g0 + G4 / 8;
+    float acc = 0.f;
+    for (int gp = g0; gp < g1; ++gp) {
+        int u;
+        const int row = perm_to_row(gp, H, u);
+        if (u < H) acc = fmaf(S[gp], Wx[(size_t)row * D + coff + k], acc);
     }
+    atomicAdd((is_t ? gEt : gEr) + (size_t)rowi * width + k, acc);
 }
 // gWx[row(gp)][k] += sum_a Tsum[a][gp] E_t[a][k]  (type columns)  and the same with Rsum / E_r for the relation columns
 __global__ void ptr_wx_kernel(const float* __restrict__ Tsum, const float* __restrict__ Rsum, const float* __restrict__ Et, const float* __restrict__ Er,
@@ -669,6 +652,100 @@ __global__ void cls_logit_kernel(const float* __restrict__ part4, int64_t npad, 
                                  float* __restrict__ path_logits) {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p < N) path_logits[p * L + cls] = ((part4[p] + part4[npad + p]) + (part4[2 * npad + p] + part4[3 * npad + p])) + *bias;
+}
+
+// ---------------------------------------------------------------------------------------------
+// LookupTable:accGradParameters for the entity table WITHOUT atomics: dX[o] (one row per path-step, staged by bgemm) is summed
+// per distinct entity row in a fixed order.  (slot, o) pairs are radix-sorted by slot (stable: occurrences stay in index
+// order); a warp per chunk of EG_CHUNK sorted entries sums runs of equal slot; a run that lies inside one chunk is added to
+// its gradient row directly (no other writer exists), runs crossing chunk boundaries leave partial rows that one warp per run
+// combines in chunk order.  Deterministic, and immune to the contention float atomics suffer on hot rows (the pad row alone
+// is ~20 % of all steps of a batch).
+
+constexpr int EG_CHUNK = 64;
+
+__global__ void eg_keys_kernel(const uint32_t* __restrict__ pos, const uint32_t* __restrict__ slot_of, int64_t n, uint32_t* __restrict__ keys,
+                               uint32_t* __restrict__ vals) {
+    const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= n) return;
+    const uint32_t p = pos[o];
+    keys[o] = p == 0xFFFFFFFFu ? (uint32_t)n : slot_of[p];      // rows of a ragged last tile sort to the end
+    vals[o] = (uint32_t)o;
+}
+
+struct EgArgs {
+    const uint32_t* keys; const uint32_t* vals; int64_t n; int64_t n_chunks;
+    const float* dX; int ldx; int d_e;
+    float* target; const int32_t* rows;       // target row of slot s: rows ? rows[s] - 1 : s   (dense table / compact buffer)
+    float* part;                              // [chunk][2][d_e]: 0 = run touching the chunk's begin, 1 = run touching its end
+    int32_t* flags;                           // [chunk][4]: head key (-1 none), head continues into the next chunk, tail key (-1 none), unused
+};
+
+__global__ void __launch_bounds__(256) eg_reduce_kernel(EgArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int64_t chunk = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (chunk >= a.n_chunks) return;
+    const int64_t e0 = chunk * EG_CHUNK, e1 = (e0 + EG_CHUNK < a.n) ? e0 + EG_CHUNK : a.n;
+    const uint32_t INVALID = (uint32_t)a.n;
+    const uint32_t prev_key = e0 > 0 ? a.keys[e0 - 1] : INVALID;
+    const uint32_t next_key = e1 < a.n ? a.keys[e1] : INVALID;
+    int32_t head_key = -1, head_cont = 0, tail_key = -1;
+    constexpr int MAXV = 8;                    // d_e <= 256: 8 floats per lane
+    float acc[MAXV];
+    int64_t e = e0;
+    while (e < e1) {
+        const uint32_t key = a.keys[e];
+        if (key == INVALID) break;             // the rest of the array is padding
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) acc[i] = 0.f;
+        const bool starts_here = !(e == e0 && prev_key == key);
+        int64_t f = e;
+        while (f < e1 && a.keys[f] == key) {
+            const float* src = a.dX + (size_t)a.vals[f] * a.ldx;
+#pragma unroll
+            for (int i = 0; i < MAXV; ++i) { const int k = i * 32 + lane; if (k < a.d_e) acc[i] += src[k]; }
+            ++f;
+        }
+        const bool ends_here = !(f == e1 && next_key == key);
+        if (starts_here && ends_here) {
+            float* dst = a.target + (size_t)(a.rows ? a.rows[key] - 1 : key) * a.d_e;
+#pragma unroll
+            for (int i = 0; i < MAXV; ++i) { const int k = i * 32 + lane; if (k < a.d_e) dst[k] += acc[i]; }
+        } else {
+            const int which = starts_here ? 1 : 0;
+            float* dst = a.part + ((size_t)chunk * 2 + which) * a.d_e;
+#pragma unroll
+            for (int i = 0; i < MAXV; ++i) { const int k = i * 32 + lane; if (k < a.d_e) dst[k] = acc[i]; }
+            if (which) tail_key = (int32_t)key;
+            else { head_key = (int32_t)key; head_cont = ends_here ? 0 : 1; }
+        }
+        e = f;
+    }
+    if (lane == 0) { a.flags[chunk * 4] = head_key; a.flags[chunk * 4 + 1] = head_cont; a.flags[chunk * 4 + 2] = tail_key; }
+}
+
+// one warp per chunk that OWNS a boundary-crossing run (the chunk where the run starts): tail + following heads, in chunk order
+__global__ void __launch_bounds__(256) eg_fixup_kernel(EgArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int64_t chunk = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (chunk >= a.n_chunks) return;
+    const int32_t key = a.flags[chunk * 4 + 2];
+    if (key < 0) return;
+    constexpr int MAXV = 8;
+    float acc[MAXV];
+    const float* src = a.part + ((size_t)chunk * 2 + 1) * a.d_e;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) { const int k = i * 32 + lane; acc[i] = k < a.d_e ? src[k] : 0.f; }
+    for (int64_t j = chunk + 1; j < a.n_chunks; ++j) {
+        if (a.flags[j * 4] != key) break;
+        const float* s2 = a.part + ((size_t)j * 2) * a.d_e;
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) { const int k = i * 32 + lane; if (k < a.d_e) acc[i] += s2[k]; }
+        if (!a.flags[j * 4 + 1]) break;
+    }
+    float* dst = a.target + (size_t)(a.rows ? a.rows[key] - 1 : key) * a.d_e;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) { const int k = i * 32 + lane; if (k < a.d_e) dst[k] += acc[i]; }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -765,8 +842,16 @@ int tc_backward(kprn_ctx* ctx, float scale) {
     splits = (int)cdiv(nblocks, bps);
     KPRN_TRY(ensure(tt->wpart, sizeof(float) * (size_t)splits * 2 * G4 * 320));
     KPRN_TRY(ensure(tt->gP, sizeof(float) * (size_t)(64 + c.V_t + c.V_r) * G4));
-    // entity-row gradient target: the compact buffer of a sparse training step, or the dense table
-    float* gE = ctx->sparse_gE ? ctx->sparse_gE : gr + l.E_e;
+    // entity-row gradients: bgemm stages dX per path-step; the sorted segment reduce below adds them per distinct row into the
+    // compact buffer of a sparse training step (slot-indexed) or into the dense table
+    const int64_t n_order = ptiles * T * TILE_M;
+    KPRN_TRY(ensure(tt->dX, sizeof(float) * (size_t)n_order * KE));
+    const uint32_t* eg_pos; const uint32_t* eg_slot_of; const int32_t* eg_rows = nullptr; float* eg_target;
+    if (ctx->sparse_gE) { eg_pos = ctx->sparse_pos; eg_slot_of = ctx->sparse_slot_of; eg_target = ctx->sparse_gE; }
+    else {
+        KPRN_TRY(dedup_build(ctx, tt->es, 1, ctx->d_ids, N, T, 0));
+        eg_pos = tt->es.pos.as<uint32_t>(); eg_slot_of = tt->es.slot_of.as<uint32_t>(); eg_rows = tt->es.ids.as<int32_t>(); eg_target = gr + l.E_e;
+    }
     const size_t bg_smem = BG_STAGES * (2 * 16384 + 2 * 8 * (Hp / 2) * 16 + 2 * 8 * (KE / 2) * 16) + 256;
     KPRN_CUDA(cudaFuncSetAttribute(bgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bg_smem));
     const int64_t n_tp = (ptiles + 1) / 2;
@@ -781,9 +866,34 @@ int tc_backward(kprn_ctx* ctx, float scale) {
         BgArgs ba;
         ba.dgop = tt->dgop.as<bf16>(); ba.WT = tt->WT; ba.T = T; ba.t = t; ba.G4 = G4; ba.N0 = Hp; ba.N1 = KE; ba.num_tiles = ptiles; ba.N = N;
         ba.part_begin = t == 0 ? 1 : 0; ba.dh = tt->dh.as<float>();
-        ba.gE = gE; ba.d_e = c.d_e; ba.ids = ctx->d_ids; ba.pos = ctx->sparse_gE ? ctx->sparse_pos : nullptr;
-        ba.slot_of = ctx->sparse_gE ? ctx->sparse_slot_of : nullptr; ba.V_e = c.V_e;
+        ba.dX = tt->dX.as<float>();
         bgemm_kernel<<<bg_grid, BG_THREADS, bg_smem, ctx->stream>>>(ba);
+        KPRN_LAUNCH_CHECK(ctx);
+    }
+    // ---- entity-table gradient: sorted segment reduce of the staged dX rows ----
+    {
+        int end_bit = 1;
+        while ((1ll << end_bit) <= n_order) ++end_bit;
+        KPRN_TRY(ensure(tt->eg_keys, sizeof(uint32_t) * 2 * (size_t)n_order));
+        KPRN_TRY(ensure(tt->eg_vals, sizeof(uint32_t) * 2 * (size_t)n_order));
+        uint32_t* k_in = tt->eg_keys.as<uint32_t>(); uint32_t* k_out = k_in + n_order;
+        uint32_t* v_in = tt->eg_vals.as<uint32_t>(); uint32_t* v_out = v_in + n_order;
+        eg_keys_kernel<<<(unsigned)cdiv(n_order, 256), 256, 0, ctx->stream>>>(eg_pos, eg_slot_of, n_order, k_in, v_in);
+        KPRN_LAUNCH_CHECK(ctx);
+        size_t tmp_bytes = 0;
+        KPRN_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k_in, k_out, v_in, v_out, (int)n_order, 0, end_bit, ctx->stream));
+        KPRN_TRY(ensure(tt->eg_tmp, tmp_bytes));
+        KPRN_CUDA(cub::DeviceRadixSort::SortPairs(tt->eg_tmp.p, tmp_bytes, k_in, k_out, v_in, v_out, (int)n_order, 0, end_bit, ctx->stream));
+        ctx->launches += 4;
+        EgArgs ea;
+        ea.keys = k_out; ea.vals = v_out; ea.n = n_order; ea.n_chunks = cdiv(n_order, EG_CHUNK);
+        ea.dX = tt->dX.as<float>(); ea.ldx = KE; ea.d_e = c.d_e; ea.target = eg_target; ea.rows = eg_rows;
+        KPRN_TRY(ensure(tt->eg_part, sizeof(float) * (size_t)ea.n_chunks * 2 * c.d_e));
+        KPRN_TRY(ensure(tt->eg_flags, sizeof(int32_t) * (size_t)ea.n_chunks * 4));
+        ea.part = tt->eg_part.as<float>(); ea.flags = tt->eg_flags.as<int32_t>();
+        eg_reduce_kernel<<<(unsigned)cdiv(ea.n_chunks, 8), 256, 0, ctx->stream>>>(ea);
+        KPRN_LAUNCH_CHECK(ctx);
+        eg_fixup_kernel<<<(unsigned)cdiv(ea.n_chunks, 8), 256, 0, ctx->stream>>>(ea);
         KPRN_LAUNCH_CHECK(ctx);
     }
     // ---- weight gradients ----
@@ -815,8 +925,11 @@ int tc_backward(kprn_ctx* ctx, float scale) {
     KPRN_LAUNCH_CHECK(ctx);
     ptr_sums_kernel<<<(unsigned)cdiv(G4, 128), 128, 0, ctx->stream>>>(gP, G4, c.H, (int)c.V_t, (int)c.V_r, Tsum, Rsum, gr + l.bx);
     KPRN_LAUNCH_CHECK(ctx);
-    ptr_embed_kernel<<<(unsigned)(c.V_t + c.V_r), 256, 0, ctx->stream>>>(Tsum, Rsum, P + l.Wx, G4, c.H, l.D, c.d_t, c.d_e, c.d_r, (int)c.V_t,
-                                                                        gr + l.E_t, gr + l.E_r);
+    {
+        const int wmax = c.d_t > c.d_r ? c.d_t : c.d_r;
+        ptr_embed_kernel<<<dim3((unsigned)(c.V_t + c.V_r), (unsigned)cdiv(wmax, 64), 8), 64, 0, ctx->stream>>>(
+            Tsum, Rsum, P + l.Wx, G4, c.H, l.D, c.d_t, c.d_e, c.d_r, (int)c.V_t, gr + l.E_t, gr + l.E_r);
+    }
     KPRN_LAUNCH_CHECK(ctx);
     ptr_wx_kernel<<<(unsigned)G4, 256, 0, ctx->stream>>>(Tsum, Rsum, P + l.E_t, P + l.E_r, G4, c.H, l.D, c.d_t, c.d_e, c.d_r, (int)c.V_t, (int)c.V_r,
                                                         gr + l.Wx);
@@ -829,8 +942,10 @@ void tc_train_destroy(kprn_ctx* ctx) {
     if (!s || !s->tt) return;
     TcTrain* tt = s->tt;
     if (tt->WT) cudaFree(tt->WT);
-    for (DBuf* b : {&tt->cache, &tt->hcache, &tt->dgop, &tt->dh, &tt->dc, &tt->wpart, &tt->gP, &tt->cls})
+    for (DBuf* b : {&tt->cache, &tt->hcache, &tt->dgop, &tt->dh, &tt->dc, &tt->wpart, &tt->gP, &tt->cls, &tt->dX, &tt->eg_keys, &tt->eg_vals,
+                    &tt->eg_tmp, &tt->eg_part, &tt->eg_flags})
         if (b->p) { cudaFree(b->p); b->p = nullptr; b->cap = 0; }
+    dedup_free(tt->es);
     delete tt;
     s->tt = nullptr;
 }

@@ -79,16 +79,24 @@ struct RowsArgs {
     __nv_bfloat16* E_hi; __nv_bfloat16* E_lo;       // packed bf16 copies of the entity table (tensor-core forward), or null
 };
 
-// one block per slot (grid-stride): catch the row up, optionally apply this step's gradient, refresh the packed copies
-__global__ void adam_rows_kernel(RowsArgs a) {
+// one WARP per slot (grid-stride over slots): catch the row up, optionally apply this step's gradient, refresh the packed
+// copies.  A row is a few hundred floats, so a warp streams it with a handful of independent 128-bit loads per array, and
+// thousands of rows are in flight per SM-set; rows with nothing to replay are skipped by the catch-up pass before any load.
+__global__ void __launch_bounds__(256) adam_rows_kernel(RowsArgs a) {
     const int K = *a.count;
-    for (int slot = blockIdx.x; slot < K; slot += gridDim.x) {
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    const float gs = a.gscale ? *a.gscale : 1.f;
+    for (int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; slot < K; slot += warps) {
         const int64_t row = (int64_t)a.rows[slot] - 1;
-        const int32_t lt = a.last_t[row];
+        const int32_t lt = a.last_t[row];                  // every lane reads it before lane 0 rewrites it (the __syncwarp below)
         const int64_t t0 = lt > a.base_t ? lt : a.base_t;
         const bool may_have_state = lt != 0 || a.dense_ever;
-        const float gs = a.gscale ? *a.gscale : 1.f;
-        for (int k = threadIdx.x; k < a.d_e; k += blockDim.x) {
+        if (!a.apply && (t0 >= a.t_now - 1 || !may_have_state)) {       // nothing postponed for this row
+            __syncwarp();
+            continue;
+        }
+        for (int k = lane; k < a.d_e; k += 32) {
             const int64_t i = row * a.d_e + k;
             float x = a.x[i], m = a.m[i], v = a.v[i];
             if (may_have_state) adam_replay(x, m, v, t0, a.t_now - 1, a.steps, a.b1, a.b2, a.eps);
@@ -109,9 +117,8 @@ __global__ void adam_rows_kernel(RowsArgs a) {
             a.x[i] = x; a.m[i] = m; a.v[i] = v;
             if (a.E_hi) split_store(x, a.E_hi, a.E_lo, row * a.KE + k);
         }
-        __syncthreads();                                   // every thread has read last_t[row]
-        if (threadIdx.x == 0) a.last_t[row] = (int32_t)(a.apply ? a.t_now : a.t_now - 1);
-        __syncthreads();
+        __syncwarp();
+        if (lane == 0) a.last_t[row] = (int32_t)(a.apply ? a.t_now : a.t_now - 1);
     }
 }
 
@@ -368,9 +375,8 @@ static int rows_launch(kprn_ctx* ctx, TrainState* tr, const int32_t* rows, const
     a.gscale = gscale; a.steps = tr->steps.as<float>(); a.b1 = tr->b1; a.b2 = tr->b2; a.eps = tr->eps; a.d_e = c.d_e;
     a.E_hi = nullptr; a.E_lo = nullptr; a.KE = 0;
     packed_entity(ctx, &a.E_hi, &a.E_lo, &a.KE);
-    const int threads = c.d_e >= 256 ? 256 : (c.d_e >= 128 ? 128 : 64);
-    int64_t grid = grid_hint < 148 * 8 ? (grid_hint < 1 ? 1 : grid_hint) : 148 * 8;
-    adam_rows_kernel<<<(unsigned)grid, threads, 0, ctx->stream>>>(a);
+    int64_t grid = cdiv(grid_hint, 8) < 148 * 8 ? (grid_hint < 1 ? 1 : cdiv(grid_hint, 8)) : 148 * 8;      // 8 warps per block, a warp per row
+    adam_rows_kernel<<<(unsigned)grid, 256, 0, ctx->stream>>>(a);
     KPRN_LAUNCH_CHECK(ctx);
     return KPRN_OK;
 }

@@ -197,8 +197,18 @@ end
 
 function Scorer:zeroGradParameters() check(C.kprn_zero_grad(self.ctx)) end
 
--- host mirrors of the flat vectors (slow for the 2.85M-row table; prefer kprn.Optimizer)
-function Scorer:getParameters()
+-- Flat parameter / gradient vectors.  In Torch7 getParameters() returns tensors that ALIAS the module's storage, and
+-- MyOptimizer relies on that (optim.adam mutates `parameters` in place, MyOptimizer.lua:42,218).  The parameters of this
+-- module live in HBM, so a host tensor cannot alias them: an unmodified MyOptimizer would train a stale copy without any
+-- error.  getParameters() therefore REFUSES unless the caller states that it wants host mirrors and will push them back:
+--     local p, g = model:getParameters{mirror = true} ... model:pushParameters(p)
+-- The supported training route is kprn.Optimizer (below), whose trainBatch runs the whole step on the device.
+function Scorer:getParameters(how)
+   if not (type(how) == 'table' and how.mirror) then
+      error('nn.KPRNPathScorer:getParameters(): parameters live on the device and cannot alias a host tensor; an in-place '
+            .. 'host optimizer (MyOptimizer + optim.adam) would train a stale copy. Use kprn.Optimizer, or ask for mirrors '
+            .. 'explicitly with getParameters{mirror=true} and call pushParameters() after every host-side update.', 2)
+   end
    self._flat = self._flat or torch.FloatTensor(self.nParams)
    self._flatGrad = self._flatGrad or torch.FloatTensor(self.nParams)
    check(C.kprn_get_params(self.ctx, self._flat:data(), self.nParams))
@@ -206,7 +216,7 @@ function Scorer:getParameters()
    return self._flat, self._flatGrad
 end
 function Scorer:parameters()
-   local p, g = self:getParameters()
+   local p, g = self:getParameters{mirror = true}
    return {p}, {g}
 end
 function Scorer:pushParameters(flat)          -- after a host-side optimizer touched the mirror
@@ -231,7 +241,7 @@ function Scorer:__tostring__()
 end
 -- torch.save / torch.load of the module object (saver hook OneModel.lua:393-401): parameters travel as a FloatTensor
 function Scorer:write(file)
-   local flat = self:getParameters()
+   local flat = self:getParameters{mirror = true}
    file:writeObject({opt = self.opt, flat = flat})
 end
 function Scorer:read(file)
@@ -275,18 +285,60 @@ function Opt:__init(model, optConfig, optInfo)
    self.numEpochs = optInfo.numEpochs or 1
 end
 
--- MyOptimizer:trainBatch (MyOptimizer.lua:177-221) entirely on the device
+function Opt:_opts(loss)
+   local o = ffi.new('kprn_train_opts')
+   o.loss = loss
+   o.bpr_on_logits = self.bprOnLogits and 1 or 0
+   o.regularize, o.use_clip, o.clip_norm, o.l2 = self.regularize, self.useGradClip, self.gradClipNorm, self.l2
+   o.lr, o.beta1, o.beta2, o.eps = self.lr, self.beta1, self.beta2, self.epsilon
+   o.grad_scale = self.gradScale or 1      -- S_local / S_global when this process holds one shard of the batch
+   o.dense = self.dense and 1 or 0         -- 1: the reference's dense flow literally (dense gradient, dense optim.adam)
+   return o
+end
+
+local function denseSegments(B, P)
+   local seg = torch.IntTensor(B + 1)
+   for i = 0, B do seg[i + 1] = i * P end
+   return seg
+end
+
+-- MyOptimizer:trainBatch (MyOptimizer.lua:177-221) entirely on the device, nn.BCECriterion (OneModel.lua:300)
 function Opt:trainBatch(inputs, targets)
    local B, P = inputs:size(1), inputs:size(2)
    local ids = inputs:int():contiguous()
-   local seg = torch.IntTensor(B + 1)
-   for i = 0, B do seg[i + 1] = i * P end
+   local seg = denseSegments(B, P)
    local y = targets:float():contiguous()
    local loss = ffi.new('float[1]')
-   check(C.kprn_train_batch_bce(self.model.ctx, ids:data(), seg:data(), B * P, B, y:data(), self.pads,
-                                self.regularize, self.useGradClip, self.gradClipNorm, self.l2,
-                                self.lr, self.beta1, self.beta2, self.epsilon, loss))
+   check(C.kprn_train_step(self.model.ctx, ids:data(), seg:data(), B * P, B, y:data(), nil, nil, 0, self.pads, self:_opts(0), loss))
    return loss[0]
+end
+
+-- the same step with nn.BPRLoss (criterion/BPRLoss.lua:18-32): posSeg/negSeg are 0-based bucket indices, paired element-wise
+function Opt:trainBatchBPR(inputs, posSeg, negSeg)
+   local B, P = inputs:size(1), inputs:size(2)
+   local ids = inputs:int():contiguous()
+   local seg = denseSegments(B, P)
+   local a, b = posSeg:int():contiguous(), negSeg:int():contiguous()
+   local loss = ffi.new('float[1]')
+   check(C.kprn_train_step(self.model.ctx, ids:data(), seg:data(), B * P, B, nil, a:data(), b:data(), a:nElement(), self.pads,
+                           self:_opts(1), loss))
+   return loss[0]
+end
+
+-- multi-GPU: one Lua process per GPU.  Rank 0 writes the 128-byte NCCL id to `path`, the others read it.
+function Opt:initComm(rank, world, path)
+   local id = ffi.new('char[128]')
+   if rank == 0 then
+      check(C.kprn_comm_unique_id(id))
+      local f = assert(io.open(path .. '.tmp', 'wb')); f:write(ffi.string(id, 128)); f:close()
+      os.rename(path .. '.tmp', path)
+   else
+      local f
+      repeat f = io.open(path, 'rb') until f
+      ffi.copy(id, f:read(128), 128); f:close()
+   end
+   check(C.kprn_comm_init(self.model.ctx, rank, world, id))
+   check(C.kprn_broadcast_params(self.model.ctx, 0))
 end
 
 -- MyOptimizer:train (MyOptimizer.lua:95-172): epoch loop over a BatcherFileList

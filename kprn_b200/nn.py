@@ -85,12 +85,19 @@ class KPRNPathScorer:
         self.engine.zero_grad()
 
     # -- parameters --------------------------------------------------------------------------------
-    def getParameters(self):
-        """Flat (parameters, gradParameters) host copies in nn.Module:getParameters() order (MyOptimizer.lua:42)."""
+    def getParameters(self, mirror=False):
+        """Flat (parameters, gradParameters) in nn.Module:getParameters() order (MyOptimizer.lua:42).  Torch7 returns tensors
+        that ALIAS the module storage and MyOptimizer relies on it (optim.adam mutates them in place, MyOptimizer.lua:218); these
+        parameters live in HBM, so host arrays cannot alias them and an unmodified host optimizer would train a stale copy.
+        Like the Lua shim, the call refuses unless the caller asks for mirrors explicitly (and pushes them back with
+        setParameters); the supported training route is MyOptimizer below (the whole step on the device)."""
+        if not mirror:
+            raise RuntimeError("KPRNPathScorer.getParameters(): parameters live on the device and cannot alias a host tensor; "
+                               "use nn.MyOptimizer (device-side trainBatch) or getParameters(mirror=True) + setParameters()")
         return self.engine.get_params(), self.engine.get_grads()
 
     def parameters(self):
-        p, g = self.getParameters()
+        p, g = self.getParameters(mirror=True)
         return [p], [g]
 
     def setParameters(self, flat):
@@ -178,6 +185,14 @@ class MyOptimizer:
     def trainBatchCSR(self, ids, seg, targets):
         err = self.model.engine.train_batch_bce(ids, seg, targets, pad_rows=self.pads, regularize=bool(self.regularize),
                                                 use_clip=self.useGradClip, clip_norm=self.gradClipNorm, l2=self.l2, **self.opt)
+        self.totalError += err
+        return err
+
+    def trainBatchBPR(self, ids, seg, pos_seg, neg_seg, on_logits=False):
+        """The same step with nn.BPRLoss on (pos, neg) pairs of segments (criterion/BPRLoss.lua:18-32; BASELINE configs[3])."""
+        err = self.model.engine.train_batch_bpr(ids, seg, pos_seg, neg_seg, on_logits=on_logits, pad_rows=self.pads,
+                                                regularize=bool(self.regularize), use_clip=self.useGradClip,
+                                                clip_norm=self.gradClipNorm, l2=self.l2, **self.opt)
         self.totalError += err
         return err
 

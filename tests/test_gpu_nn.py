@@ -34,7 +34,7 @@ def test_forward_backward_like_MyOptimizer_fEval(precision):
     assert gi.size == 0                                                   # MapReduce.lua:83: no grad w.r.t. ids
     assert_rel(output, ref["scores"], what="output")
     assert abs(err - loss_ref) <= 1e-4 * loss_ref
-    _, g = model.getParameters()
+    _, g = model.getParameters(mirror=True)
     assert_rel(g, g_ref, what="gradParameters")
     # updateGradInput and accGradParameters invoked separately (MapReduce.lua:58-71), explicit df_do, idempotent
     model.zeroGradParameters()
@@ -42,7 +42,7 @@ def test_forward_backward_like_MyOptimizer_fEval(precision):
     model.updateGradInput(inputs, dsc)
     model.accGradParameters(inputs)
     model.accGradParameters(inputs)
-    assert_rel(model.getParameters()[1], g_ref, what="split backward")
+    assert_rel(model.getParameters(mirror=True)[1], g_ref, what="split backward")
 
 
 def test_scoring_loop_like_test_from_checkpoint(tmp_path):
@@ -82,7 +82,7 @@ def test_MyOptimizer_train_epochs_decrease_loss(tmp_path):
     opt = nn.MyOptimizer(model, learningRate=5e-3, entityTypePadToken=c.V_t, entityPadToken=c.V_e, relationPadToken=c.V_r, numEpochs=6)
     hist = opt.train(batcher)
     assert hist[-1] < hist[0]
-    p = model.getParameters()[0]
+    p = model.getParameters(mirror=True)[0]
     assert np.all(o.view(p, "E_e")[c.V_e - 1] == 0)           # zeroPadTokens after the step (MyOptimizer.lua:219)
 
 
@@ -140,3 +140,14 @@ def test_shipped_sample_end_to_end_hit_at_k_identical_to_oracle(tmp_path):
     # one sample, so also allow 1/n on this small sample
     tol = max(0.001, (2.0 / n1 if diff else 0.0))
     assert max(abs(a - b) for a, b in zip(h1, h2)) <= tol and max(abs(a - b) for a, b in zip(d1, d2)) <= tol
+
+
+def test_get_parameters_refuses_to_hand_out_a_stale_alias():
+    """Torch7's getParameters() aliases module storage and MyOptimizer mutates it in place (MyOptimizer.lua:42,218); a host copy
+    of device-resident parameters cannot, so the call refuses unless mirrors are asked for explicitly (same rule in the Lua shim)."""
+    from kprn_b200 import nn
+    model = nn.KPRNPathScorer(6, 8, 300, 16, 9, 8, 16, precision=0)
+    with pytest.raises(RuntimeError):
+        model.getParameters()
+    p, g = model.getParameters(mirror=True)
+    assert p.shape == g.shape
