@@ -29,9 +29,10 @@ bool tc_supported(const kprn_ctx* ctx) {
     const kprn_config& c = ctx->cfg;
     if (c.cell != KPRN_CELL_LSTM) return false;
     int KE = round_up(c.d_e, 64);
-    if (c.H > 256 || KE > 256) return false;
+    if (c.H > 512 || KE > 512) return false;      // 256 < d_e <= 512: projection in two K halves; 256 < H <= 512: per-step recurrence (tc_wide.cu)
     int noh = (int)((c.V_t * c.V_r + 63) / 64);
-    if (noh > 2 || KE / 64 + noh > MAX_NS || c.V_t + c.V_r > 160) return false;   // (type,relation) combos ride the MMA as a one-hot k-slice
+    const int KE0 = KE > 256 ? 256 : KE;
+    if (noh > 2 || KE0 / 64 + noh > MAX_NS || c.V_t + c.V_r > 160) return false;   // (type,relation) combos ride the MMA as a one-hot k-slice
     return true;
 }
 
@@ -72,7 +73,7 @@ __device__ __forceinline__ float gate_scale(int gp) {
 //   s <  KSe : Wx[:, d_t : d_t+d_e]  (entity columns of the input projection)
 //   s >= KSe : P_tr^T, the hoisted (type,relation) table, multiplied by a one-hot k-slice of the A tile
 __global__ void pack_wxe_kernel(const float* __restrict__ Wx, const float* __restrict__ Ptr, int H, int D, int d_t, int d_e,
-                                int NCH, int KSe, int NS, int ncombo, int G4, bf16* __restrict__ out) {
+                                int NCH, int KSe, int NS, int ncombo, int G4, int k_off, bf16* __restrict__ out) {
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t total = (int64_t)NCH * NS * B_SLAB_ELEMS;
     if (idx >= total) return;
@@ -85,7 +86,7 @@ __global__ void pack_wxe_kernel(const float* __restrict__ Wx, const float* __res
     int row = perm_to_row(gp, H, u);
     float v;
     if (s < KSe) {
-        int k = s * 64 + kc * 8 + e;
+        int k = k_off + s * 64 + kc * 8 + e;
         v = (u < H && k < d_e) ? Wx[(int64_t)row * D + d_t + k] : 0.f;
     } else {
         int combo = (s - KSe) * 64 + kc * 8 + e;
@@ -161,6 +162,8 @@ struct ProjArgs {
     int KE, KSe, NOH, NS, NCH, G4; int64_t num_tiles; int passes;   // passes: 3 = bf16x3, 1 = hi*hi only
     unsigned long long* dbg;   // optional wait-cycle counters (KPRN_TC_DEBUG=1): see tc_debug_dump
     const int32_t* n_dev;      // when set: the row count lives on the device (distinct step inputs, see dedup below); T is 1
+    int k_base;                // first entity column of this launch (d_e > 256 runs as two launches over column halves)
+    int accumulate;            // the epilogue adds to XW (second half) instead of storing
 };
 
 // the projection of a deduplicated step list learns its size on the device (no host round trip): N = *n_dev rows, T = 1
@@ -336,8 +339,8 @@ proj3_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ 
                     if (lane == 0) ptx::mbar_arrive_expect_tx(BAR(B_ALAND + s), 2 * TILE_M * 128);
                     __syncwarp();
                     const uint32_t off = s * 16384 + lane * 512;
-                    ptx::tma_gather4(dHi + off, &tm_hi, s * 64, eid[0], eid[1], eid[2], eid[3], BAR(B_ALAND + s));
-                    ptx::tma_gather4(dLo + off, &tm_lo, s * 64, eid[0], eid[1], eid[2], eid[3], BAR(B_ALAND + s));
+                    ptx::tma_gather4(dHi + off, &tm_hi, a.k_base + s * 64, eid[0], eid[1], eid[2], eid[3], BAR(B_ALAND + s));
+                    ptx::tma_gather4(dLo + off, &tm_lo, a.k_base + s * 64, eid[0], eid[1], eid[2], eid[3], BAR(B_ALAND + s));
                 } else {
                     const int o = s - a.KSe;
 #pragma unroll
@@ -390,7 +393,15 @@ proj3_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ 
                 ptx::tmem_ld32(tbase + blk * 32, v);
                 ptx::tc_wait_ld();
 #pragma unroll
-                for (int i = 0; i < 4; ++i) ptx::stg256(xw + (int64_t)(blk * 4 + i) * TILE_M * 8, v + 8 * i);     // one 32-byte sector per thread
+                for (int i = 0; i < 4; ++i) {
+                    float* dstp = xw + (int64_t)(blk * 4 + i) * TILE_M * 8;
+                    if (a.accumulate) {
+                        const float4 o0 = *reinterpret_cast<const float4*>(dstp), o1 = *reinterpret_cast<const float4*>(dstp + 4);
+                        v[8 * i] += o0.x; v[8 * i + 1] += o0.y; v[8 * i + 2] += o0.z; v[8 * i + 3] += o0.w;
+                        v[8 * i + 4] += o1.x; v[8 * i + 5] += o1.y; v[8 * i + 6] += o1.z; v[8 * i + 7] += o1.w;
+                    }
+                    ptx::stg256(dstp, v + 8 * i);     // one 32-byte sector per thread
+                }
             }
             ptx::tc_fence_before();
             __syncwarp();
@@ -1035,14 +1046,15 @@ static int tc_pack(kprn_ctx* ctx) {
     const Layout& l = ctx->lay;
     if (s->packed_version == ctx->params_version && s->packed_small == ctx->small_version) return KPRN_OK;
     const bool full = s->packed_version != ctx->params_version;
-    if (!s->E_hi || !s->E_lo || !s->WxE || !s->Wh || !s->Ptr) {
+    if (!s->E_hi || !s->E_lo || !s->WxE || !s->Wh || !s->Ptr || !s->WxE2) {
         // all or nothing: a failed allocation must not leave a half-built state that the next call takes for complete
-        void** ptrs[5] = {(void**)&s->E_hi, (void**)&s->E_lo, (void**)&s->WxE, (void**)&s->Wh, (void**)&s->Ptr};
+        void** ptrs[6] = {(void**)&s->E_hi, (void**)&s->E_lo, (void**)&s->WxE, (void**)&s->Wh, (void**)&s->Ptr, (void**)&s->WxE2};
         for (void** pp : ptrs) if (*pp) { cudaFree(*pp); *pp = nullptr; }
         const size_t eb = sizeof(bf16) * (size_t)c.V_e * s->KE;
-        const size_t sizes[5] = {eb, eb, sizeof(bf16) * (size_t)s->NCH * s->NS * 2 * B_SLAB_ELEMS,
-                                 sizeof(bf16) * (size_t)s->NCH * s->KSh * 2 * B_SLAB_ELEMS, sizeof(float) * (size_t)c.V_t * c.V_r * s->G4};
-        for (int i = 0; i < 5; ++i) {
+        const size_t sizes[6] = {eb, eb, sizeof(bf16) * (size_t)s->NCH * s->NS * 2 * B_SLAB_ELEMS,
+                                 sizeof(bf16) * (size_t)s->NCH * s->KSh * 2 * B_SLAB_ELEMS, sizeof(float) * (size_t)c.V_t * c.V_r * s->G4,
+                                 sizeof(bf16) * (size_t)s->NCH * (s->KSe1 > 0 ? s->KSe1 : 1) * 2 * B_SLAB_ELEMS};
+        for (int i = 0; i < 6; ++i) {
             cudaError_t e = cudaMalloc(ptrs[i], sizes[i]);
             if (e != cudaSuccess) {
                 for (void** pp : ptrs) if (*pp) { cudaFree(*pp); *pp = nullptr; }
@@ -1056,15 +1068,25 @@ static int tc_pack(kprn_ctx* ctx) {
         split_entity_kernel<<<(unsigned)cdiv(ne, 256), 256, 0, ctx->stream>>>(ctx->d_params + l.E_e, c.V_e, c.d_e, s->KE, s->E_hi, s->E_lo);
         KPRN_LAUNCH_CHECK(ctx);
     }
-    int64_t nh = (int64_t)s->NCH * s->KSh * B_SLAB_ELEMS;
-    pack_wh_kernel<<<(unsigned)cdiv(nh, 256), 256, 0, ctx->stream>>>(ctx->d_params + l.Wh, c.H, s->NCH, s->KSh, s->recur_pairs ? 1 : 0, s->Wh);
-    KPRN_LAUNCH_CHECK(ctx);
+    if (s->Hp > 256) {      // per-step recurrence (tc_wide.cu): 256-column blocks x 64-wide k slices; same byte count as the slab form
+        KPRN_TRY(pack_wh_wide(ctx, ctx->d_params + l.Wh, c.H, s->Hp, s->Wh));
+    } else {
+        int64_t nh = (int64_t)s->NCH * s->KSh * B_SLAB_ELEMS;
+        pack_wh_kernel<<<(unsigned)cdiv(nh, 256), 256, 0, ctx->stream>>>(ctx->d_params + l.Wh, c.H, s->NCH, s->KSh, s->recur_pairs ? 1 : 0, s->Wh);
+        KPRN_LAUNCH_CHECK(ctx);
+    }
     ptr_table_kernel<<<(unsigned)s->G4, 128, 0, ctx->stream>>>(ctx->d_params, l, c.d_t, c.d_e, c.d_r, c.H, (int)c.V_t, (int)c.V_r, s->G4, s->Ptr);
     KPRN_LAUNCH_CHECK(ctx);
     int64_t nw = (int64_t)s->NCH * s->NS * B_SLAB_ELEMS;
     pack_wxe_kernel<<<(unsigned)cdiv(nw, 256), 256, 0, ctx->stream>>>(ctx->d_params + l.Wx, s->Ptr, c.H, l.D, c.d_t, c.d_e, s->NCH,
-                                                                      s->KSe, s->NS, (int)(c.V_t * c.V_r), s->G4, s->WxE);
+                                                                      s->KSe, s->NS, (int)(c.V_t * c.V_r), s->G4, 0, s->WxE);
     KPRN_LAUNCH_CHECK(ctx);
+    if (s->KSe1 > 0) {      // entity columns 256.. : a second projection launch accumulates them into XW
+        int64_t nw1 = (int64_t)s->NCH * s->KSe1 * B_SLAB_ELEMS;
+        pack_wxe_kernel<<<(unsigned)cdiv(nw1, 256), 256, 0, ctx->stream>>>(ctx->d_params + l.Wx, s->Ptr, c.H, l.D, c.d_t, c.d_e, s->NCH,
+                                                                           s->KSe1, s->KSe1, 0, s->G4, 256, s->WxE2);
+        KPRN_LAUNCH_CHECK(ctx);
+    }
     s->packed_version = ctx->params_version;
     s->packed_small = ctx->small_version;
     return KPRN_OK;
@@ -1106,7 +1128,8 @@ int tc_forward(kprn_ctx* ctx, const int32_t* d_ids, const int32_t* d_seg, int64_
         ctx->tc = new TcState();
         TcState* s = ctx->tc;
         s->Hp = pad_hidden(c.H); s->KE = round_up(c.d_e, 64);
-        s->NCH = s->Hp / 32; s->KSh = s->Hp / 64; s->KSe = s->KE / 64; s->G4 = 4 * s->Hp;
+        s->NCH = s->Hp / 32; s->KSh = s->Hp / 64; s->G4 = 4 * s->Hp;
+        s->KE0 = s->KE > 256 ? 256 : s->KE; s->KSe = s->KE0 / 64; s->KSe1 = (s->KE - s->KE0) / 64;      // entity columns in two K halves when d_e > 256
         s->NOH = (int)((c.V_t * c.V_r + 63) / 64); s->NS = s->KSe + s->NOH;
         cudaDeviceProp prop;
         KPRN_CUDA(cudaGetDeviceProperties(&prop, ctx->device));
@@ -1122,7 +1145,7 @@ int tc_forward(kprn_ctx* ctx, const int32_t* d_ids, const int32_t* d_seg, int64_
     TcState* s = ctx->tc;
     s->dedup = dedup_enabled(ctx);
     if (!s->attrs_set) {
-        KPRN_CUDA(cudaFuncSetAttribute(proj3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)proj_smem(s->KE, s->NOH)));
+        KPRN_CUDA(cudaFuncSetAttribute(proj3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)proj_smem(s->KE0, s->NOH)));
         s->attrs_set = true;
     }
     KPRN_TRY(tc_pack(ctx));
@@ -1141,8 +1164,8 @@ int tc_forward(kprn_ctx* ctx, const int32_t* d_ids, const int32_t* d_seg, int64_
         ProjArgs a;
         a.ids = d_ids; a.N = N; a.T = c.T; a.V_e = c.V_e; a.V_t = (int)c.V_t; a.V_r = (int)c.V_r;
         a.E_hi = s->E_hi; a.E_lo = s->E_lo; a.W = s->WxE; a.XW = s->xw.as<float>();
-        a.KE = s->KE; a.KSe = s->KSe; a.NOH = s->NOH; a.NS = s->NS; a.NCH = s->NCH; a.G4 = s->G4; a.num_tiles = ptiles * c.T; a.passes = passes; a.dbg = dbg;
-        a.n_dev = nullptr;
+        a.KE = s->KE0; a.KSe = s->KSe; a.NOH = s->NOH; a.NS = s->NS; a.NCH = s->NCH; a.G4 = s->G4; a.num_tiles = ptiles * c.T; a.passes = passes; a.dbg = dbg;
+        a.n_dev = nullptr; a.k_base = 0; a.accumulate = 0;
         cudaEvent_t e0;
         KPRN_TRY(prof_begin(ctx, &e0));
         const int64_t n_steps = N * c.T, n_order = ptiles * c.T * TILE_M;       // n_order: read-order indices incl. the ragged tail
@@ -1155,9 +1178,15 @@ int tc_forward(kprn_ctx* ctx, const int32_t* d_ids, const int32_t* d_seg, int64_
         {   // a single (or odd last) tile is computed by both CTAs of a pair: identical values, identical stores
             int64_t pairs = (a.num_tiles + 1) / 2;
             int64_t g2 = 2 * (pairs < s->num_sms / 2 ? pairs : s->num_sms / 2);
-            proj3_kernel<<<(unsigned)g2, NUM_THREADS, proj_smem(s->KE, s->NOH), ctx->stream>>>(s->tm_hi, s->tm_lo, a);
+            proj3_kernel<<<(unsigned)g2, NUM_THREADS, proj_smem(s->KE0, s->NOH), ctx->stream>>>(s->tm_hi, s->tm_lo, a);
+            KPRN_LAUNCH_CHECK(ctx);
+            if (s->KSe1 > 0) {      // entity columns 256..: same kernel, no one-hot slice, accumulating epilogue
+                ProjArgs b = a;
+                b.KE = s->KE - s->KE0; b.KSe = s->KSe1; b.NOH = 0; b.NS = s->KSe1; b.W = s->WxE2; b.k_base = 256; b.accumulate = 1;
+                proj3_kernel<<<(unsigned)g2, NUM_THREADS, proj_smem(s->KE0, s->NOH), ctx->stream>>>(s->tm_hi, s->tm_lo, b);
+                KPRN_LAUNCH_CHECK(ctx);
+            }
         }
-        KPRN_LAUNCH_CHECK(ctx);
         KPRN_TRY(prof_end(ctx, e0, 1));
     }
     {
@@ -1185,7 +1214,17 @@ int tc_forward(kprn_ctx* ctx, const int32_t* d_ids, const int32_t* d_seg, int64_
 
         cudaEvent_t e0;
         KPRN_TRY(prof_begin(ctx, &e0));
-        if (tc_train) {           // CTA pairs, epilogue also writes the activation caches of the backward
+        if (s->Hp > 256) {        // 256 < H <= 512: one launch per step, state through HBM (tc_wide.cu)
+            const size_t hbytes = (size_t)ptiles * 2 * TILE_M * s->Hp * 2;
+            KPRN_TRY(ensure(s->wide_h0, hbytes));
+            KPRN_TRY(ensure(s->wide_h1, hbytes));
+            KPRN_TRY(ensure(s->wide_c, sizeof(float) * (size_t)ptiles * s->Hp * TILE_M));
+            RecurWide w;
+            w.XW = a.XW; w.W = s->Wh; w.h0 = s->wide_h0.as<bf16>(); w.h1 = s->wide_h1.as<bf16>(); w.c = s->wide_c.as<float>();
+            w.N = N; w.T = c.T; w.H = c.H; w.Hp = s->Hp; w.num_sms = s->num_sms; w.pos = a.pos; w.slot_of = a.slot_of;
+            w.wo = a.wo; w.part4 = a.part4; w.npad = a.npad; w.hT = a.part4 ? nullptr : a.hT;
+            KPRN_TRY(wide_recurrence(ctx, w));
+        } else if (tc_train) {           // CTA pairs, epilogue also writes the activation caches of the backward
             grid_r = 2 * ((ptiles + 1) / 2 < s->num_sms / 2 ? (ptiles + 1) / 2 : s->num_sms / 2);
             if (s->Hp == 64) KPRN_CUDA((launch_recur<64, true, true>(a, grid_r, ctx->stream)));
             else if (s->Hp == 128) KPRN_CUDA((launch_recur<128, true, true>(a, grid_r, ctx->stream)));
@@ -1238,7 +1277,8 @@ void tc_destroy(kprn_ctx* ctx) {
     if (s->WxE) cudaFree(s->WxE);
     if (s->Wh) cudaFree(s->Wh);
     if (s->Ptr) cudaFree(s->Ptr);
-    for (DBuf* b : {&s->xw, &s->hT, &s->hscratch, &s->dbg, &s->part4})
+    if (s->WxE2) cudaFree(s->WxE2);
+    for (DBuf* b : {&s->xw, &s->hT, &s->hscratch, &s->dbg, &s->part4, &s->wide_h0, &s->wide_h1, &s->wide_c})
         if (b->p) { cudaFree(b->p); b->p = nullptr; b->cap = 0; }
     dedup_free(s->dd);
     delete s;

@@ -38,6 +38,9 @@ struct TcState {
     int Hp = 0, KE = 0, NCH = 0, KSh = 0, KSe = 0, G4 = 0, NOH = 0, NS = 0;
     bf16* E_hi = nullptr; bf16* E_lo = nullptr;
     bf16* WxE = nullptr; bf16* Wh = nullptr;
+    bf16* WxE2 = nullptr;              // projection weights of entity columns 256.. (d_e > 256)
+    int KE0 = 0, KSe1 = 0;             // entity columns / k-slices of the first and second projection launch
+    DBuf wide_h0, wide_h1, wide_c;     // per-step recurrence (H > 256): ping-pong h (operand layout) and c
     float* Ptr = nullptr;
     DBuf xw, hT, hscratch, dbg, part4;
     DedupBufs dd;              // step-input deduplication
@@ -53,7 +56,7 @@ struct TcState {
 
 static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 // hidden size padded to an instantiated recur_kernel<HP> (padded units have zero weights and stay exactly 0)
-static inline int pad_hidden(int H) { return H <= 64 ? 64 : (H <= 128 ? 128 : 256); }
+static inline int pad_hidden(int H) { return H <= 64 ? 64 : (H <= 128 ? 128 : (H <= 256 ? 256 : 512)); }
 
 // permuted gate column g' = chunk*128 + gate*32 + uu  <->  reference row gate*H + chunk*32 + uu
 __host__ __device__ __forceinline__ int perm_to_row(int gp, int H, int& u) {
@@ -65,6 +68,14 @@ __device__ __forceinline__ void split_bf16(float v, bf16& hi, bf16& lo) {
     hi = __float2bfloat16_rn(v);
     lo = __float2bfloat16_rn(v - __bfloat162float(hi));
 }
+
+// wide hidden sizes (tc_wide.cu): one launch per step, state through HBM
+struct RecurWide {
+    const float* XW; const bf16* W; bf16* h0; bf16* h1; float* c; int64_t N; int T; int H; int Hp; int num_sms;
+    const uint32_t* pos; const uint32_t* slot_of; const float* wo; float* part4; int64_t npad; float* hT;
+};
+int wide_recurrence(kprn_ctx* ctx, const RecurWide& w);
+int pack_wh_wide(kprn_ctx* ctx, const float* Wh, int H, int Hp, bf16* out);
 
 // training side (tc_train.cu)
 int tc_train_pack(kprn_ctx* ctx);

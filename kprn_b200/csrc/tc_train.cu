@@ -681,71 +681,120 @@ struct EgArgs {
     int32_t* flags;                           // [chunk][4]: head key (-1 none), head continues into the next chunk, tail key (-1 none), unused
 };
 
+// NV4 = d_e / 128: a lane owns the float4 at columns [4 lane, +4) of every 128-column block of a row (coalesced 512-byte warp loads)
+template <int NV4>
 __global__ void __launch_bounds__(256) eg_reduce_kernel(EgArgs a) {
     const int lane = threadIdx.x & 31;
     const int64_t chunk = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (chunk >= a.n_chunks) return;
     const int64_t e0 = chunk * EG_CHUNK, e1 = (e0 + EG_CHUNK < a.n) ? e0 + EG_CHUNK : a.n;
+    const int cnt = (int)(e1 - e0);
     const uint32_t INVALID = (uint32_t)a.n;
     const uint32_t prev_key = e0 > 0 ? a.keys[e0 - 1] : INVALID;
     const uint32_t next_key = e1 < a.n ? a.keys[e1] : INVALID;
+    // the chunk's keys and row indices, two per lane
+    const uint32_t k0 = lane < cnt ? a.keys[e0 + lane] : INVALID, k1 = lane + 32 < cnt ? a.keys[e0 + 32 + lane] : INVALID;
+    const uint32_t v0 = lane < cnt ? a.vals[e0 + lane] : 0u, v1 = lane + 32 < cnt ? a.vals[e0 + 32 + lane] : 0u;
     int32_t head_key = -1, head_cont = 0, tail_key = -1;
-    constexpr int MAXV = 8;                    // d_e <= 256: 8 floats per lane
-    float acc[MAXV];
-    int64_t e = e0;
-    while (e < e1) {
-        const uint32_t key = a.keys[e];
-        if (key == INVALID) break;             // the rest of the array is padding
+    float4 acc[NV4];
 #pragma unroll
-        for (int i = 0; i < MAXV; ++i) acc[i] = 0.f;
-        const bool starts_here = !(e == e0 && prev_key == key);
-        int64_t f = e;
-        while (f < e1 && a.keys[f] == key) {
-            const float* src = a.dX + (size_t)a.vals[f] * a.ldx;
+    for (int i = 0; i < NV4; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint32_t cur = INVALID;
+    bool cur_starts = false;
+    auto flush = [&](bool ends_here) {
+        if (cur == INVALID) return;
+        float* dst;
+        if (cur_starts && ends_here) {
+            dst = a.target + (size_t)(a.rows ? a.rows[cur] - 1 : cur) * a.d_e;
 #pragma unroll
-            for (int i = 0; i < MAXV; ++i) { const int k = i * 32 + lane; if (k < a.d_e) acc[i] += src[k]; }
-            ++f;
-        }
-        const bool ends_here = !(f == e1 && next_key == key);
-        if (starts_here && ends_here) {
-            float* dst = a.target + (size_t)(a.rows ? a.rows[key] - 1 : key) * a.d_e;
-#pragma unroll
-            for (int i = 0; i < MAXV; ++i) { const int k = i * 32 + lane; if (k < a.d_e) dst[k] += acc[i]; }
+            for (int i = 0; i < NV4; ++i) {
+                float4 o = *reinterpret_cast<float4*>(dst + i * 128 + lane * 4);
+                o.x += acc[i].x; o.y += acc[i].y; o.z += acc[i].z; o.w += acc[i].w;
+                *reinterpret_cast<float4*>(dst + i * 128 + lane * 4) = o;
+            }
         } else {
-            const int which = starts_here ? 1 : 0;
-            float* dst = a.part + ((size_t)chunk * 2 + which) * a.d_e;
+            const int which = cur_starts ? 1 : 0;
+            dst = a.part + ((size_t)chunk * 2 + which) * a.d_e;
 #pragma unroll
-            for (int i = 0; i < MAXV; ++i) { const int k = i * 32 + lane; if (k < a.d_e) dst[k] = acc[i]; }
-            if (which) tail_key = (int32_t)key;
-            else { head_key = (int32_t)key; head_cont = ends_here ? 0 : 1; }
+            for (int i = 0; i < NV4; ++i) *reinterpret_cast<float4*>(dst + i * 128 + lane * 4) = acc[i];
+            if (which) tail_key = (int32_t)cur;
+            else { head_key = (int32_t)cur; head_cont = ends_here ? 0 : 1; }
         }
-        e = f;
+#pragma unroll
+        for (int i = 0; i < NV4; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    for (int base = 0; base < cnt; base += 4) {
+        uint32_t key[4];
+        float4 row[4][NV4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {                   // four rows in flight
+            const int i = base + u;
+            key[u] = __shfl_sync(0xffffffffu, i < 32 ? k0 : k1, i & 31);
+            const uint32_t val = __shfl_sync(0xffffffffu, i < 32 ? v0 : v1, i & 31);
+            if (i >= cnt) key[u] = INVALID;
+            if (key[u] != INVALID) {
+                const float* src = a.dX + (size_t)val * a.ldx;
+#pragma unroll
+                for (int q = 0; q < NV4; ++q) row[u][q] = *reinterpret_cast<const float4*>(src + q * 128 + lane * 4);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (key[u] == INVALID) continue;            // sorted: padding comes last
+            if (key[u] != cur) {
+                flush(true);
+                cur = key[u];
+                cur_starts = !(base + u == 0 && prev_key == cur);
+            }
+#pragma unroll
+            for (int q = 0; q < NV4; ++q) { acc[q].x += row[u][q].x; acc[q].y += row[u][q].y; acc[q].z += row[u][q].z; acc[q].w += row[u][q].w; }
+        }
+    }
+    // the last run ends here unless the next chunk starts with the same key (a run ending exactly at the array's valid end ends here)
+    {
+        const uint32_t last_key = __shfl_sync(0xffffffffu, (cnt - 1) < 32 ? k0 : k1, (cnt - 1) & 31);
+        flush(!(cur == last_key && next_key == cur));
     }
     if (lane == 0) { a.flags[chunk * 4] = head_key; a.flags[chunk * 4 + 1] = head_cont; a.flags[chunk * 4 + 2] = tail_key; }
 }
 
-// one warp per chunk that OWNS a boundary-crossing run (the chunk where the run starts): tail + following heads, in chunk order
-__global__ void __launch_bounds__(256) eg_fixup_kernel(EgArgs a) {
-    const int lane = threadIdx.x & 31;
-    const int64_t chunk = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (chunk >= a.n_chunks) return;
+// one BLOCK per chunk that owns a boundary-crossing run (the chunk where the run starts): its tail partial plus the head
+// partials of the following chunks (contiguous, the keys are sorted).  Warp w takes chunks start+1+w, +16, ... ; the warps'
+// partial sums are combined in warp order: deterministic.
+template <int NV4>
+__global__ void __launch_bounds__(512) eg_fixup_kernel(EgArgs a) {
+    __shared__ float4 red[16][NV4][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t chunk = blockIdx.x;
     const int32_t key = a.flags[chunk * 4 + 2];
     if (key < 0) return;
-    constexpr int MAXV = 8;
-    float acc[MAXV];
-    const float* src = a.part + ((size_t)chunk * 2 + 1) * a.d_e;
+    float4 acc[NV4];
 #pragma unroll
-    for (int i = 0; i < MAXV; ++i) { const int k = i * 32 + lane; acc[i] = k < a.d_e ? src[k] : 0.f; }
-    for (int64_t j = chunk + 1; j < a.n_chunks; ++j) {
+    for (int i = 0; i < NV4; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t j = chunk + 1 + w; j < a.n_chunks; j += 16) {
         if (a.flags[j * 4] != key) break;
         const float* s2 = a.part + ((size_t)j * 2) * a.d_e;
 #pragma unroll
-        for (int i = 0; i < MAXV; ++i) { const int k = i * 32 + lane; if (k < a.d_e) acc[i] += s2[k]; }
-        if (!a.flags[j * 4 + 1]) break;
+        for (int q = 0; q < NV4; ++q) {
+            const float4 v = *reinterpret_cast<const float4*>(s2 + q * 128 + lane * 4);
+            acc[q].x += v.x; acc[q].y += v.y; acc[q].z += v.z; acc[q].w += v.w;
+        }
     }
-    float* dst = a.target + (size_t)(a.rows ? a.rows[key] - 1 : key) * a.d_e;
 #pragma unroll
-    for (int i = 0; i < MAXV; ++i) { const int k = i * 32 + lane; if (k < a.d_e) dst[k] += acc[i]; }
+    for (int q = 0; q < NV4; ++q) red[w][q][lane] = acc[q];
+    __syncthreads();
+    if (w == 0) {
+        const float* t0 = a.part + ((size_t)chunk * 2 + 1) * a.d_e;
+        float* dst = a.target + (size_t)(a.rows ? a.rows[key] - 1 : key) * a.d_e;
+#pragma unroll
+        for (int q = 0; q < NV4; ++q) {
+            float4 t = *reinterpret_cast<const float4*>(t0 + q * 128 + lane * 4);
+            for (int ww = 0; ww < 16; ++ww) { const float4 v = red[ww][q][lane]; t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w; }
+            float4 o = *reinterpret_cast<float4*>(dst + q * 128 + lane * 4);
+            o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w;
+            *reinterpret_cast<float4*>(dst + q * 128 + lane * 4) = o;
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -759,9 +808,10 @@ static TcTrain* tt_get(kprn_ctx* ctx) {
 
 bool tc_train_supported(const kprn_ctx* ctx) {
     const kprn_config& c = ctx->cfg;
-    if (!tc_supported(ctx) || c.precision != KPRN_PREC_TC_ALL || c.head_layers != 1) return false;
+    if (!tc_supported(ctx) || c.precision != KPRN_PREC_TC_ALL || c.head_layers != 1 || c.H > 256) return false;
     const int KE = round_up(c.d_e, 64);
-    if (KE != 128 && KE != 256) return false;            // the entity operand of wgrad is staged in 64-column swizzled panels per CTA
+    if (c.d_e != 128 && c.d_e != 256) return false;      // wgrad stages the entity operand in 64-column swizzled panels per CTA; the
+                                                         // segment reduce moves rows as float4 per lane per 128 columns
     if (c.V_t * c.V_r > 64) return false;                // one one-hot slice
     { const char* d = getenv("KPRN_TC_TRAIN"); if (d && d[0] == '0') return false; }
     return true;
@@ -891,9 +941,15 @@ int tc_backward(kprn_ctx* ctx, float scale) {
         KPRN_TRY(ensure(tt->eg_part, sizeof(float) * (size_t)ea.n_chunks * 2 * c.d_e));
         KPRN_TRY(ensure(tt->eg_flags, sizeof(int32_t) * (size_t)ea.n_chunks * 4));
         ea.part = tt->eg_part.as<float>(); ea.flags = tt->eg_flags.as<int32_t>();
-        eg_reduce_kernel<<<(unsigned)cdiv(ea.n_chunks, 8), 256, 0, ctx->stream>>>(ea);
-        KPRN_LAUNCH_CHECK(ctx);
-        eg_fixup_kernel<<<(unsigned)cdiv(ea.n_chunks, 8), 256, 0, ctx->stream>>>(ea);
+        if (c.d_e == 256) {
+            eg_reduce_kernel<2><<<(unsigned)cdiv(ea.n_chunks, 8), 256, 0, ctx->stream>>>(ea);
+            KPRN_LAUNCH_CHECK(ctx);
+            eg_fixup_kernel<2><<<(unsigned)ea.n_chunks, 512, 0, ctx->stream>>>(ea);
+        } else {        // d_e = 128 (tc_train_supported admits KE of 128 or 256 with d_e a multiple of 128)
+            eg_reduce_kernel<1><<<(unsigned)cdiv(ea.n_chunks, 8), 256, 0, ctx->stream>>>(ea);
+            KPRN_LAUNCH_CHECK(ctx);
+            eg_fixup_kernel<1><<<(unsigned)ea.n_chunks, 512, 0, ctx->stream>>>(ea);
+        }
         KPRN_LAUNCH_CHECK(ctx);
     }
     // ---- weight gradients ----

@@ -80,8 +80,10 @@ struct RowsArgs {
 };
 
 // one WARP per slot (grid-stride over slots): catch the row up, optionally apply this step's gradient, refresh the packed
-// copies.  A row is a few hundred floats, so a warp streams it with a handful of independent 128-bit loads per array, and
-// thousands of rows are in flight per SM-set; rows with nothing to replay are skipped by the catch-up pass before any load.
+// copies.  NV4 > 0: d_e = 128 NV4 -- a lane owns one float4 per 128 columns of x, m, v (and of the gradient): all loads of a
+// row are issued before any arithmetic; NV4 = 0: any width, scalar.  Rows with nothing to replay are skipped by the catch-up
+// pass before any load.
+template <int NV4>
 __global__ void __launch_bounds__(256) adam_rows_kernel(RowsArgs a) {
     const int K = *a.count;
     const int lane = threadIdx.x & 31;
@@ -96,26 +98,74 @@ __global__ void __launch_bounds__(256) adam_rows_kernel(RowsArgs a) {
             __syncwarp();
             continue;
         }
-        for (int k = lane; k < a.d_e; k += 32) {
-            const int64_t i = row * a.d_e + k;
-            float x = a.x[i], m = a.m[i], v = a.v[i];
-            if (may_have_state) adam_replay(x, m, v, t0, a.t_now - 1, a.steps, a.b1, a.b2, a.eps);
-            if (a.apply) {
-                float g;
-                if (a.recv_g) {
-                    g = 0.f;
-                    for (int r = 0; r < a.world; ++r) {           // fixed rank order: identical sums on every rank
-                        const int32_t c = a.contrib[(int64_t)slot * a.world + r];
-                        if (c >= 0) g += a.recv_g[((int64_t)r * a.maxK + c) * a.d_e + k];
-                    }
-                } else {
-                    g = a.g[(int64_t)slot * a.g_stride + k];
-                }
-                if (a.gscale) g *= gs;
-                adam_elem(x, m, v, g, a.steps[a.t_now], a.b1, a.b2, a.eps);
+        if (NV4 > 0) {
+            constexpr int NV = NV4 > 0 ? NV4 : 1;
+            float4 x[NV], m[NV], v[NV], g[NV];
+            float* px = a.x + row * a.d_e; float* pm = a.m + row * a.d_e; float* pv = a.v + row * a.d_e;
+#pragma unroll
+            for (int q = 0; q < NV; ++q) {
+                x[q] = *reinterpret_cast<const float4*>(px + q * 128 + lane * 4);
+                m[q] = *reinterpret_cast<const float4*>(pm + q * 128 + lane * 4);
+                v[q] = *reinterpret_cast<const float4*>(pv + q * 128 + lane * 4);
             }
-            a.x[i] = x; a.m[i] = m; a.v[i] = v;
-            if (a.E_hi) split_store(x, a.E_hi, a.E_lo, row * a.KE + k);
+            if (a.apply) {
+#pragma unroll
+                for (int q = 0; q < NV; ++q) {
+                    if (a.recv_g) {
+                        g[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        for (int r = 0; r < a.world; ++r) {       // fixed rank order: identical sums on every rank
+                            const int32_t c = a.contrib[(int64_t)slot * a.world + r];
+                            if (c >= 0) {
+                                const float4 t = *reinterpret_cast<const float4*>(a.recv_g + ((int64_t)r * a.maxK + c) * a.d_e + q * 128 + lane * 4);
+                                g[q].x += t.x; g[q].y += t.y; g[q].z += t.z; g[q].w += t.w;
+                            }
+                        }
+                    } else {
+                        g[q] = *reinterpret_cast<const float4*>(a.g + (int64_t)slot * a.g_stride + q * 128 + lane * 4);
+                    }
+                    if (a.gscale) { g[q].x *= gs; g[q].y *= gs; g[q].z *= gs; g[q].w *= gs; }
+                }
+            }
+            const float step = a.apply ? a.steps[a.t_now] : 0.f;
+#pragma unroll
+            for (int q = 0; q < NV; ++q) {
+                float* xs = reinterpret_cast<float*>(&x[q]); float* ms = reinterpret_cast<float*>(&m[q]); float* vs = reinterpret_cast<float*>(&v[q]);
+                const float* gq = reinterpret_cast<const float*>(&g[q]);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    if (may_have_state) adam_replay(xs[e], ms[e], vs[e], t0, a.t_now - 1, a.steps, a.b1, a.b2, a.eps);
+                    if (a.apply) adam_elem(xs[e], ms[e], vs[e], gq[e], step, a.b1, a.b2, a.eps);
+                }
+                *reinterpret_cast<float4*>(px + q * 128 + lane * 4) = x[q];
+                *reinterpret_cast<float4*>(pm + q * 128 + lane * 4) = m[q];
+                *reinterpret_cast<float4*>(pv + q * 128 + lane * 4) = v[q];
+                if (a.E_hi) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) split_store(xs[e], a.E_hi, a.E_lo, row * a.KE + q * 128 + lane * 4 + e);
+                }
+            }
+        } else {
+            for (int k = lane; k < a.d_e; k += 32) {
+                const int64_t i = row * a.d_e + k;
+                float x = a.x[i], m = a.m[i], v = a.v[i];
+                if (may_have_state) adam_replay(x, m, v, t0, a.t_now - 1, a.steps, a.b1, a.b2, a.eps);
+                if (a.apply) {
+                    float g;
+                    if (a.recv_g) {
+                        g = 0.f;
+                        for (int r = 0; r < a.world; ++r) {
+                            const int32_t c = a.contrib[(int64_t)slot * a.world + r];
+                            if (c >= 0) g += a.recv_g[((int64_t)r * a.maxK + c) * a.d_e + k];
+                        }
+                    } else {
+                        g = a.g[(int64_t)slot * a.g_stride + k];
+                    }
+                    if (a.gscale) g *= gs;
+                    adam_elem(x, m, v, g, a.steps[a.t_now], a.b1, a.b2, a.eps);
+                }
+                a.x[i] = x; a.m[i] = m; a.v[i] = v;
+                if (a.E_hi) split_store(x, a.E_hi, a.E_lo, row * a.KE + k);
+            }
         }
         __syncwarp();
         if (lane == 0) a.last_t[row] = (int32_t)(a.apply ? a.t_now : a.t_now - 1);
@@ -376,7 +426,9 @@ static int rows_launch(kprn_ctx* ctx, TrainState* tr, const int32_t* rows, const
     a.E_hi = nullptr; a.E_lo = nullptr; a.KE = 0;
     packed_entity(ctx, &a.E_hi, &a.E_lo, &a.KE);
     int64_t grid = cdiv(grid_hint, 8) < 148 * 8 ? (grid_hint < 1 ? 1 : cdiv(grid_hint, 8)) : 148 * 8;      // 8 warps per block, a warp per row
-    adam_rows_kernel<<<(unsigned)grid, 256, 0, ctx->stream>>>(a);
+    if (c.d_e == 256) adam_rows_kernel<2><<<(unsigned)grid, 256, 0, ctx->stream>>>(a);
+    else if (c.d_e == 128) adam_rows_kernel<1><<<(unsigned)grid, 256, 0, ctx->stream>>>(a);
+    else adam_rows_kernel<0><<<(unsigned)grid, 256, 0, ctx->stream>>>(a);
     KPRN_LAUNCH_CHECK(ctx);
     return KPRN_OK;
 }
