@@ -383,6 +383,7 @@ proj3_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ 
             const int np = (int)(au % NP);
             const int buf = au & 1;
             const int64_t m = tile_of(it);
+            const bool dup = (2 * (pair + it * npairs) + rank) >= a.num_tiles;
             float* xw = a.XW + ((m * (a.G4 / 8) + np * 32) * TILE_M + r) * 8;
             TWAIT(5, BAR(B_ACCF + buf), (au >> 1) & 1);
             ptx::tc_fence_after();
@@ -395,6 +396,7 @@ proj3_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ 
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     float* dstp = xw + (int64_t)(blk * 4 + i) * TILE_M * 8;
+                    if (a.accumulate && dup) continue;      // an odd tail tile runs on both CTAs of the last pair: only one may add
                     if (a.accumulate) {
                         const float4 o0 = *reinterpret_cast<const float4*>(dstp), o1 = *reinterpret_cast<const float4*>(dstp + 4);
                         v[8 * i] += o0.x; v[8 * i + 1] += o0.y; v[8 * i + 2] += o0.z; v[8 * i + 3] += o0.w;

@@ -15,6 +15,8 @@
 // The head / pool / loss gradients stay on the fp32 kernels of kernels_simple.cu (0.2 % of the flops).
 #include <cub/device/device_radix_sort.cuh>
 
+#include <stdio.h>
+
 #include "tc_state.cuh"
 
 namespace kprn {
@@ -30,6 +32,7 @@ struct TcTrain {
     bf16* WT = nullptr;               // bgemm B operand: [part 2][ks G4/64][hi|lo][half 2][kc 8][n Nh][8]
     DBuf cache, hcache, dgop, dh, dc, wpart, gP, cls;
     DBuf dX, eg_keys, eg_vals, eg_tmp, eg_part, eg_flags;     // entity-gradient staging + sorted segment reduce
+    DBuf step_eid, step_combo, dbg;
     DedupBufs es;                     // distinct entity rows of the batch when the caller (a sparse training step) did not build them
     CUtensorMap tm_dg, tm_hc;         // 2-D maps over dgop / hcache (uint32 view): box = 64 rows x 16 k-chunks
     void* tm_dg_base = nullptr; void* tm_hc_base = nullptr; int64_t tm_dg_rows = 0, tm_hc_rows = 0;
@@ -323,8 +326,29 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BG_THREADS, 1) bgemm
 // A = dgop read as an MN-major operand (M = gate column, K = path row): the bytes [kc][row][8] that bgemm reads K-major.
 // K is split over gridDim.y CTA pairs; each writes its partial tile, wgrad_reduce_kernel sums them in a fixed order.
 
+// entity row (0-based, clamped) and (type,relation) combo of every path-step in READ ORDER o = ((tile*T + t)*128 + r): what the
+// weight-gradient kernel's gather / one-hot warps need per 64-row stage becomes one coalesced load instead of 64 strided ones
+__global__ void step_keys_kernel(const int32_t* __restrict__ ids, int64_t N, int T, int64_t n_order, int64_t V_e, int V_t, int V_r,
+                                 int32_t* __restrict__ eid, int8_t* __restrict__ combo) {
+    const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= n_order) return;
+    const int64_t tile_t = o >> 7, tile = tile_t / T;
+    const int t = (int)(tile_t - tile * T);
+    const int64_t n = tile * TILE_M + (o & 127);
+    if (n >= N) { eid[o] = 0; combo[o] = -1; return; }      // its dG row is zero; no one-hot column
+    const int32_t* idp = ids + (n * T + t) * 3;
+    int64_t e = (int64_t)idp[1] - 1;
+    int ta = idp[0] - 1, rb = idp[2] - 1;
+    eid[o] = (int32_t)(e < 0 ? 0 : (e >= V_e ? V_e - 1 : e));
+    ta = ta < 0 ? 0 : (ta >= V_t ? V_t - 1 : ta);
+    rb = rb < 0 ? 0 : (rb >= V_r ? V_r - 1 : rb);
+    combo[o] = (int8_t)(ta * V_r + rb);
+}
+
 struct WgArgs {
-    const int32_t* ids; int64_t N; int T; int64_t num_tiles; int V_r; int64_t V_e; int V_t;
+    const int32_t* eid; const int8_t* combo;      // per path-step, read order (step_keys_kernel)
+    unsigned long long* dbg;                      // optional wait-cycle counters (KPRN_TC_DEBUG=1)
+    int64_t N; int T; int64_t num_tiles; int V_r; int64_t V_e; int V_t;
     int G4, N0, KE, NOH;
     int64_t blocks_per_split;       // (tile, t) blocks per K-split
     int hc_box;                     // k-chunk rows per TMA box of the h map: min(16, N0/16)
@@ -372,6 +396,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_dg, const __grid_constant__ 
     const int kc_rows = a.G4 / 8;                                    // k-chunk rows of one of hi / lo of a dgop step
     const int hc_rows = a.N0 / 8;
     const int kcA = (mp * 2 + (int)rank) * 16;                       // first k-chunk of this CTA's 128 gate columns
+    const long long dbg_t0 = clock64();
     // stage sequence: for b in [b0, b1): for half in {0, 1} (64 rows each)
 
     if (warp == 0) {
@@ -383,7 +408,8 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_dg, const __grid_constant__ 
                 const int64_t m = b / a.T;
                 const bool has_h = part == 0 && t > 0;
                 for (int half = 0; half < 2; ++half) {
-                    ptx::mbar_wait(BAR(S + stage), phase ^ 1);
+                    if (a.dbg) { long long t0 = clock64(); ptx::mbar_wait(BAR(S + stage), phase ^ 1); if (leader) atomicAdd(a.dbg + 3, (unsigned long long)(clock64() - t0)); }
+                    else ptx::mbar_wait(BAR(S + stage), phase ^ 1);
                     uint32_t tx = 2 * A_BYTES;
                     if (has_h) tx += 2 * B_BYTES;
                     if (part == 1) tx += 2 * B_BYTES;                // the gathers of warp 2 count on the same barrier
@@ -426,8 +452,14 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_dg, const __grid_constant__ 
                 const int t = (int)(b % a.T);
                 const bool has_main = part == 1 || t > 0;
                 for (int half = 0; half < 2; ++half) {
-                    ptx::mbar_wait(BAR(stage), phase);
-                    ptx::mbar_wait_cluster(BAR(B_PEER + stage), phase);
+                    if (a.dbg) {
+                        long long t0 = clock64(); ptx::mbar_wait(BAR(stage), phase); long long t1 = clock64();
+                        ptx::mbar_wait_cluster(BAR(B_PEER + stage), phase);
+                        if (issue) { atomicAdd(a.dbg + 0, (unsigned long long)(t1 - t0)); atomicAdd(a.dbg + 1, (unsigned long long)(clock64() - t1)); }
+                    } else {
+                        ptx::mbar_wait(BAR(stage), phase);
+                        ptx::mbar_wait_cluster(BAR(B_PEER + stage), phase);
+                    }
                     ptx::tc_fence_after();
                     const uint32_t sb0 = ptx::smem_u32(smem + stage * STAGE_BYTES);
                     const uint32_t ah = ptx::desc_lo(sb0, 128), al = ptx::desc_lo(sb0 + A_BYTES, 128);
@@ -463,6 +495,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_dg, const __grid_constant__ 
                 }
             }
             if (issue) ptx::umma2_commit(BAR(B_ACCF), 3);
+            if (issue && a.dbg) atomicAdd(a.dbg + 4, (unsigned long long)(clock64() - dbg_t0));
         } else if (lane == 0) {
             uint32_t stage = 0, phase = 0;
             const uint32_t remote = ptx::mapa(BAR(B_PEER), 0);
@@ -474,62 +507,56 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_dg, const __grid_constant__ 
                 }
         }
     } else if (warp == 2) {
-        // ===== part 1: TMA gather of the entity rows (lane l owns rows 2l, 2l+1 of the 64-row stage ... as 16 row quads: lanes 0-15)
-        //       part 0: writer of the one-hot (type,relation) slice (this CTA's 32 combos) =====
+        // ===== part 1: TMA gather of the entity rows (lanes 0-15 own 4 consecutive rows each of the 64-row stage)
+        //       part 0: writer of the one-hot (type,relation) slice (this CTA's 32 combos; lane l owns rows 2l, 2l+1)
+        //       the stage's keys are one coalesced load, fetched one stage ahead =====
         uint32_t stage = 0, phase = 0;
-        for (int64_t b = b0; b < b1; ++b) {
-            const int t = (int)(b % a.T);
-            const int64_t m = b / a.T;
-            for (int half = 0; half < 2; ++half) {
-                ptx::mbar_wait(BAR(S + stage), phase ^ 1);
-                const uint32_t sb0 = ptx::smem_u32(smem + stage * STAGE_BYTES);
-                if (part == 1) {
-                    if (lane < 16) {
-                        int32_t eid[4];
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            int64_t n = m * TILE_M + half * WG_ROWS + lane * 4 + q;
-                            if (n >= a.N) n = a.N - 1;               // its dG row is zero
-                            int64_t id = (int64_t)a.ids[(n * a.T + t) * 3 + 1] - 1;
-                            eid[q] = (int32_t)(id < 0 ? 0 : (id >= a.V_e ? a.V_e - 1 : id));
-                        }
-                        for (int pnl = 0; pnl < Nh / 64; ++pnl) {
-                            const int32_t col = ((int)rank * (Nh / 64) + pnl) * 64;
-                            const uint32_t off = pnl * 8192 + lane * 512;      // 4 rows x 128 B
-                            ptx::tma_gather4(sb0 + B_OFF + off, &tm_hi, col, eid[0], eid[1], eid[2], eid[3], BAR(stage));
-                            ptx::tma_gather4(sb0 + B_LO_OFF + off, &tm_lo, col, eid[0], eid[1], eid[2], eid[3], BAR(stage));
-                        }
+        const int64_t n_stage = (b1 - b0) * 2;
+        int4 e_next = make_int4(0, 0, 0, 0);
+        int c_next0 = -1, c_next1 = -1;
+        auto fetch = [&](int64_t si) {
+            if (si >= n_stage) return;
+            const int64_t o0 = (b0 + (si >> 1)) * TILE_M + (si & 1) * WG_ROWS;
+            if (part == 1) { if (lane < 16) e_next = *reinterpret_cast<const int4*>(a.eid + o0 + lane * 4); }
+            else { const char2 cc = *reinterpret_cast<const char2*>(a.combo + o0 + lane * 2); c_next0 = cc.x; c_next1 = cc.y; }
+        };
+        fetch(0);
+        for (int64_t si = 0; si < n_stage; ++si) {
+            const int4 eid = e_next;
+            const int cb[2] = {c_next0, c_next1};
+            fetch(si + 1);
+            if (a.dbg) { long long t0 = clock64(); ptx::mbar_wait(BAR(S + stage), phase ^ 1); if (lane == 0 && leader) atomicAdd(a.dbg + 2, (unsigned long long)(clock64() - t0)); }
+            else ptx::mbar_wait(BAR(S + stage), phase ^ 1);
+            const uint32_t sb0 = ptx::smem_u32(smem + stage * STAGE_BYTES);
+            if (part == 1) {
+                if (lane < 16) {
+                    for (int pnl = 0; pnl < Nh / 64; ++pnl) {
+                        const int32_t col = ((int)rank * (Nh / 64) + pnl) * 64;
+                        const uint32_t off = pnl * 8192 + lane * 512;      // 4 rows x 128 B
+                        ptx::tma_gather4(sb0 + B_OFF + off, &tm_hi, col, eid.x, eid.y, eid.z, eid.w, BAR(stage));
+                        ptx::tma_gather4(sb0 + B_LO_OFF + off, &tm_lo, col, eid.x, eid.y, eid.z, eid.w, BAR(stage));
                     }
-                    __syncwarp();
-                    if (lane == 0) ptx::mbar_arrive(BAR(stage));
-                } else {
-#pragma unroll
-                    for (int q = 0; q < 2; ++q) {
-                        const int rr = lane * 2 + q;
-                        int64_t n = m * TILE_M + half * WG_ROWS + rr;
-                        int combo = -1;
-                        if (n < a.N) {
-                            const int32_t* idp = a.ids + (n * a.T + t) * 3;
-                            int ta = idp[0] - 1, rb = idp[2] - 1;
-                            ta = ta < 0 ? 0 : (ta >= a.V_t ? a.V_t - 1 : ta);
-                            rb = rb < 0 ? 0 : (rb >= a.V_r ? a.V_r - 1 : rb);
-                            combo = ta * a.V_r + rb - (int)rank * 32 - 0;
-                        }
-                        // this CTA holds combos [rank*32, rank*32+32) of the 64-column slice (NOH = 1) as 4 k-chunks of 8
-#pragma unroll
-                        for (int kc = 0; kc < 4; ++kc) {
-                            uint32_t w[4] = {0u, 0u, 0u, 0u};
-                            if (combo >= 0 && combo < 32 && (combo >> 3) == kc) w[(combo & 7) >> 1] = 0x3F80u << (16 * (combo & 1));
-                            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(sb0 + OH_OFF + kc * (WG_ROWS * 16) + rr * 16),
-                                         "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
-                        }
-                    }
-                    ptx::fence_proxy_async_smem();
-                    __syncwarp();
-                    if (lane == 0) ptx::mbar_arrive(BAR(stage));
                 }
-                if (++stage == S) { stage = 0; phase ^= 1; }
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(BAR(stage));
+            } else {
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int rr = lane * 2 + q;
+                    const int combo = cb[q] < 0 ? -1 : cb[q] - (int)rank * 32;      // this CTA holds combos [rank*32, +32) as 4 k-chunks of 8
+#pragma unroll
+                    for (int kc = 0; kc < 4; ++kc) {
+                        uint32_t w[4] = {0u, 0u, 0u, 0u};
+                        if (combo >= 0 && combo < 32 && (combo >> 3) == kc) w[(combo & 7) >> 1] = 0x3F80u << (16 * (combo & 1));
+                        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(sb0 + OH_OFF + kc * (WG_ROWS * 16) + rr * 16),
+                                     "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+                    }
+                }
+                ptx::fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(BAR(stage));
             }
+            if (++stage == S) { stage = 0; phase ^= 1; }
         }
     } else if (warp >= 4) {
         // ===== epilogue: this CTA's 128 gate columns x (Nmain [+ 64]) -> partial buffer [split][part][gp][320] =====
@@ -964,14 +991,33 @@ int tc_backward(kprn_ctx* ctx, float scale) {
         tt->tm_hc_base = tt->hcache.p; tt->tm_hc_rows = hc_rows;
     }
     {
+        KPRN_TRY(ensure(tt->step_eid, sizeof(int32_t) * (size_t)n_order));
+        KPRN_TRY(ensure(tt->step_combo, (size_t)n_order));
+        step_keys_kernel<<<(unsigned)cdiv(n_order, 256), 256, 0, ctx->stream>>>(ctx->d_ids, N, T, n_order, c.V_e, (int)c.V_t, (int)c.V_r,
+                                                                              tt->step_eid.as<int32_t>(), tt->step_combo.as<int8_t>());
+        KPRN_LAUNCH_CHECK(ctx);
         WgArgs wa;
-        wa.ids = ctx->d_ids; wa.N = N; wa.T = T; wa.num_tiles = ptiles; wa.V_r = (int)c.V_r; wa.V_e = c.V_e; wa.V_t = (int)c.V_t;
+        wa.eid = tt->step_eid.as<int32_t>(); wa.combo = tt->step_combo.as<int8_t>(); wa.dbg = nullptr;
+        if (s->debug) {
+            KPRN_TRY(ensure(tt->dbg, 8 * sizeof(unsigned long long)));
+            KPRN_CUDA(cudaMemsetAsync(tt->dbg.p, 0, 8 * sizeof(unsigned long long), ctx->stream));
+            wa.dbg = tt->dbg.as<unsigned long long>();
+        }
+        wa.N = N; wa.T = T; wa.num_tiles = ptiles; wa.V_r = (int)c.V_r; wa.V_e = c.V_e; wa.V_t = (int)c.V_t;
         wa.G4 = G4; wa.N0 = Hp; wa.KE = KE; wa.NOH = 1; wa.blocks_per_split = bps; wa.part = tt->wpart.as<float>(); wa.H_BYTES = TILE_M * Hp * 2;
         wa.hc_box = hc_box;
         const size_t wg_smem = (size_t)WG_STAGES * (2 * 16384 + 2 * 8192 * 2 + 4096) + 256;
         KPRN_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wg_smem));
         wgrad_kernel<<<dim3((unsigned)(items * 2), (unsigned)splits), WG_THREADS, wg_smem, ctx->stream>>>(tt->tm_dg, tt->tm_hc, s->tm_hi, s->tm_lo, wa);
         KPRN_LAUNCH_CHECK(ctx);
+        if (wa.dbg) {
+            unsigned long long h[8];
+            KPRN_CUDA(cudaMemcpyAsync(h, wa.dbg, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+            KPRN_CUDA(cudaStreamSynchronize(ctx->stream));
+            const double np_ = (double)items * splits;
+            fprintf(stderr, "[kprn tc debug] wgrad: issuer cycles/pair %.0f | waits/pair: issuer.full %.0f, issuer.peer %.0f, gather|onehot.empty %.0f, "
+                            "producer.empty %.0f\n", h[4] / np_, h[0] / np_, h[1] / np_, h[2] / np_, h[3] / np_);
+        }
     }
     float* gP = tt->gP.as<float>();
     float* Tsum = gP + (size_t)64 * G4;
@@ -999,7 +1045,7 @@ void tc_train_destroy(kprn_ctx* ctx) {
     TcTrain* tt = s->tt;
     if (tt->WT) cudaFree(tt->WT);
     for (DBuf* b : {&tt->cache, &tt->hcache, &tt->dgop, &tt->dh, &tt->dc, &tt->wpart, &tt->gP, &tt->cls, &tt->dX, &tt->eg_keys, &tt->eg_vals,
-                    &tt->eg_tmp, &tt->eg_part, &tt->eg_flags})
+                    &tt->eg_tmp, &tt->eg_part, &tt->eg_flags, &tt->step_eid, &tt->step_combo, &tt->dbg})
         if (b->p) { cudaFree(b->p); b->p = nullptr; b->cap = 0; }
     dedup_free(tt->es);
     delete tt;

@@ -131,7 +131,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WS_THREADS, 1) wide_
         uint32_t ug[2] = {0, 0};
         for (int64_t it = 0; it < my_tiles; ++it) {
             const int64_t m = tile_of(it);
-            const int64_t n = m * TILE_M + r;
+            // an odd tail tile runs on both CTAs of the last pair (the MMA needs both): the duplicate takes part in the MMAs and the
+            // barriers but writes nothing -- c is updated in place, two writers would race
+            const bool dup = (2 * (pair + it * npairs) + rank) >= a.num_tiles;
+            const int64_t n = dup ? a.N : m * TILE_M + r;
             uint32_t slot = 0;
             if (a.pos) { const uint32_t p = a.pos[(m * a.T + a.t) * TILE_M + r]; slot = p == 0xFFFFFFFFu ? 0u : a.slot_of[p]; }
             const float* xw_t = a.pos ? a.XW + (int64_t)(slot >> 7) * tile_xw + (slot & 127) * 8 : a.XW + (m * a.T + a.t) * tile_xw + r * 8;
@@ -190,7 +193,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WS_THREADS, 1) wide_
                                 hv[e] = ptx::lo2(h2); hv[e + 1] = ptx::hi2(h2);
                             }
                         }
-                        if (!last) {
+                        if (dup) {
+                            // nothing to store
+                        } else if (!last) {
                             *reinterpret_cast<float4*>(cptr) = make_float4(cn[0], cn[1], cn[2], cn[3]);
                             *reinterpret_cast<float4*>(cptr + 4) = make_float4(cn[4], cn[5], cn[6], cn[7]);
                             uint32_t wh[4], wl[4];
