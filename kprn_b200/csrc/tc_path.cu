@@ -441,7 +441,8 @@ struct RecurArgs {
     // see the dedup kernels); null = its own row (tile tile*T + t, row r)
     const uint32_t* pos; const uint32_t* slot_of;
     // training forward (TRAIN = true): the activations the backward needs, written by the epilogue as it computes them
-    //   cache  [tile][t][chunk j][sub-block sb][i,g,f,o,c][pair p 4][row 128][2] fp32: each st.global.v2 of a warp is 256 contiguous bytes
+    //   cache  [tile][t][chunk j][sub-block sb][i,g,f,o,c][half 2][row 128][4] fp32 (units 4 half .. +3 of the thread's 8): each
+    //          st.global.v4 of a warp is 512 contiguous bytes
     //   hcache [tile][t][hi|lo][kc Hp/8][row 128][8] bf16: h_t in the UMMA operand layout (what the next step's MMAs read, and the
     //          B operand of the weight-gradient product dG^T h_{t-1}); replaces the per-CTA scratch
     float* cache; bf16* hcache;
@@ -712,7 +713,7 @@ __global__ void __launch_bounds__(RECUR_THREADS, 1) recur_kernel(RecurArgs a) {
                                            : a.XW + (pt * T + t) * tile_xw + r * 8;
                 const bool last = (t == T - 1);
                 uint8_t* const scratch = h_image(pt, t);
-                float* const cache_t = TRAIN ? a.cache + (size_t)(pt * T + t) * NCH * 20480 + r * 2 : nullptr;
+                float* const cache_t = TRAIN ? a.cache + (size_t)(pt * T + t) * NCH * 20480 + r * 4 : nullptr;
                 float xa[32], xb[32];                 // XW of the current / next chunk, ping-pong (no register copies)
                 float dot = 0.f;                      // last step, scores-only: this thread's share of h_T . wo
                 KPRN_LOAD_XW(xa, xw_t, 0)
@@ -765,6 +766,7 @@ __global__ void __launch_bounds__(RECUR_THREADS, 1) recur_kernel(RecurArgs a) {
                     {
                         const uint64_t one2 = ptx::pack2(1.f, 1.f), mtwo2 = ptx::pack2(-2.f, -2.f);
                         const uint64_t k2 = ptx::pack2(2.8853900817779268f, 2.8853900817779268f);
+                        uint64_t ki = 0, kg = 0, kf = 0, ko = 0, kc2 = 0;      // TRAIN: the even pair, kept until its odd neighbour is ready
 #pragma unroll
                         for (int p = 0; p < 4; ++p) {
                             const int e = 2 * p;
@@ -784,12 +786,15 @@ __global__ void __launch_bounds__(RECUR_THREADS, 1) recur_kernel(RecurArgs a) {
                             cn[e] = ptx::lo2(c2); cn[e + 1] = ptx::hi2(c2);
                             hv[e] = ptx::lo2(h2); hv[e + 1] = ptx::hi2(h2);
                             if (TRAIN) {
-                                float* cc = cache_t + (size_t)(j * 4 + sb) * 5120 + p * 256;
-                                asm volatile("st.global.v2.f32 [%0], {%1, %2};" ::"l"(cc), "f"(ptx::lo2(i_)), "f"(ptx::hi2(i_)) : "memory");
-                                asm volatile("st.global.v2.f32 [%0], {%1, %2};" ::"l"(cc + 1024), "f"(ptx::lo2(g_)), "f"(ptx::hi2(g_)) : "memory");
-                                asm volatile("st.global.v2.f32 [%0], {%1, %2};" ::"l"(cc + 2048), "f"(ptx::lo2(f_)), "f"(ptx::hi2(f_)) : "memory");
-                                asm volatile("st.global.v2.f32 [%0], {%1, %2};" ::"l"(cc + 3072), "f"(ptx::lo2(o_)), "f"(ptx::hi2(o_)) : "memory");
-                                asm volatile("st.global.v2.f32 [%0], {%1, %2};" ::"l"(cc + 4096), "f"(ptx::lo2(c2)), "f"(ptx::hi2(c2)) : "memory");
+                                // activation cache: two pairs per 128-bit store; a warp store is 512 contiguous bytes
+                                if (p & 1) {
+                                    float* cc = cache_t + (size_t)(j * 4 + sb) * 5120 + (p >> 1) * 512;
+                                    asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cc), "f"(ptx::lo2(ki)), "f"(ptx::hi2(ki)), "f"(ptx::lo2(i_)), "f"(ptx::hi2(i_)) : "memory");
+                                    asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cc + 1024), "f"(ptx::lo2(kg)), "f"(ptx::hi2(kg)), "f"(ptx::lo2(g_)), "f"(ptx::hi2(g_)) : "memory");
+                                    asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cc + 2048), "f"(ptx::lo2(kf)), "f"(ptx::hi2(kf)), "f"(ptx::lo2(f_)), "f"(ptx::hi2(f_)) : "memory");
+                                    asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cc + 3072), "f"(ptx::lo2(ko)), "f"(ptx::hi2(ko)), "f"(ptx::lo2(o_)), "f"(ptx::hi2(o_)) : "memory");
+                                    asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cc + 4096), "f"(ptx::lo2(kc2)), "f"(ptx::hi2(kc2)), "f"(ptx::lo2(c2)), "f"(ptx::hi2(c2)) : "memory");
+                                } else { ki = i_; kg = g_; kf = f_; ko = o_; kc2 = c2; }
                             }
                         }
                     }

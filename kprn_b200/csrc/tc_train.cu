@@ -16,6 +16,7 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "tc_state.cuh"
 
@@ -107,19 +108,20 @@ __global__ void __launch_bounds__(512) cell_bwd_kernel(CellBwdArgs a) {
     const int64_t n = m * TILE_M + r;
     const bool live = n < a.N;
     const size_t step_floats = (size_t)a.NCH * 20480;
-    const float* ct = a.cache + (size_t)(m * a.T + a.t) * step_floats + (size_t)(j * 4 + sb) * 5120 + r * 2;
+    const float* ct = a.cache + (size_t)(m * a.T + a.t) * step_floats + (size_t)(j * 4 + sb) * 5120 + r * 4;
     const float* cprev = a.t > 0 ? ct - step_floats + 4096 : nullptr;
     float gi[8], gg[8], gf[8], go[8], cc[8], cp[8];
 #pragma unroll
-    for (int p = 0; p < 4; ++p) {
-        const float2 vi = *reinterpret_cast<const float2*>(ct + p * 256), vg = *reinterpret_cast<const float2*>(ct + 1024 + p * 256);
-        const float2 vf = *reinterpret_cast<const float2*>(ct + 2048 + p * 256), vo = *reinterpret_cast<const float2*>(ct + 3072 + p * 256);
-        const float2 vc = *reinterpret_cast<const float2*>(ct + 4096 + p * 256);
-        gi[2 * p] = vi.x; gi[2 * p + 1] = vi.y; gg[2 * p] = vg.x; gg[2 * p + 1] = vg.y; gf[2 * p] = vf.x; gf[2 * p + 1] = vf.y;
-        go[2 * p] = vo.x; go[2 * p + 1] = vo.y; cc[2 * p] = vc.x; cc[2 * p + 1] = vc.y;
-        float2 vp = make_float2(0.f, 0.f);
-        if (cprev) vp = *reinterpret_cast<const float2*>(cprev + p * 256);
-        cp[2 * p] = vp.x; cp[2 * p + 1] = vp.y;
+    for (int hf = 0; hf < 2; ++hf) {            // cache layout [i,g,f,o,c][half 2][row 128][4]: 128-bit loads, 512 B per warp
+        const float4 vi = *reinterpret_cast<const float4*>(ct + hf * 512), vg = *reinterpret_cast<const float4*>(ct + 1024 + hf * 512);
+        const float4 vf = *reinterpret_cast<const float4*>(ct + 2048 + hf * 512), vo = *reinterpret_cast<const float4*>(ct + 3072 + hf * 512);
+        const float4 vc = *reinterpret_cast<const float4*>(ct + 4096 + hf * 512);
+        float4 vp = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (cprev) vp = *reinterpret_cast<const float4*>(cprev + hf * 512);
+        const int b = 4 * hf;
+        gi[b] = vi.x; gi[b + 1] = vi.y; gi[b + 2] = vi.z; gi[b + 3] = vi.w; gg[b] = vg.x; gg[b + 1] = vg.y; gg[b + 2] = vg.z; gg[b + 3] = vg.w;
+        gf[b] = vf.x; gf[b + 1] = vf.y; gf[b + 2] = vf.z; gf[b + 3] = vf.w; go[b] = vo.x; go[b + 1] = vo.y; go[b + 2] = vo.z; go[b + 3] = vo.w;
+        cc[b] = vc.x; cc[b + 1] = vc.y; cc[b + 2] = vc.z; cc[b + 3] = vc.w; cp[b] = vp.x; cp[b + 1] = vp.y; cp[b + 2] = vp.z; cp[b + 3] = vp.w;
     }
     const int grp = j * 4 + sb;                                 // 8-unit group of this thread
     const size_t gi8 = ((size_t)(m * (a.G4 / 32) + grp) * TILE_M + r) * 8;      // G4/32 = Hp/8 groups per tile
@@ -352,6 +354,7 @@ struct WgArgs {
     int G4, N0, KE, NOH;
     int64_t blocks_per_split;       // (tile, t) blocks per K-split
     int hc_box;                     // k-chunk rows per TMA box of the h map: min(16, N0/16)
+    const bf16* dgop; const bf16* hcache; int bulk1d;
     float* part;                    // [split][part 2][gp G4][n 320] fp32
     int H_BYTES;                    // bytes of one of hi / lo of an hcache step
 };
@@ -400,21 +403,36 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_dg, const __grid_constant__ 
     // stage sequence: for b in [b0, b1): for half in {0, 1} (64 rows each)
 
     if (warp == 0) {
-        // ===== TMA producer: A (dG, hi + lo) and, part 0, this CTA's half of h_{t-1} (hi + lo); 2-D maps, one op each =====
-        if (lane == 0) {
-            uint32_t stage = 0, phase = 0;
-            for (int64_t b = b0; b < b1; ++b) {
-                const int t = (int)(b % a.T);
-                const int64_t m = b / a.T;
-                const bool has_h = part == 0 && t > 0;
-                for (int half = 0; half < 2; ++half) {
+        // ===== TMA producer: A (dG, hi + lo) and, part 0, this CTA's half of h_{t-1} (hi + lo).  A stage is 64 path rows of 16
+        // k-chunks: sixteen 1 KB pieces per operand half.  bulk1d: every lane issues one 1-D bulk copy per operand (lane = (hi|lo,
+        // k-chunk)); else one 2-D tensor-map copy per operand half from lane 0 =====
+        uint32_t stage = 0, phase = 0;
+        const uint8_t* dg8 = reinterpret_cast<const uint8_t*>(a.dgop);
+        const uint8_t* hc8 = reinterpret_cast<const uint8_t*>(a.hcache);
+        for (int64_t b = b0; b < b1; ++b) {
+            const int t = (int)(b % a.T);
+            const int64_t m = b / a.T;
+            const bool has_h = part == 0 && t > 0;
+            for (int half = 0; half < 2; ++half) {
+                if (lane == 0) {
                     if (a.dbg) { long long t0 = clock64(); ptx::mbar_wait(BAR(S + stage), phase ^ 1); if (leader) atomicAdd(a.dbg + 3, (unsigned long long)(clock64() - t0)); }
                     else ptx::mbar_wait(BAR(S + stage), phase ^ 1);
                     uint32_t tx = 2 * A_BYTES;
                     if (has_h) tx += 2 * B_BYTES;
                     if (part == 1) tx += 2 * B_BYTES;                // the gathers of warp 2 count on the same barrier
                     ptx::mbar_arrive_expect_tx(BAR(stage), tx);
-                    const uint32_t sb0 = ptx::smem_u32(smem + stage * STAGE_BYTES);
+                }
+                __syncwarp();
+                const uint32_t sb0 = ptx::smem_u32(smem + stage * STAGE_BYTES);
+                if (a.bulk1d) {
+                    const int hlx = lane >> 4, kc = lane & 15;
+                    const size_t rowA = (size_t)((b * 2 + hlx) * kc_rows + kcA + kc);
+                    ptx::tma_bulk_g2s(sb0 + hlx * A_BYTES + kc * 1024, dg8 + rowA * 2048 + half * 1024, 1024, BAR(stage));
+                    if (has_h && kc < Nh / 8) {
+                        const size_t rowH = (size_t)(((m * a.T + (t - 1)) * 2 + hlx) * hc_rows + (int)rank * (Nh / 8) + kc);
+                        ptx::tma_bulk_g2s(sb0 + (hlx ? B_LO_OFF : B_OFF) + kc * 1024, hc8 + rowH * 2048 + half * 1024, 1024, BAR(stage));
+                    }
+                } else if (lane == 0) {
                     const int32_t col = half * (WG_ROWS * 4);        // uint32 column: 64 rows x 16 B
                     const int32_t rowA = (int32_t)((b * 2) * kc_rows + kcA);
                     asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
@@ -430,8 +448,8 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_dg, const __grid_constant__ 
                                          ::"r"(sb0 + B_LO_OFF + c * 1024), "l"(&tm_hc), "r"(col), "r"(rowH + hc_rows + c), "r"(BAR(stage)) : "memory");
                         }
                     }
-                    if (++stage == S) { stage = 0; phase ^= 1; }
                 }
+                if (++stage == S) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
@@ -1005,7 +1023,8 @@ int tc_backward(kprn_ctx* ctx, float scale) {
         }
         wa.N = N; wa.T = T; wa.num_tiles = ptiles; wa.V_r = (int)c.V_r; wa.V_e = c.V_e; wa.V_t = (int)c.V_t;
         wa.G4 = G4; wa.N0 = Hp; wa.KE = KE; wa.NOH = 1; wa.blocks_per_split = bps; wa.part = tt->wpart.as<float>(); wa.H_BYTES = TILE_M * Hp * 2;
-        wa.hc_box = hc_box;
+        wa.hc_box = hc_box; wa.dgop = tt->dgop.as<bf16>(); wa.hcache = tt->hcache.as<bf16>();
+        { const char* d = getenv("KPRN_WG_BULK"); wa.bulk1d = !(d && d[0] == '0'); }
         const size_t wg_smem = (size_t)WG_STAGES * (2 * 16384 + 2 * 8192 * 2 + 4096) + 256;
         KPRN_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wg_smem));
         wgrad_kernel<<<dim3((unsigned)(items * 2), (unsigned)splits), WG_THREADS, wg_smem, ctx->stream>>>(tt->tm_dg, tt->tm_hc, s->tm_hi, s->tm_lo, wa);
