@@ -33,10 +33,8 @@ struct TcTrain {
     bf16* WT = nullptr;               // bgemm B operand: [part 2][ks G4/64][hi|lo][half 2][kc 8][n Nh][8]
     DBuf cache, hcache, dgop, dh, dc, wpart, gP, cls;
     DBuf dX, eg_keys, eg_vals, eg_tmp, eg_part, eg_flags;     // entity-gradient staging + sorted segment reduce
-    DBuf step_eid, step_combo, dbg;
+    DBuf xop, ohop, dbg;              // gathered entity rows / one-hot slice in operand layout (prep_operands_kernel)
     DedupBufs es;                     // distinct entity rows of the batch when the caller (a sparse training step) did not build them
-    CUtensorMap tm_dg, tm_hc;         // 2-D maps over dgop / hcache (uint32 view): box = 64 rows x 16 k-chunks
-    void* tm_dg_base = nullptr; void* tm_hc_base = nullptr; int64_t tm_dg_rows = 0, tm_hc_rows = 0;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -328,40 +326,69 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BG_THREADS, 1) bgemm
 // A = dgop read as an MN-major operand (M = gate column, K = path row): the bytes [kc][row][8] that bgemm reads K-major.
 // K is split over gridDim.y CTA pairs; each writes its partial tile, wgrad_reduce_kernel sums them in a fixed order.
 
-// entity row (0-based, clamped) and (type,relation) combo of every path-step in READ ORDER o = ((tile*T + t)*128 + r): what the
-// weight-gradient kernel's gather / one-hot warps need per 64-row stage becomes one coalesced load instead of 64 strided ones
-__global__ void step_keys_kernel(const int32_t* __restrict__ ids, int64_t N, int T, int64_t n_order, int64_t V_e, int V_t, int V_r,
-                                 int32_t* __restrict__ eid, int8_t* __restrict__ combo) {
-    const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (o >= n_order) return;
-    const int64_t tile_t = o >> 7, tile = tile_t / T;
-    const int t = (int)(tile_t - tile * T);
-    const int64_t n = tile * TILE_M + (o & 127);
-    if (n >= N) { eid[o] = 0; combo[o] = -1; return; }      // its dG row is zero; no one-hot column
-    const int32_t* idp = ids + (n * T + t) * 3;
-    int64_t e = (int64_t)idp[1] - 1;
-    int ta = idp[0] - 1, rb = idp[2] - 1;
-    eid[o] = (int32_t)(e < 0 ? 0 : (e >= V_e ? V_e - 1 : e));
-    ta = ta < 0 ? 0 : (ta >= V_t ? V_t - 1 : ta);
-    rb = rb < 0 ? 0 : (rb >= V_r ? V_r - 1 : rb);
-    combo[o] = (int8_t)(ta * V_r + rb);
+// Operands of the weight-gradient product that do not exist yet in operand layout, built once per backward:
+//   xop  [(tile*T + t)][hi|lo][kc KE/8][row 128][8] bf16 : the gathered entity rows x_e of every path-step (from the pre-split table)
+//   ohop [(tile*T + t)][kc 8][row 128][8] bf16            : onehot(type*V_r + relation), 64 columns (exact in bf16: hi only)
+// so that wgrad_kernel streams every operand with plain bulk copies (a TMA tile::gather4 per use costs ~50-100 issue cycles per
+// 4 rows, which made the entity part of wgrad gather-issue-bound).  One block per (tile, t), one thread per path row.
+__global__ void __launch_bounds__(128) prep_operands_kernel(const int32_t* __restrict__ ids, int64_t N, int T, int64_t V_e, int V_t, int V_r,
+                                                            const bf16* __restrict__ E_hi, const bf16* __restrict__ E_lo, int KE,
+                                                            bf16* __restrict__ xop, bf16* __restrict__ ohop) {
+    const int64_t b = blockIdx.x;                 // tile*T + t
+    const int r = threadIdx.x;
+    const int64_t m = b / T;
+    const int t = (int)(b - m * T);
+    const int64_t n = m * TILE_M + r;
+    const bool live = n < N;
+    int64_t e = 0; int combo = -1;
+    if (live) {
+        const int32_t* idp = ids + (n * T + t) * 3;
+        e = (int64_t)idp[1] - 1;
+        e = e < 0 ? 0 : (e >= V_e ? V_e - 1 : e);
+        int ta = idp[0] - 1, rb = idp[2] - 1;
+        ta = ta < 0 ? 0 : (ta >= V_t ? V_t - 1 : ta);
+        rb = rb < 0 ? 0 : (rb >= V_r ? V_r - 1 : rb);
+        combo = ta * V_r + rb;
+    }
+    const int KC = KE / 8;
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    const uint4* sh = reinterpret_cast<const uint4*>(E_hi + e * KE);
+    const uint4* sl = reinterpret_cast<const uint4*>(E_lo + e * KE);
+    uint4* dh = reinterpret_cast<uint4*>(xop + (size_t)(b * 2) * KC * TILE_M * 8) + r;
+    uint4* dl = dh + (size_t)KC * TILE_M;
+    for (int kc = 0; kc < KC; ++kc) {             // a warp's store is 512 contiguous bytes
+        dh[(size_t)kc * TILE_M] = live ? sh[kc] : z;
+        dl[(size_t)kc * TILE_M] = live ? sl[kc] : z;
+    }
+    uint4* doh = reinterpret_cast<uint4*>(ohop + (size_t)b * 8 * TILE_M * 8) + r;
+#pragma unroll
+    for (int kc = 0; kc < 8; ++kc) {
+        uint32_t w[4] = {0u, 0u, 0u, 0u};
+        if (combo >= 0 && (combo >> 3) == kc) w[(combo & 7) >> 1] = 0x3F80u << (16 * (combo & 1));      // bf16 1.0
+        doh[(size_t)kc * TILE_M] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
 }
 
+// ---------------------------------------------------------------------------------------------
+// wgrad: G[gp, n] = sum over path-steps of dG[step, gp] * B[step, n]  for one 256-row block of gate columns (128 per CTA of a
+// pair) and one operand family:
+//   part 0: B = [h_{t-1} (Hp columns) | onehot(type,relation) (64 columns)]   -> gWh and gP (two accumulators)
+//   part 1: B = x_e (KE columns)                                              -> gWx[:, entity columns]
+// A = dgop read as an MN-major operand (M = gate column, K = path row): the bytes [kc][row][8] that bgemm reads K-major;
+// B likewise (hcache / xop / ohop).  A stage is 64 path rows: every operand half is sixteen (or fewer) 1 KB pieces, one
+// cp.async.bulk per lane of the producer warp.  K is split over gridDim.y CTA pairs; each writes its partial tile,
+// wgrad_reduce_kernel sums them in a fixed order.
+
 struct WgArgs {
-    const int32_t* eid; const int8_t* combo;      // per path-step, read order (step_keys_kernel)
+    const bf16* dgop; const bf16* hcache; const bf16* xop; const bf16* ohop;
     unsigned long long* dbg;                      // optional wait-cycle counters (KPRN_TC_DEBUG=1)
-    int64_t N; int T; int64_t num_tiles; int V_r; int64_t V_e; int V_t;
-    int G4, N0, KE, NOH;
+    int T; int64_t num_tiles;
+    int G4, N0, KE;
     int64_t blocks_per_split;       // (tile, t) blocks per K-split
-    int hc_box;                     // k-chunk rows per TMA box of the h map: min(16, N0/16)
-    const bf16* dgop; const bf16* hcache; int bulk1d;
     float* part;                    // [split][part 2][gp G4][n 320] fp32
-    int H_BYTES;                    // bytes of one of hi / lo of an hcache step
 };
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WG_THREADS, 1)
-wgrad_kernel(const __grid_constant__ CUtensorMap tm_dg, const __grid_constant__ CUtensorMap tm_hc, const __grid_constant__ CUtensorMap tm_hi,
-             const __grid_constant__ CUtensorMap tm_lo, WgArgs a) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WG_THREADS, 1) wgrad_kernel(WgArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = ptx::cluster_ctarank();
@@ -372,21 +399,19 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_dg, const __grid_constant__ 
     const int split = blockIdx.y;
     const int Nmain = part ? a.KE : a.N0, Nh = Nmain / 2;
     constexpr uint32_t A_BYTES = 16 * WG_ROWS * 16;                  // [kc 16][row 64][16 B] = 16 KB per hi / lo
-    const uint32_t B_BYTES = (uint32_t)Nh * WG_ROWS * 2;             // per hi / lo: part 0 [kc Nh/8][row 64][16 B]; part 1 [panel Nh/64][row 64][128 B]
+    const uint32_t B_BYTES = (uint32_t)Nh * WG_ROWS * 2;             // per hi / lo: [kc Nh/8][row 64][16 B]
     constexpr uint32_t OH_BYTES = 4 * WG_ROWS * 16;                  // one-hot: this CTA's 32 combos x 64 rows (hi only)
-    const uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * 8192 * (uint32_t)((Nh + 63) / 64) + OH_BYTES;   // B region rounded to 8 KB panels (1024-aligned)
-    const uint32_t B_OFF = 2 * A_BYTES, B_LO_OFF = B_OFF + 8192 * (uint32_t)((Nh + 63) / 64), OH_OFF = STAGE_BYTES - OH_BYTES;
+    constexpr uint32_t B_OFF = 2 * A_BYTES, B_LO_OFF = B_OFF + 16384, OH_OFF = B_LO_OFF + 16384, STAGE_BYTES = OH_OFF + OH_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * STAGE_BYTES);
     const uint32_t bar0 = ptx::smem_u32(bars);
     auto BAR = [&](int i) { return bar0 + 8u * i; };
-    // [0,S) full (TMA tx + one-hot writer)  [S,2S) empty  [2S,3S) peer_full (leader)  3S acc_full
+    // [0,S) full (TMA tx)  [S,2S) empty  [2S,3S) peer_full (leader)  3S acc_full
     constexpr int B_PEER = 2 * S, B_ACCF = 3 * S;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_ACCF + 1);
     if (threadIdx.x == 0) {
-        for (int i = 0; i < S; ++i) { ptx::mbar_init(BAR(i), 2); ptx::mbar_init(BAR(S + i), 1); ptx::mbar_init(BAR(B_PEER + i), 1); }
+        for (int i = 0; i < S; ++i) { ptx::mbar_init(BAR(i), 1); ptx::mbar_init(BAR(S + i), 1); ptx::mbar_init(BAR(B_PEER + i), 1); }
         ptx::mbar_init(BAR(B_ACCF), 1);
         ptx::fence_mbar_init();
-        ptx::prefetch_tensormap(&tm_dg); ptx::prefetch_tensormap(&tm_hc); ptx::prefetch_tensormap(&tm_hi); ptx::prefetch_tensormap(&tm_lo);
     }
     if (warp == 2) { ptx::tmem_alloc2(ptx::smem_u32(tmem_slot), 512); ptx::tmem_relinquish2(); }
     ptx::tc_fence_before();
@@ -397,57 +422,38 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_dg, const __grid_constant__ 
     const int64_t nblocks = a.num_tiles * a.T;
     const int64_t b0 = split * a.blocks_per_split, b1 = (b0 + a.blocks_per_split < nblocks) ? b0 + a.blocks_per_split : nblocks;
     const int kc_rows = a.G4 / 8;                                    // k-chunk rows of one of hi / lo of a dgop step
-    const int hc_rows = a.N0 / 8;
+    const int bk_rows = (part ? a.KE : a.N0) / 8;                    // ... of an hcache / xop step
     const int kcA = (mp * 2 + (int)rank) * 16;                       // first k-chunk of this CTA's 128 gate columns
     const long long dbg_t0 = clock64();
-    // stage sequence: for b in [b0, b1): for half in {0, 1} (64 rows each)
 
     if (warp == 0) {
-        // ===== TMA producer: A (dG, hi + lo) and, part 0, this CTA's half of h_{t-1} (hi + lo).  A stage is 64 path rows of 16
-        // k-chunks: sixteen 1 KB pieces per operand half.  bulk1d: every lane issues one 1-D bulk copy per operand (lane = (hi|lo,
-        // k-chunk)); else one 2-D tensor-map copy per operand half from lane 0 =====
+        // ===== TMA producer: lane = (hi|lo, k-chunk); one 1 KB bulk copy per lane and operand =====
         uint32_t stage = 0, phase = 0;
         const uint8_t* dg8 = reinterpret_cast<const uint8_t*>(a.dgop);
-        const uint8_t* hc8 = reinterpret_cast<const uint8_t*>(a.hcache);
+        const uint8_t* b8 = reinterpret_cast<const uint8_t*>(part ? a.xop : a.hcache);
+        const uint8_t* oh8 = reinterpret_cast<const uint8_t*>(a.ohop);
+        const int hlx = lane >> 4, kc = lane & 15;
         for (int64_t b = b0; b < b1; ++b) {
             const int t = (int)(b % a.T);
-            const int64_t m = b / a.T;
-            const bool has_h = part == 0 && t > 0;
+            const int64_t bsrc = part ? b : b - 1;                   // h_{t-1} of the same tile (t > 0), x_e of the step itself
+            const bool has_b = part == 1 || t > 0;
             for (int half = 0; half < 2; ++half) {
                 if (lane == 0) {
                     if (a.dbg) { long long t0 = clock64(); ptx::mbar_wait(BAR(S + stage), phase ^ 1); if (leader) atomicAdd(a.dbg + 3, (unsigned long long)(clock64() - t0)); }
                     else ptx::mbar_wait(BAR(S + stage), phase ^ 1);
-                    uint32_t tx = 2 * A_BYTES;
-                    if (has_h) tx += 2 * B_BYTES;
-                    if (part == 1) tx += 2 * B_BYTES;                // the gathers of warp 2 count on the same barrier
-                    ptx::mbar_arrive_expect_tx(BAR(stage), tx);
+                    ptx::mbar_arrive_expect_tx(BAR(stage), 2 * A_BYTES + (has_b ? 2 * B_BYTES : 0) + (part == 0 ? OH_BYTES : 0));
                 }
                 __syncwarp();
                 const uint32_t sb0 = ptx::smem_u32(smem + stage * STAGE_BYTES);
-                if (a.bulk1d) {
-                    const int hlx = lane >> 4, kc = lane & 15;
-                    const size_t rowA = (size_t)((b * 2 + hlx) * kc_rows + kcA + kc);
-                    ptx::tma_bulk_g2s(sb0 + hlx * A_BYTES + kc * 1024, dg8 + rowA * 2048 + half * 1024, 1024, BAR(stage));
-                    if (has_h && kc < Nh / 8) {
-                        const size_t rowH = (size_t)(((m * a.T + (t - 1)) * 2 + hlx) * hc_rows + (int)rank * (Nh / 8) + kc);
-                        ptx::tma_bulk_g2s(sb0 + (hlx ? B_LO_OFF : B_OFF) + kc * 1024, hc8 + rowH * 2048 + half * 1024, 1024, BAR(stage));
-                    }
-                } else if (lane == 0) {
-                    const int32_t col = half * (WG_ROWS * 4);        // uint32 column: 64 rows x 16 B
-                    const int32_t rowA = (int32_t)((b * 2) * kc_rows + kcA);
-                    asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                                 ::"r"(sb0), "l"(&tm_dg), "r"(col), "r"(rowA), "r"(BAR(stage)) : "memory");
-                    asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                                 ::"r"(sb0 + A_BYTES), "l"(&tm_dg), "r"(col), "r"(rowA + kc_rows), "r"(BAR(stage)) : "memory");
-                    if (has_h) {
-                        const int32_t rowH = (int32_t)(((m * a.T + (t - 1)) * 2) * hc_rows + (int)rank * (Nh / 8));
-                        for (int c = 0; c < Nh / 8; c += a.hc_box) {
-                            asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                                         ::"r"(sb0 + B_OFF + c * 1024), "l"(&tm_hc), "r"(col), "r"(rowH + c), "r"(BAR(stage)) : "memory");
-                            asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                                         ::"r"(sb0 + B_LO_OFF + c * 1024), "l"(&tm_hc), "r"(col), "r"(rowH + hc_rows + c), "r"(BAR(stage)) : "memory");
-                        }
-                    }
+                const size_t rowA = (size_t)((b * 2 + hlx) * kc_rows + kcA + kc);
+                ptx::tma_bulk_g2s(sb0 + hlx * A_BYTES + kc * 1024, dg8 + rowA * 2048 + half * 1024, 1024, BAR(stage));
+                if (has_b && kc < Nh / 8) {
+                    const size_t rowB = (size_t)((bsrc * 2 + hlx) * bk_rows + (int)rank * (Nh / 8) + kc);
+                    ptx::tma_bulk_g2s(sb0 + (hlx ? B_LO_OFF : B_OFF) + kc * 1024, b8 + rowB * 2048 + half * 1024, 1024, BAR(stage));
+                }
+                if (part == 0 && lane < 4) {
+                    const size_t rowO = (size_t)(b * 8 + (int)rank * 4 + lane);
+                    ptx::tma_bulk_g2s(sb0 + OH_OFF + lane * 1024, oh8 + rowO * 2048 + half * 1024, 1024, BAR(stage));
                 }
                 if (++stage == S) { stage = 0; phase ^= 1; }
             }
@@ -460,9 +466,6 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_dg, const __grid_constant__ 
             // MN-major no-swizzle operand [k-chunk (8 mn)][row (k)][16 B]: LBO = 128 B between 8-row k groups, SBO = 1024 B
             // between 8-element mn groups (tools/umma_probe.cu); a K=16 step = 16 rows = 256 B
             constexpr uint32_t DHI_MN = ptx::desc_hi(1024);
-            // MN-major SWIZZLE_128B operand (TMA gather image): panels of 64 mn [row (k)][128 B]: LBO = 8192 B panel stride,
-            // SBO = 1024 B between 8-row k groups; a K=16 step = 16 rows = 2048 B
-            constexpr uint32_t DHI_SW = ((1024u >> 4) & 0x3FFF) | (1u << 14) | (2u << 29);
             const uint32_t idesc_main = ptx::make_idesc_f16(1, 256, Nmain) | (1u << 15) | (1u << 16);
             const uint32_t idesc_oh = ptx::make_idesc_f16(1, 256, 64) | (1u << 15) | (1u << 16);
             bool first_main = true, first_oh = true;
@@ -483,18 +486,16 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_dg, const __grid_constant__ 
                     const uint32_t ah = ptx::desc_lo(sb0, 128), al = ptx::desc_lo(sb0 + A_BYTES, 128);
                     if (issue) {
                         if (has_main) {
-                            uint32_t bh, bl, bk16, bhi;
-                            if (part == 0) { bh = ptx::desc_lo(sb0 + B_OFF, 128); bl = ptx::desc_lo(sb0 + B_LO_OFF, 128); bk16 = 256u >> 4; bhi = DHI_MN; }
-                            else { bh = ptx::desc_lo(sb0 + B_OFF, 8192); bl = ptx::desc_lo(sb0 + B_LO_OFF, 8192); bk16 = 2048u >> 4; bhi = DHI_SW; }
+                            const uint32_t bh = ptx::desc_lo(sb0 + B_OFF, 128), bl = ptx::desc_lo(sb0 + B_LO_OFF, 128);
 #pragma unroll
                             for (int k = 0; k < 4; ++k)
-                                ptx::umma2_f16(tmem, ptx::desc_join(DHI_MN, ah + k * 16u), ptx::desc_join(bhi, bh + k * bk16), idesc_main, !(first_main && k == 0));
+                                ptx::umma2_f16(tmem, ptx::desc_join(DHI_MN, ah + k * 16u), ptx::desc_join(DHI_MN, bh + k * 16u), idesc_main, !(first_main && k == 0));
 #pragma unroll
                             for (int k = 0; k < 4; ++k)
-                                ptx::umma2_f16(tmem, ptx::desc_join(DHI_MN, al + k * 16u), ptx::desc_join(bhi, bh + k * bk16), idesc_main, 1);
+                                ptx::umma2_f16(tmem, ptx::desc_join(DHI_MN, al + k * 16u), ptx::desc_join(DHI_MN, bh + k * 16u), idesc_main, 1);
 #pragma unroll
                             for (int k = 0; k < 4; ++k)
-                                ptx::umma2_f16(tmem, ptx::desc_join(DHI_MN, ah + k * 16u), ptx::desc_join(bhi, bl + k * bk16), idesc_main, 1);
+                                ptx::umma2_f16(tmem, ptx::desc_join(DHI_MN, ah + k * 16u), ptx::desc_join(DHI_MN, bl + k * 16u), idesc_main, 1);
                             first_main = false;
                         }
                         if (part == 0) {
@@ -523,58 +524,6 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_dg, const __grid_constant__ 
                     ptx::mbar_arrive_cluster(remote + 8u * stage);
                     if (++stage == S) { stage = 0; phase ^= 1; }
                 }
-        }
-    } else if (warp == 2) {
-        // ===== part 1: TMA gather of the entity rows (lanes 0-15 own 4 consecutive rows each of the 64-row stage)
-        //       part 0: writer of the one-hot (type,relation) slice (this CTA's 32 combos; lane l owns rows 2l, 2l+1)
-        //       the stage's keys are one coalesced load, fetched one stage ahead =====
-        uint32_t stage = 0, phase = 0;
-        const int64_t n_stage = (b1 - b0) * 2;
-        int4 e_next = make_int4(0, 0, 0, 0);
-        int c_next0 = -1, c_next1 = -1;
-        auto fetch = [&](int64_t si) {
-            if (si >= n_stage) return;
-            const int64_t o0 = (b0 + (si >> 1)) * TILE_M + (si & 1) * WG_ROWS;
-            if (part == 1) { if (lane < 16) e_next = *reinterpret_cast<const int4*>(a.eid + o0 + lane * 4); }
-            else { const char2 cc = *reinterpret_cast<const char2*>(a.combo + o0 + lane * 2); c_next0 = cc.x; c_next1 = cc.y; }
-        };
-        fetch(0);
-        for (int64_t si = 0; si < n_stage; ++si) {
-            const int4 eid = e_next;
-            const int cb[2] = {c_next0, c_next1};
-            fetch(si + 1);
-            if (a.dbg) { long long t0 = clock64(); ptx::mbar_wait(BAR(S + stage), phase ^ 1); if (lane == 0 && leader) atomicAdd(a.dbg + 2, (unsigned long long)(clock64() - t0)); }
-            else ptx::mbar_wait(BAR(S + stage), phase ^ 1);
-            const uint32_t sb0 = ptx::smem_u32(smem + stage * STAGE_BYTES);
-            if (part == 1) {
-                if (lane < 16) {
-                    for (int pnl = 0; pnl < Nh / 64; ++pnl) {
-                        const int32_t col = ((int)rank * (Nh / 64) + pnl) * 64;
-                        const uint32_t off = pnl * 8192 + lane * 512;      // 4 rows x 128 B
-                        ptx::tma_gather4(sb0 + B_OFF + off, &tm_hi, col, eid.x, eid.y, eid.z, eid.w, BAR(stage));
-                        ptx::tma_gather4(sb0 + B_LO_OFF + off, &tm_lo, col, eid.x, eid.y, eid.z, eid.w, BAR(stage));
-                    }
-                }
-                __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(BAR(stage));
-            } else {
-#pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    const int rr = lane * 2 + q;
-                    const int combo = cb[q] < 0 ? -1 : cb[q] - (int)rank * 32;      // this CTA holds combos [rank*32, +32) as 4 k-chunks of 8
-#pragma unroll
-                    for (int kc = 0; kc < 4; ++kc) {
-                        uint32_t w[4] = {0u, 0u, 0u, 0u};
-                        if (combo >= 0 && combo < 32 && (combo >> 3) == kc) w[(combo & 7) >> 1] = 0x3F80u << (16 * (combo & 1));
-                        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(sb0 + OH_OFF + kc * (WG_ROWS * 16) + rr * 16),
-                                     "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
-                    }
-                }
-                ptx::fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(BAR(stage));
-            }
-            if (++stage == S) { stage = 0; phase ^= 1; }
         }
     } else if (warp >= 4) {
         // ===== epilogue: this CTA's 128 gate columns x (Nmain [+ 64]) -> partial buffer [split][part][gp][320] =====
@@ -613,7 +562,6 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_dg, const __grid_constant__ 
     ptx::cluster_sync();
     if (warp == 2) ptx::tmem_dealloc2(tmem, 512);
 }
-
 
 // fixed-order sum of the K-split partials into the flat gradient (accumulating, as accGradParameters does):
 //   part 0, n < N0        -> gWh[row(gp)][n]          part 0, n in [256, 320) -> gP[n - 256][gp] (temporary, overwritten)
@@ -862,21 +810,6 @@ bool tc_train_supported(const kprn_ctx* ctx) {
     return true;
 }
 
-static bool encode_2d_u32(CUtensorMap* tm, void* base, uint64_t rows, uint32_t box_rows) {
-    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-    void* fn = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) { cudaGetLastError(); return false; }
-    const cuuint64_t gdim[2] = {512, rows};                 // a k-chunk row = 128 path rows x 16 B = 512 uint32
-    const cuuint64_t gstride[1] = {2048};
-    const cuuint32_t box[2] = {256, box_rows};              // 64 path rows x box_rows k-chunks
-    const cuuint32_t estr[2] = {1, 1};
-    return reinterpret_cast<EncodeFn>(fn)(tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
 int tc_train_pack(kprn_ctx* ctx) {
     TcState* s = ctx->tc;
     TcTrain* tt = tt_get(ctx);
@@ -998,44 +931,33 @@ int tc_backward(kprn_ctx* ctx, float scale) {
         KPRN_LAUNCH_CHECK(ctx);
     }
     // ---- weight gradients ----
-    const int64_t dg_rows = ptiles * T * 2 * (G4 / 8), hc_rows = ptiles * T * 2 * (Hp / 8);
-    const int hc_box = (Hp / 16) < 16 ? (Hp / 16) : 16;
-    if (tt->tm_dg_base != tt->dgop.p || tt->tm_dg_rows != dg_rows) {
-        if (!encode_2d_u32(&tt->tm_dg, tt->dgop.p, (uint64_t)dg_rows, 16)) { set_error("tc backward: tensor map (dG) failed"); return KPRN_ECUDA; }
-        tt->tm_dg_base = tt->dgop.p; tt->tm_dg_rows = dg_rows;
-    }
-    if (tt->tm_hc_base != tt->hcache.p || tt->tm_hc_rows != hc_rows) {
-        if (!encode_2d_u32(&tt->tm_hc, tt->hcache.p, (uint64_t)hc_rows, (uint32_t)hc_box)) { set_error("tc backward: tensor map (h) failed"); return KPRN_ECUDA; }
-        tt->tm_hc_base = tt->hcache.p; tt->tm_hc_rows = hc_rows;
-    }
     {
-        KPRN_TRY(ensure(tt->step_eid, sizeof(int32_t) * (size_t)n_order));
-        KPRN_TRY(ensure(tt->step_combo, (size_t)n_order));
-        step_keys_kernel<<<(unsigned)cdiv(n_order, 256), 256, 0, ctx->stream>>>(ctx->d_ids, N, T, n_order, c.V_e, (int)c.V_t, (int)c.V_r,
-                                                                              tt->step_eid.as<int32_t>(), tt->step_combo.as<int8_t>());
+        const size_t xop_bytes = (size_t)nblocks * 2 * (KE / 8) * 2048, oh_bytes = (size_t)nblocks * 8 * 2048;
+        KPRN_TRY(ensure(tt->xop, xop_bytes));
+        KPRN_TRY(ensure(tt->ohop, oh_bytes));
+        prep_operands_kernel<<<(unsigned)nblocks, 128, 0, ctx->stream>>>(ctx->d_ids, N, T, c.V_e, (int)c.V_t, (int)c.V_r, s->E_hi, s->E_lo, KE,
+                                                                        tt->xop.as<bf16>(), tt->ohop.as<bf16>());
         KPRN_LAUNCH_CHECK(ctx);
         WgArgs wa;
-        wa.eid = tt->step_eid.as<int32_t>(); wa.combo = tt->step_combo.as<int8_t>(); wa.dbg = nullptr;
+        wa.dgop = tt->dgop.as<bf16>(); wa.hcache = tt->hcache.as<bf16>(); wa.xop = tt->xop.as<bf16>(); wa.ohop = tt->ohop.as<bf16>();
+        wa.dbg = nullptr;
         if (s->debug) {
             KPRN_TRY(ensure(tt->dbg, 8 * sizeof(unsigned long long)));
             KPRN_CUDA(cudaMemsetAsync(tt->dbg.p, 0, 8 * sizeof(unsigned long long), ctx->stream));
             wa.dbg = tt->dbg.as<unsigned long long>();
         }
-        wa.N = N; wa.T = T; wa.num_tiles = ptiles; wa.V_r = (int)c.V_r; wa.V_e = c.V_e; wa.V_t = (int)c.V_t;
-        wa.G4 = G4; wa.N0 = Hp; wa.KE = KE; wa.NOH = 1; wa.blocks_per_split = bps; wa.part = tt->wpart.as<float>(); wa.H_BYTES = TILE_M * Hp * 2;
-        wa.hc_box = hc_box; wa.dgop = tt->dgop.as<bf16>(); wa.hcache = tt->hcache.as<bf16>();
-        { const char* d = getenv("KPRN_WG_BULK"); wa.bulk1d = !(d && d[0] == '0'); }
-        const size_t wg_smem = (size_t)WG_STAGES * (2 * 16384 + 2 * 8192 * 2 + 4096) + 256;
+        wa.T = T; wa.num_tiles = ptiles; wa.G4 = G4; wa.N0 = Hp; wa.KE = KE; wa.blocks_per_split = bps; wa.part = tt->wpart.as<float>();
+        const size_t wg_smem = (size_t)WG_STAGES * (2 * 16384 + 2 * 16384 + 4096) + 256;
         KPRN_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wg_smem));
-        wgrad_kernel<<<dim3((unsigned)(items * 2), (unsigned)splits), WG_THREADS, wg_smem, ctx->stream>>>(tt->tm_dg, tt->tm_hc, s->tm_hi, s->tm_lo, wa);
+        wgrad_kernel<<<dim3((unsigned)(items * 2), (unsigned)splits), WG_THREADS, wg_smem, ctx->stream>>>(wa);
         KPRN_LAUNCH_CHECK(ctx);
         if (wa.dbg) {
             unsigned long long h[8];
             KPRN_CUDA(cudaMemcpyAsync(h, wa.dbg, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
             KPRN_CUDA(cudaStreamSynchronize(ctx->stream));
             const double np_ = (double)items * splits;
-            fprintf(stderr, "[kprn tc debug] wgrad: issuer cycles/pair %.0f | waits/pair: issuer.full %.0f, issuer.peer %.0f, gather|onehot.empty %.0f, "
-                            "producer.empty %.0f\n", h[4] / np_, h[0] / np_, h[1] / np_, h[2] / np_, h[3] / np_);
+            fprintf(stderr, "[kprn tc debug] wgrad: issuer cycles/pair %.0f | waits/pair: issuer.full %.0f, issuer.peer %.0f, producer.empty %.0f\n",
+                    h[4] / np_, h[0] / np_, h[1] / np_, h[3] / np_);
         }
     }
     float* gP = tt->gP.as<float>();
@@ -1064,7 +986,7 @@ void tc_train_destroy(kprn_ctx* ctx) {
     TcTrain* tt = s->tt;
     if (tt->WT) cudaFree(tt->WT);
     for (DBuf* b : {&tt->cache, &tt->hcache, &tt->dgop, &tt->dh, &tt->dc, &tt->wpart, &tt->gP, &tt->cls, &tt->dX, &tt->eg_keys, &tt->eg_vals,
-                    &tt->eg_tmp, &tt->eg_part, &tt->eg_flags, &tt->step_eid, &tt->step_combo, &tt->dbg})
+                    &tt->eg_tmp, &tt->eg_part, &tt->eg_flags, &tt->xop, &tt->ohop, &tt->dbg})
         if (b->p) { cudaFree(b->p); b->p = nullptr; b->cap = 0; }
     dedup_free(tt->es);
     delete tt;
