@@ -33,7 +33,7 @@ struct TcTrain {
     bf16* WT = nullptr;               // bgemm B operand: [part 2][ks G4/64][hi|lo][half 2][kc 8][n Nh][8]
     DBuf cache, hcache, dgop, dh, dc, wpart, gP, cls;
     DBuf dX, eg_keys, eg_vals, eg_tmp, eg_part, eg_flags;     // entity-gradient staging + sorted segment reduce
-    DBuf xop, ohop, dbg;              // gathered entity rows / one-hot slice in operand layout (prep_operands_kernel)
+    DBuf xop, hop, ohop, dbg;         // gathered entity rows / h / one-hot slice in the weight-gradient kernel's stage layout
     DedupBufs es;                     // distinct entity rows of the batch when the caller (a sparse training step) did not build them
 };
 
@@ -326,6 +326,71 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BG_THREADS, 1) bgemm
 // A = dgop read as an MN-major operand (M = gate column, K = path row): the bytes [kc][row][8] that bgemm reads K-major.
 // K is split over gridDim.y CTA pairs; each writes its partial tile, wgrad_reduce_kernel sums them in a fixed order.
 
+// Operands of the weight-gradient product, staged once per backward in the layout its stages consume.  A stage of
+// wgrad_kernel is 64 path rows; the TMA unit sustains roughly one contiguous segment per ~55 cycles per SM whatever its size
+// (measured: 64 one-kilobyte copies per stage made the kernel issue-bound), so everything that is free to choose its layout
+// is stored [(tile*T + t)][hi|lo][row half 2][kc][row 64][8 bf16]: the [kc][64 rows] tile of a stage is ONE contiguous copy.
+//   xop : the gathered entity rows x_e of every path-step (from the pre-split table), kc = KE/8
+//   hop : h_t re-laid out from the forward's hcache ([kc][row 128][8], which its own MMAs need), kc = Hp/8, t < T-1
+//   ohop: onehot(type*V_r + relation), 64 columns, exact in bf16 (hi only): [(tile*T + t)][row half][kc 8][row 64][8]
+// One block per (tile, t), one thread per path row.
+__global__ void __launch_bounds__(128) prep_operands_kernel(const int32_t* __restrict__ ids, int64_t N, int T, int64_t V_e, int V_t, int V_r,
+                                                            const bf16* __restrict__ E_hi, const bf16* __restrict__ E_lo, int KE,
+                                                            const bf16* __restrict__ hcache, int Hp,
+                                                            bf16* __restrict__ xop, bf16* __restrict__ hop, bf16* __restrict__ ohop) {
+    const int64_t b = blockIdx.x;                 // tile*T + t
+    const int r = threadIdx.x, rh = r >> 6, rr = r & 63;
+    const int64_t m = b / T;
+    const int t = (int)(b - m * T);
+    const int64_t n = m * TILE_M + r;
+    const bool live = n < N;
+    int64_t e = 0; int combo = -1;
+    if (live) {
+        const int32_t* idp = ids + (n * T + t) * 3;
+        e = (int64_t)idp[1] - 1;
+        e = e < 0 ? 0 : (e >= V_e ? V_e - 1 : e);
+        int ta = idp[0] - 1, rb = idp[2] - 1;
+        ta = ta < 0 ? 0 : (ta >= V_t ? V_t - 1 : ta);
+        rb = rb < 0 ? 0 : (rb >= V_r ? V_r - 1 : rb);
+        combo = ta * V_r + rb;
+    }
+    const int KC = KE / 8, KH = Hp / 8;
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    const uint4* sh = reinterpret_cast<const uint4*>(E_hi + e * KE);
+    const uint4* sl = reinterpret_cast<const uint4*>(E_lo + e * KE);
+    // 16-byte units: [(b*2 + hl)*2 + rh][kc][rr]
+    uint4* dxh = reinterpret_cast<uint4*>(xop) + ((size_t)((b * 2 + 0) * 2 + rh) * KC) * 64 + rr;
+    uint4* dxl = reinterpret_cast<uint4*>(xop) + ((size_t)((b * 2 + 1) * 2 + rh) * KC) * 64 + rr;
+    for (int kc = 0; kc < KC; ++kc) {             // a warp's store is 512 contiguous bytes
+        dxh[(size_t)kc * 64] = live ? sh[kc] : z;
+        dxl[(size_t)kc * 64] = live ? sl[kc] : z;
+    }
+    if (t < T - 1) {
+        const uint4* hs = reinterpret_cast<const uint4*>(hcache) + (size_t)(b * 2) * KH * TILE_M + r;
+        uint4* dhh = reinterpret_cast<uint4*>(hop) + ((size_t)((b * 2 + 0) * 2 + rh) * KH) * 64 + rr;
+        uint4* dhl = reinterpret_cast<uint4*>(hop) + ((size_t)((b * 2 + 1) * 2 + rh) * KH) * 64 + rr;
+        for (int kc = 0; kc < KH; ++kc) {
+            dhh[(size_t)kc * 64] = hs[(size_t)kc * TILE_M];
+            dhl[(size_t)kc * 64] = hs[(size_t)(KH + kc) * TILE_M];
+        }
+    }
+    uint4* doh = reinterpret_cast<uint4*>(ohop) + ((size_t)(b * 2 + rh) * 8) * 64 + rr;
+#pragma unroll
+    for (int kc = 0; kc < 8; ++kc) {
+        uint32_t w[4] = {0u, 0u, 0u, 0u};
+        if (combo >= 0 && (combo >> 3) == kc) w[(combo & 7) >> 1] = 0x3F80u << (16 * (combo & 1));      // bf16 1.0
+        doh[(size_t)kc * 64] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// wgrad: G[gp, n] = sum over path-steps of dG[step, gp] * B[step, n]  for one 256-row block of gate columns (128 per CTA of a
+// pair) and one operand family:
+//   part 0: B = [h_{t-1} (Hp columns) | onehot(type,relation) (64 columns)]   -> gWh and gP (two accumulators)
+//   part 1: B = x_e (KE columns, gathered with TMA tile::gather4 from the pre-split entity table) -> gWx[:, entity columns]
+// A = dgop read as an MN-major operand (M = gate column, K = path row): the bytes [kc][row][8] that bgemm reads K-major.
+// K is split over gridDim.y CTA pairs; each writes its partial tile, wgrad_reduce_kernel sums them in a fixed order.
+
 // Operands of the weight-gradient product that do not exist yet in operand layout, built once per backward:
 //   xop  [(tile*T + t)][hi|lo][kc KE/8][row 128][8] bf16 : the gathered entity rows x_e of every path-step (from the pre-split table)
 //   ohop [(tile*T + t)][kc 8][row 128][8] bf16            : onehot(type*V_r + relation), 64 columns (exact in bf16: hi only)
@@ -380,7 +445,7 @@ __global__ void __launch_bounds__(128) prep_operands_kernel(const int32_t* __res
 // wgrad_reduce_kernel sums them in a fixed order.
 
 struct WgArgs {
-    const bf16* dgop; const bf16* hcache; const bf16* xop; const bf16* ohop;
+    const bf16* dgop; const bf16* hop; const bf16* xop; const bf16* ohop;
     unsigned long long* dbg;                      // optional wait-cycle counters (KPRN_TC_DEBUG=1)
     int T; int64_t num_tiles;
     int G4, N0, KE;
@@ -427,10 +492,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WG_THREADS, 1) wgrad
     const long long dbg_t0 = clock64();
 
     if (warp == 0) {
-        // ===== TMA producer: lane = (hi|lo, k-chunk); one 1 KB bulk copy per lane and operand =====
+        // ===== TMA producer.  A (dG, the layout bgemm needs): lane = (hi|lo, k-chunk), one 1 KB bulk copy each; B (hop / xop)
+        //       and the one-hot slice come from the wgrad-layout copies: one contiguous copy per operand half =====
         uint32_t stage = 0, phase = 0;
         const uint8_t* dg8 = reinterpret_cast<const uint8_t*>(a.dgop);
-        const uint8_t* b8 = reinterpret_cast<const uint8_t*>(part ? a.xop : a.hcache);
+        const uint8_t* b8 = reinterpret_cast<const uint8_t*>(part ? a.xop : a.hop);
         const uint8_t* oh8 = reinterpret_cast<const uint8_t*>(a.ohop);
         const int hlx = lane >> 4, kc = lane & 15;
         for (int64_t b = b0; b < b1; ++b) {
@@ -447,13 +513,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WG_THREADS, 1) wgrad
                 const uint32_t sb0 = ptx::smem_u32(smem + stage * STAGE_BYTES);
                 const size_t rowA = (size_t)((b * 2 + hlx) * kc_rows + kcA + kc);
                 ptx::tma_bulk_g2s(sb0 + hlx * A_BYTES + kc * 1024, dg8 + rowA * 2048 + half * 1024, 1024, BAR(stage));
-                if (has_b && kc < Nh / 8) {
-                    const size_t rowB = (size_t)((bsrc * 2 + hlx) * bk_rows + (int)rank * (Nh / 8) + kc);
-                    ptx::tma_bulk_g2s(sb0 + (hlx ? B_LO_OFF : B_OFF) + kc * 1024, b8 + rowB * 2048 + half * 1024, 1024, BAR(stage));
+                if (has_b && lane < 2) {          // lane = hi | lo: [kc Nh/8][row 64][16 B] of this CTA's column half, contiguous
+                    const size_t off = ((size_t)((bsrc * 2 + lane) * 2 + half) * bk_rows + (size_t)rank * (Nh / 8)) * 1024;
+                    ptx::tma_bulk_g2s(sb0 + (lane ? B_LO_OFF : B_OFF), b8 + off, B_BYTES, BAR(stage));
                 }
-                if (part == 0 && lane < 4) {
-                    const size_t rowO = (size_t)(b * 8 + (int)rank * 4 + lane);
-                    ptx::tma_bulk_g2s(sb0 + OH_OFF + lane * 1024, oh8 + rowO * 2048 + half * 1024, 1024, BAR(stage));
+                if (part == 0 && lane == 2) {
+                    const size_t off = ((size_t)(b * 2 + half) * 8 + (size_t)rank * 4) * 1024;
+                    ptx::tma_bulk_g2s(sb0 + OH_OFF, oh8 + off, OH_BYTES, BAR(stage));
                 }
                 if (++stage == S) { stage = 0; phase ^= 1; }
             }
@@ -932,14 +998,16 @@ int tc_backward(kprn_ctx* ctx, float scale) {
     }
     // ---- weight gradients ----
     {
-        const size_t xop_bytes = (size_t)nblocks * 2 * (KE / 8) * 2048, oh_bytes = (size_t)nblocks * 8 * 2048;
+        const size_t xop_bytes = (size_t)nblocks * 2 * (KE / 8) * 2048, hop_bytes = (size_t)nblocks * 2 * (Hp / 8) * 2048, oh_bytes = (size_t)nblocks * 8 * 2048;
         KPRN_TRY(ensure(tt->xop, xop_bytes));
+        KPRN_TRY(ensure(tt->hop, hop_bytes));
         KPRN_TRY(ensure(tt->ohop, oh_bytes));
         prep_operands_kernel<<<(unsigned)nblocks, 128, 0, ctx->stream>>>(ctx->d_ids, N, T, c.V_e, (int)c.V_t, (int)c.V_r, s->E_hi, s->E_lo, KE,
-                                                                        tt->xop.as<bf16>(), tt->ohop.as<bf16>());
+                                                                        tt->hcache.as<bf16>(), Hp, tt->xop.as<bf16>(), tt->hop.as<bf16>(),
+                                                                        tt->ohop.as<bf16>());
         KPRN_LAUNCH_CHECK(ctx);
         WgArgs wa;
-        wa.dgop = tt->dgop.as<bf16>(); wa.hcache = tt->hcache.as<bf16>(); wa.xop = tt->xop.as<bf16>(); wa.ohop = tt->ohop.as<bf16>();
+        wa.dgop = tt->dgop.as<bf16>(); wa.hop = tt->hop.as<bf16>(); wa.xop = tt->xop.as<bf16>(); wa.ohop = tt->ohop.as<bf16>();
         wa.dbg = nullptr;
         if (s->debug) {
             KPRN_TRY(ensure(tt->dbg, 8 * sizeof(unsigned long long)));
@@ -986,7 +1054,7 @@ void tc_train_destroy(kprn_ctx* ctx) {
     TcTrain* tt = s->tt;
     if (tt->WT) cudaFree(tt->WT);
     for (DBuf* b : {&tt->cache, &tt->hcache, &tt->dgop, &tt->dh, &tt->dc, &tt->wpart, &tt->gP, &tt->cls, &tt->dX, &tt->eg_keys, &tt->eg_vals,
-                    &tt->eg_tmp, &tt->eg_part, &tt->eg_flags, &tt->xop, &tt->ohop, &tt->dbg})
+                    &tt->eg_tmp, &tt->eg_part, &tt->eg_flags, &tt->xop, &tt->hop, &tt->ohop, &tt->dbg})
         if (b->p) { cudaFree(b->p); b->p = nullptr; b->cap = 0; }
     dedup_free(tt->es);
     delete tt;
