@@ -34,6 +34,11 @@ struct TcTrain {
     DBuf cache, hcache, dgop, dh, dc, wpart, gP, cls;
     DBuf dX, eg_keys, eg_vals, eg_tmp, eg_part, eg_flags;     // entity-gradient staging + sorted segment reduce
     DBuf xop, hop, ohop, dbg;         // gathered entity rows / h / one-hot slice in the weight-gradient kernel's stage layout
+    // a second stream for the memory-bound side work of the backward (operand staging, entity-gradient segment reduce): it runs
+    // beside the tensor-bound kernels of the main stream; fork / join with events, so the caller's stream semantics are unchanged
+    cudaStream_t side = nullptr;
+    bool use_side = true;
+    cudaEvent_t ev_fork = nullptr, ev_loop = nullptr, ev_prep = nullptr, ev_eg = nullptr;
     DedupBufs es;                     // distinct entity rows of the batch when the caller (a sparse training step) did not build them
 };
 
@@ -914,6 +919,12 @@ int tc_backward(kprn_ctx* ctx, float scale) {
     float* gr = ctx->d_grads;
     const float* P = ctx->d_params;
     KPRN_TRY(tc_train_pack(ctx));
+    if (!tt->side) {
+        KPRN_CUDA(cudaStreamCreateWithFlags(&tt->side, cudaStreamNonBlocking));
+        for (cudaEvent_t* e : {&tt->ev_fork, &tt->ev_loop, &tt->ev_prep, &tt->ev_eg}) KPRN_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    }
+    { const char* d = getenv("KPRN_TC_SIDE"); tt->use_side = !(d && d[0] == '0'); }
+    cudaStream_t side = tt->use_side ? tt->side : ctx->stream;
     // ---- pool / head gradients on the fp32 kernels (kernels_simple.cu): ds_c[p], gbo[c], gWo[c,:] ----
     if (ctx->head_part4) {
         cls_logit_kernel<<<(unsigned)cdiv(N, 256), 256, 0, ctx->stream>>>(ctx->head_part4, ctx->head_npad, P + l.bo + (c.class_id - 1), N, c.L,
@@ -946,6 +957,19 @@ int tc_backward(kprn_ctx* ctx, float scale) {
         KPRN_TRY(dedup_build(ctx, tt->es, 1, ctx->d_ids, N, T, 0));
         eg_pos = tt->es.pos.as<uint32_t>(); eg_slot_of = tt->es.slot_of.as<uint32_t>(); eg_rows = tt->es.ids.as<int32_t>(); eg_target = gr + l.E_e;
     }
+    // ---- side stream: the weight-gradient kernel's operands (needs only the forward's outputs) ----
+    {
+        const size_t xop_bytes = (size_t)nblocks * 2 * (KE / 8) * 2048, hop_bytes = (size_t)nblocks * 2 * (Hp / 8) * 2048, oh_bytes = (size_t)nblocks * 8 * 2048;
+        KPRN_TRY(ensure(tt->xop, xop_bytes));
+        KPRN_TRY(ensure(tt->hop, hop_bytes));
+        KPRN_TRY(ensure(tt->ohop, oh_bytes));
+        if (tt->use_side) { KPRN_CUDA(cudaEventRecord(tt->ev_fork, ctx->stream)); KPRN_CUDA(cudaStreamWaitEvent(side, tt->ev_fork, 0)); }
+        prep_operands_kernel<<<(unsigned)nblocks, 128, 0, side>>>(ctx->d_ids, N, T, c.V_e, (int)c.V_t, (int)c.V_r, s->E_hi, s->E_lo, KE,
+                                                                  tt->hcache.as<bf16>(), Hp, tt->xop.as<bf16>(), tt->hop.as<bf16>(),
+                                                                  tt->ohop.as<bf16>());
+        KPRN_LAUNCH_CHECK(ctx);
+        if (tt->use_side) KPRN_CUDA(cudaEventRecord(tt->ev_prep, side));
+    }
     const size_t bg_smem = BG_STAGES * (2 * 16384 + 2 * 8 * (Hp / 2) * 16 + 2 * 8 * (KE / 2) * 16) + 256;
     KPRN_CUDA(cudaFuncSetAttribute(bgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bg_smem));
     const int64_t n_tp = (ptiles + 1) / 2;
@@ -964,20 +988,21 @@ int tc_backward(kprn_ctx* ctx, float scale) {
         bgemm_kernel<<<bg_grid, BG_THREADS, bg_smem, ctx->stream>>>(ba);
         KPRN_LAUNCH_CHECK(ctx);
     }
-    // ---- entity-table gradient: sorted segment reduce of the staged dX rows ----
+    // ---- entity-table gradient: sorted segment reduce of the staged dX rows (side stream, beside the weight-gradient kernel) ----
     {
+        if (tt->use_side) { KPRN_CUDA(cudaEventRecord(tt->ev_loop, ctx->stream)); KPRN_CUDA(cudaStreamWaitEvent(side, tt->ev_loop, 0)); }
         int end_bit = 1;
         while ((1ll << end_bit) <= n_order) ++end_bit;
         KPRN_TRY(ensure(tt->eg_keys, sizeof(uint32_t) * 2 * (size_t)n_order));
         KPRN_TRY(ensure(tt->eg_vals, sizeof(uint32_t) * 2 * (size_t)n_order));
         uint32_t* k_in = tt->eg_keys.as<uint32_t>(); uint32_t* k_out = k_in + n_order;
         uint32_t* v_in = tt->eg_vals.as<uint32_t>(); uint32_t* v_out = v_in + n_order;
-        eg_keys_kernel<<<(unsigned)cdiv(n_order, 256), 256, 0, ctx->stream>>>(eg_pos, eg_slot_of, n_order, k_in, v_in);
+        eg_keys_kernel<<<(unsigned)cdiv(n_order, 256), 256, 0, side>>>(eg_pos, eg_slot_of, n_order, k_in, v_in);
         KPRN_LAUNCH_CHECK(ctx);
         size_t tmp_bytes = 0;
-        KPRN_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k_in, k_out, v_in, v_out, (int)n_order, 0, end_bit, ctx->stream));
+        KPRN_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k_in, k_out, v_in, v_out, (int)n_order, 0, end_bit, side));
         KPRN_TRY(ensure(tt->eg_tmp, tmp_bytes));
-        KPRN_CUDA(cub::DeviceRadixSort::SortPairs(tt->eg_tmp.p, tmp_bytes, k_in, k_out, v_in, v_out, (int)n_order, 0, end_bit, ctx->stream));
+        KPRN_CUDA(cub::DeviceRadixSort::SortPairs(tt->eg_tmp.p, tmp_bytes, k_in, k_out, v_in, v_out, (int)n_order, 0, end_bit, side));
         ctx->launches += 4;
         EgArgs ea;
         ea.keys = k_out; ea.vals = v_out; ea.n = n_order; ea.n_chunks = cdiv(n_order, EG_CHUNK);
@@ -986,26 +1011,20 @@ int tc_backward(kprn_ctx* ctx, float scale) {
         KPRN_TRY(ensure(tt->eg_flags, sizeof(int32_t) * (size_t)ea.n_chunks * 4));
         ea.part = tt->eg_part.as<float>(); ea.flags = tt->eg_flags.as<int32_t>();
         if (c.d_e == 256) {
-            eg_reduce_kernel<2><<<(unsigned)cdiv(ea.n_chunks, 8), 256, 0, ctx->stream>>>(ea);
+            eg_reduce_kernel<2><<<(unsigned)cdiv(ea.n_chunks, 8), 256, 0, side>>>(ea);
             KPRN_LAUNCH_CHECK(ctx);
-            eg_fixup_kernel<2><<<(unsigned)ea.n_chunks, 512, 0, ctx->stream>>>(ea);
+            eg_fixup_kernel<2><<<(unsigned)ea.n_chunks, 512, 0, side>>>(ea);
         } else {        // d_e = 128 (tc_train_supported admits KE of 128 or 256 with d_e a multiple of 128)
-            eg_reduce_kernel<1><<<(unsigned)cdiv(ea.n_chunks, 8), 256, 0, ctx->stream>>>(ea);
+            eg_reduce_kernel<1><<<(unsigned)cdiv(ea.n_chunks, 8), 256, 0, side>>>(ea);
             KPRN_LAUNCH_CHECK(ctx);
-            eg_fixup_kernel<1><<<(unsigned)ea.n_chunks, 512, 0, ctx->stream>>>(ea);
+            eg_fixup_kernel<1><<<(unsigned)ea.n_chunks, 512, 0, side>>>(ea);
         }
         KPRN_LAUNCH_CHECK(ctx);
+        if (tt->use_side) KPRN_CUDA(cudaEventRecord(tt->ev_eg, side));
     }
     // ---- weight gradients ----
     {
-        const size_t xop_bytes = (size_t)nblocks * 2 * (KE / 8) * 2048, hop_bytes = (size_t)nblocks * 2 * (Hp / 8) * 2048, oh_bytes = (size_t)nblocks * 8 * 2048;
-        KPRN_TRY(ensure(tt->xop, xop_bytes));
-        KPRN_TRY(ensure(tt->hop, hop_bytes));
-        KPRN_TRY(ensure(tt->ohop, oh_bytes));
-        prep_operands_kernel<<<(unsigned)nblocks, 128, 0, ctx->stream>>>(ctx->d_ids, N, T, c.V_e, (int)c.V_t, (int)c.V_r, s->E_hi, s->E_lo, KE,
-                                                                        tt->hcache.as<bf16>(), Hp, tt->xop.as<bf16>(), tt->hop.as<bf16>(),
-                                                                        tt->ohop.as<bf16>());
-        KPRN_LAUNCH_CHECK(ctx);
+        if (tt->use_side) KPRN_CUDA(cudaStreamWaitEvent(ctx->stream, tt->ev_prep, 0));
         WgArgs wa;
         wa.dgop = tt->dgop.as<bf16>(); wa.hop = tt->hop.as<bf16>(); wa.xop = tt->xop.as<bf16>(); wa.ohop = tt->ohop.as<bf16>();
         wa.dbg = nullptr;
@@ -1045,6 +1064,7 @@ int tc_backward(kprn_ctx* ctx, float scale) {
     ptr_wx_kernel<<<(unsigned)G4, 256, 0, ctx->stream>>>(Tsum, Rsum, P + l.E_t, P + l.E_r, G4, c.H, l.D, c.d_t, c.d_e, c.d_r, (int)c.V_t, (int)c.V_r,
                                                         gr + l.Wx);
     KPRN_LAUNCH_CHECK(ctx);
+    if (tt->use_side) KPRN_CUDA(cudaStreamWaitEvent(ctx->stream, tt->ev_eg, 0));      // join: everything after sees the entity gradient
     return KPRN_OK;
 }
 
@@ -1053,6 +1073,11 @@ void tc_train_destroy(kprn_ctx* ctx) {
     if (!s || !s->tt) return;
     TcTrain* tt = s->tt;
     if (tt->WT) cudaFree(tt->WT);
+    if (tt->side) {
+        cudaStreamSynchronize(tt->side);
+        for (cudaEvent_t e : {tt->ev_fork, tt->ev_loop, tt->ev_prep, tt->ev_eg}) if (e) cudaEventDestroy(e);
+        cudaStreamDestroy(tt->side);
+    }
     for (DBuf* b : {&tt->cache, &tt->hcache, &tt->dgop, &tt->dh, &tt->dc, &tt->wpart, &tt->gP, &tt->cls, &tt->dX, &tt->eg_keys, &tt->eg_vals,
                     &tt->eg_tmp, &tt->eg_part, &tt->eg_flags, &tt->xop, &tt->hop, &tt->ohop, &tt->dbg})
         if (b->p) { cudaFree(b->p); b->p = nullptr; b->cap = 0; }
