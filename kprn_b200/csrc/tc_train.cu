@@ -323,14 +323,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BG_THREADS, 1) bgemm
 }
 
 
-// ---------------------------------------------------------------------------------------------
-// wgrad: G[gp, n] = sum over path-steps of dG[step, gp] * B[step, n]  for one 256-row block of gate columns (128 per CTA of a
-// pair) and one operand family:
-//   part 0: B = [h_{t-1} (Hp columns) | onehot(type,relation) (64 columns)]   -> gWh and gP (two accumulators)
-//   part 1: B = x_e (KE columns, gathered with TMA tile::gather4 from the pre-split entity table) -> gWx[:, entity columns]
-// A = dgop read as an MN-major operand (M = gate column, K = path row): the bytes [kc][row][8] that bgemm reads K-major.
-// K is split over gridDim.y CTA pairs; each writes its partial tile, wgrad_reduce_kernel sums them in a fixed order.
-
 // Operands of the weight-gradient product, staged once per backward in the layout its stages consume.  A stage of
 // wgrad_kernel is 64 path rows; the TMA unit sustains roughly one contiguous segment per ~55 cycles per SM whatever its size
 // (measured: 64 one-kilobyte copies per stage made the kernel issue-bound), so everything that is free to choose its layout
@@ -385,57 +377,6 @@ __global__ void __launch_bounds__(128) prep_operands_kernel(const int32_t* __res
         uint32_t w[4] = {0u, 0u, 0u, 0u};
         if (combo >= 0 && (combo >> 3) == kc) w[(combo & 7) >> 1] = 0x3F80u << (16 * (combo & 1));      // bf16 1.0
         doh[(size_t)kc * 64] = make_uint4(w[0], w[1], w[2], w[3]);
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// wgrad: G[gp, n] = sum over path-steps of dG[step, gp] * B[step, n]  for one 256-row block of gate columns (128 per CTA of a
-// pair) and one operand family:
-//   part 0: B = [h_{t-1} (Hp columns) | onehot(type,relation) (64 columns)]   -> gWh and gP (two accumulators)
-//   part 1: B = x_e (KE columns, gathered with TMA tile::gather4 from the pre-split entity table) -> gWx[:, entity columns]
-// A = dgop read as an MN-major operand (M = gate column, K = path row): the bytes [kc][row][8] that bgemm reads K-major.
-// K is split over gridDim.y CTA pairs; each writes its partial tile, wgrad_reduce_kernel sums them in a fixed order.
-
-// Operands of the weight-gradient product that do not exist yet in operand layout, built once per backward:
-//   xop  [(tile*T + t)][hi|lo][kc KE/8][row 128][8] bf16 : the gathered entity rows x_e of every path-step (from the pre-split table)
-//   ohop [(tile*T + t)][kc 8][row 128][8] bf16            : onehot(type*V_r + relation), 64 columns (exact in bf16: hi only)
-// so that wgrad_kernel streams every operand with plain bulk copies (a TMA tile::gather4 per use costs ~50-100 issue cycles per
-// 4 rows, which made the entity part of wgrad gather-issue-bound).  One block per (tile, t), one thread per path row.
-__global__ void __launch_bounds__(128) prep_operands_kernel(const int32_t* __restrict__ ids, int64_t N, int T, int64_t V_e, int V_t, int V_r,
-                                                            const bf16* __restrict__ E_hi, const bf16* __restrict__ E_lo, int KE,
-                                                            bf16* __restrict__ xop, bf16* __restrict__ ohop) {
-    const int64_t b = blockIdx.x;                 // tile*T + t
-    const int r = threadIdx.x;
-    const int64_t m = b / T;
-    const int t = (int)(b - m * T);
-    const int64_t n = m * TILE_M + r;
-    const bool live = n < N;
-    int64_t e = 0; int combo = -1;
-    if (live) {
-        const int32_t* idp = ids + (n * T + t) * 3;
-        e = (int64_t)idp[1] - 1;
-        e = e < 0 ? 0 : (e >= V_e ? V_e - 1 : e);
-        int ta = idp[0] - 1, rb = idp[2] - 1;
-        ta = ta < 0 ? 0 : (ta >= V_t ? V_t - 1 : ta);
-        rb = rb < 0 ? 0 : (rb >= V_r ? V_r - 1 : rb);
-        combo = ta * V_r + rb;
-    }
-    const int KC = KE / 8;
-    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-    const uint4* sh = reinterpret_cast<const uint4*>(E_hi + e * KE);
-    const uint4* sl = reinterpret_cast<const uint4*>(E_lo + e * KE);
-    uint4* dh = reinterpret_cast<uint4*>(xop + (size_t)(b * 2) * KC * TILE_M * 8) + r;
-    uint4* dl = dh + (size_t)KC * TILE_M;
-    for (int kc = 0; kc < KC; ++kc) {             // a warp's store is 512 contiguous bytes
-        dh[(size_t)kc * TILE_M] = live ? sh[kc] : z;
-        dl[(size_t)kc * TILE_M] = live ? sl[kc] : z;
-    }
-    uint4* doh = reinterpret_cast<uint4*>(ohop + (size_t)b * 8 * TILE_M * 8) + r;
-#pragma unroll
-    for (int kc = 0; kc < 8; ++kc) {
-        uint32_t w[4] = {0u, 0u, 0u, 0u};
-        if (combo >= 0 && (combo >> 3) == kc) w[(combo & 7) >> 1] = 0x3F80u << (16 * (combo & 1));      // bf16 1.0
-        doh[(size_t)kc * TILE_M] = make_uint4(w[0], w[1], w[2], w[3]);
     }
 }
 
