@@ -209,10 +209,7 @@ int kprn_allreduce_grads(kprn_ctx* ctx, int32_t average);               /* dense
 int kprn_allreduce_host_f64(kprn_ctx* ctx, double* vals, int64_t n, int32_t op_max);   /* loss / counters: n <= 64 host doubles, sum or max */
 
 /* engine knobs (no reference counterpart; they never change results).  Keys:
- *   "dedup"  1/0: project each distinct (type, entity, relation) step input once / every step (-1: KPRN_TC_DEDUP env, default on)
- *   "fp16_split" 1/0: the two 16-bit halves of every tensor-core operand are fp16 with per-tensor power-of-two scales / bf16
- *            (default bf16; set before the first forward).  fp16 halves carry 22 instead of 16 mantissa bits: agreement with the
- *            fp64 oracle improves 1.1-3x at 4-6 % lower throughput (the tensor core's fp32 accumulation is the limiter). */
+ *   "dedup"  1/0: project each distinct (type, entity, relation) step input once / every step (-1: KPRN_TC_DEDUP env, default on) */
 int kprn_set_option(kprn_ctx* ctx, const char* key, int64_t value);
 
 /* counters for bench.py: kernels launched by this library since the last reset */

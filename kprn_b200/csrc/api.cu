@@ -774,11 +774,6 @@ int kprn_train_batch_bpr(kprn_ctx* ctx, const int32_t* ids, const int32_t* seg, 
 int kprn_set_option(kprn_ctx* ctx, const char* key, int64_t value) {
     if (!ctx || !key) { set_error("null argument"); return KPRN_EINVAL; }
     if (!strcmp(key, "dedup")) { ctx->opt_dedup = value < 0 ? -1 : (value != 0); return KPRN_OK; }
-    if (!strcmp(key, "fp16_split")) {
-        if (ctx->tc) { set_error("set_option: fp16_split must be chosen before the first tensor-core forward"); return KPRN_ESTATE; }
-        ctx->opt_fp16 = value < 0 ? -1 : (value != 0);
-        return KPRN_OK;
-    }
     set_error("set_option: unknown key '%s'", key);
     return KPRN_EINVAL;
 }

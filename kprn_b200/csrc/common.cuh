@@ -87,8 +87,6 @@ struct kprn_ctx {
     const uint32_t* sparse_slot_of = nullptr;
     bool in_train_step = false;
     double* last_loss = nullptr;    // device scalar of the last training step's loss
-    int opt_fp16 = -1;                  // kprn_set_option("fp16_split"): operand halves fp16 (1) or bf16 (0); -1 = KPRN_TC_FP16 env / bf16; read when
-                                        // the tensor-core state is created (first forward)
     int opt_dedup = -1;                 // kprn_set_option("dedup"): -1 = KPRN_TC_DEDUP / default (on), 0 / 1 = forced
 };
 

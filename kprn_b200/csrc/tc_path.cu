@@ -1218,11 +1218,7 @@ int tc_forward(kprn_ctx* ctx, const int32_t* d_ids, const int32_t* d_seg, int64_
         s->num_sms = prop.multiProcessorCount;
         { const char* d = getenv("KPRN_TC_DEBUG"); s->debug = d && d[0] == '1'; }
         { const char* d = getenv("KPRN_TC_RECUR_PAIRS"); s->recur_pairs = !(d && d[0] == '0'); }
-        // operand halves: bf16 (default: no range management) or fp16 with per-tensor scales (KPRN_TC_FP16=1 /
-        // kprn_set_option("fp16_split", 1)).  Measured: fp16 halves (22 mantissa bits instead of 16) improve the agreement with the
-        // fp64 oracle only 1.1-3x (path logits 4-9e-6 -> 1.5-4e-6, entity-table gradient 3.2e-4 -> 2.8e-4) at 4-6 % lower
-        // throughput: what limits the agreement is the tensor core's own fp32 accumulation, not the split.
-        { const char* d = getenv("KPRN_TC_FP16"); s->fmt = ctx->opt_fp16 >= 0 ? (ctx->opt_fp16 ? FMT_F16 : FMT_BF16) : ((d && d[0] == '1') ? FMT_F16 : FMT_BF16); }
+        { const char* d = getenv("KPRN_TC_FP16"); s->fmt = (d && d[0] == '0') ? FMT_BF16 : FMT_F16; }
         if (prop.major != 10) {
             delete ctx->tc; ctx->tc = nullptr;      // a retry must meet this check again
             set_error("tensor-core path needs sm_100 (found sm_%d%d)", prop.major, prop.minor);

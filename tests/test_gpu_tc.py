@@ -132,32 +132,3 @@ def test_tc_training_forward_backward_match_oracle(kw):
     for name in o.shapes():
         assert_rel(o.view(g, name), o.view(g_ref, name), rtol=5e-4, what="grad " + name)
     e.close()
-
-
-def test_fp16_operand_halves_option():
-    """kprn_set_option("fp16_split", 1): the operand halves are fp16 with per-tensor power-of-two scales (22 instead of 16 mantissa
-    bits) -- scoring and the tensor-core training step still match the oracle, a little closer than with bf16 halves."""
-    kw = dict(N=900, seed=34, d_t=32, d_e=256, d_r=32, H=256, V_e=5000)
-    o, params, ids, seg, labels = make_case(**kw)
-    ref = o.forward(params, ids, seg, cache=True)
-    loss_ref, dsc = o.bce(ref["scores"], labels)
-    g_ref = o.backward(params, ids, seg, ref, dsc)
-    errs = {}
-    for fp16 in (1, 0):
-        e = engine_for(o, precision=3)
-        e.set_option("fp16_split", fp16)
-        e.set_params(params)
-        scores, logits = e.forward(ids, seg, want_logits=True)
-        errs[fp16] = assert_rel(e.path_logits(ids.shape[0]), ref["path_logits"], what="path_logits")
-        assert_rel(scores, ref["scores"], what="scores")
-        e.zero_grad()
-        e.forward(ids, seg, train=True)
-        e.loss_bce(labels)
-        e.backward()
-        g = e.get_grads()
-        for name in o.shapes():
-            assert_rel(o.view(g, name), o.view(g_ref, name), rtol=5e-4, what="grad " + name)
-        with pytest.raises(Exception):
-            e.set_option("fp16_split", 1 - fp16)         # fixed once the tensor-core state exists
-        e.close()
-    assert errs[1] <= errs[0] * 1.5
