@@ -163,8 +163,7 @@ int loss_bce_device(kprn_ctx* ctx, const float* d_labels, int64_t S, double** d_
 int loss_bpr_device(kprn_ctx* ctx, const int32_t* d_pos, const int32_t* d_neg, int64_t n_pairs, int on_logits, double** d_loss_out);
 int backward_device(kprn_ctx* ctx, float scale);
 int host_to_device(kprn_ctx* ctx, void* dst, const void* src, size_t bytes, size_t stage_off);
-// the packed 16-bit copies of the entity table when they mirror the fp32 table (else nulls), their split format and scale
-void tc_packed_entity(kprn_ctx* ctx, __nv_bfloat16** hi, __nv_bfloat16** lo, int* KE, int* fmt, const float** scale);
+void tc_packed_entity(kprn_ctx* ctx, __nv_bfloat16** hi, __nv_bfloat16** lo, int* KE);   // valid packed bf16 entity tables, or nulls
 
 // ---- sparse training step (train.cu) ----
 int train_note_dense_step(kprn_ctx* ctx, float step);

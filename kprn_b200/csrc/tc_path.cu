@@ -50,80 +50,15 @@ bool tc_validates_ids(const kprn_ctx* ctx, int64_t N) {
 // parameter packing (runs when the parameters change)
 
 __global__ void split_entity_kernel(const float* __restrict__ E, int64_t V, int d_e, int KE, bf16* __restrict__ hi,
-                                    bf16* __restrict__ lo, int fmt, const float* __restrict__ sc) {
+                                    bf16* __restrict__ lo) {
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= V * KE) return;
     int64_t row = idx / KE;
     int k = (int)(idx % KE);
-    float v = k < d_e ? E[row * d_e + k] * sc[SC_E] : 0.f;
+    float v = k < d_e ? E[row * d_e + k] : 0.f;
     bf16 h, l;
-    split16(v, fmt, h, l);
+    split_bf16(v, h, l);
     hi[idx] = h; lo[idx] = l;
-}
-// max |x| over a range -> *out (float bits are monotone for non-negative values: integer atomicMax)
-__global__ void absmax_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ out) {
-    float m = 0.f;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) m = fmaxf(m, fabsf(x[i]));
-    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(out), __float_as_int(m));
-}
-// power of two s with max * s in [target/2, target]  (1 for an all-zero tensor)
-__device__ __forceinline__ float pow2_scale(float amax, float target) {
-    if (!(amax > 0.f)) return 1.f;
-    int e;
-    frexpf(target / amax, &e);                  // target/amax = f * 2^e, f in [0.5, 1)
-    e -= 1;
-    e = e < -60 ? -60 : (e > 60 ? 60 : e);
-    return ldexpf(1.f, e);
-}
-// Per-tensor scales of FMT_F16 (one block).  max|Wx_e * gs|, max|Wh * gs|, max|P_tr * gs| are taken here (small tensors);
-// max|E| comes from the last full split of the entity table (sc[SC_EMAX]).  Constraint: the one-hot value
-// SC_OH = SC_E * SC_WXE / SC_P must itself be a finite fp16, so SC_WXE is lowered when the table P is large.
-__global__ void tc_scales_kernel(const float* __restrict__ P, Layout l, int d_t, int d_e, int H, int G, const float* __restrict__ Ptr, int ncombo,
-                                 int G4, int fmt, float* __restrict__ sc) {
-    __shared__ float red[4][32];
-    float m_wx = 0.f, m_wh = 0.f, m_p = 0.f, m_wxr = 0.f, m_whr = 0.f;
-    const float gs_max = 2.8853900817779268f, gs_min = 1.4426950408889634f;
-    for (int64_t i = threadIdx.x; i < (int64_t)G * d_e; i += blockDim.x) {
-        const int row = (int)(i / d_e), k = (int)(i % d_e);
-        const float v = fabsf(P[l.Wx + (int64_t)row * l.D + d_t + k]);
-        m_wxr = fmaxf(m_wxr, v);
-        m_wx = fmaxf(m_wx, v * ((row / H) == 1 ? gs_max : gs_min));
-    }
-    for (int64_t i = threadIdx.x; i < (int64_t)G * H; i += blockDim.x) {
-        const int row = (int)(i / H);
-        const float v = fabsf(P[l.Wh + i]);
-        m_whr = fmaxf(m_whr, v);
-        m_wh = fmaxf(m_wh, v * ((row / H) == 1 ? gs_max : gs_min));
-    }
-    for (int64_t i = threadIdx.x; i < (int64_t)ncombo * G4; i += blockDim.x) m_p = fmaxf(m_p, fabsf(Ptr[i]) * gs_max);
-    float vals[5] = {m_wx, m_wh, m_p, m_wxr, m_whr};
-    for (int q = 0; q < 5; ++q) {
-        float m = vals[q];
-        for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-        vals[q] = m;
-    }
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    __shared__ float wred[5][32];
-    if (lane == 0) for (int q = 0; q < 5; ++q) wred[q][w] = vals[q];
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const int nw = blockDim.x >> 5;
-        for (int q = 0; q < 5; ++q) { float m = 0.f; for (int i = 0; i < nw; ++i) m = fmaxf(m, wred[q][i]); vals[q] = m; }
-        if (fmt == FMT_BF16) {
-            for (int i = 0; i < SC_EMAX; ++i) sc[i] = 1.f;
-        } else {
-            const float target = 2048.f;                   // 2^11: 32x headroom below the fp16 maximum
-            float sE = pow2_scale(sc[SC_EMAX], target), sWx = pow2_scale(vals[0], target), sP = pow2_scale(vals[2], target);
-            while (sE * sWx / sP > 16384.f) sWx *= 0.5f;   // keep the one-hot value finite in fp16
-            while (sE * sWx / sP < 1.f / 8192.f) sP *= 0.5f;
-            sc[SC_E] = sE; sc[SC_WXE] = sWx; sc[SC_P] = sP; sc[SC_OH] = sE * sWx / sP; sc[SC_INV_PROJ] = 1.f / (sE * sWx);
-            const float sWh = pow2_scale(vals[1], target);
-            sc[SC_WH] = sWh; sc[SC_H] = 8192.f; sc[SC_INV_RECUR] = 1.f / (8192.f * sWh);
-            sc[SC_WT0] = pow2_scale(vals[4], target); sc[SC_WT1] = pow2_scale(vals[3], target);
-        }
-    }
-    (void)red;
 }
 
 // The recurrent kernel evaluates the gates as sigmoid(x) = 1/(1+2^(-x log2 e)) and tanh(x) = 1 - 2/(1+2^(2x log2 e)) with
@@ -138,8 +73,7 @@ __device__ __forceinline__ float gate_scale(int gp) {
 //   s <  KSe : Wx[:, d_t : d_t+d_e]  (entity columns of the input projection)
 //   s >= KSe : P_tr^T, the hoisted (type,relation) table, multiplied by a one-hot k-slice of the A tile
 __global__ void pack_wxe_kernel(const float* __restrict__ Wx, const float* __restrict__ Ptr, int H, int D, int d_t, int d_e,
-                                int NCH, int KSe, int NS, int ncombo, int G4, int k_off, bf16* __restrict__ out, int fmt,
-                                const float* __restrict__ sc) {
+                                int NCH, int KSe, int NS, int ncombo, int G4, int k_off, bf16* __restrict__ out) {
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t total = (int64_t)NCH * NS * B_SLAB_ELEMS;
     if (idx >= total) return;
@@ -153,14 +87,14 @@ __global__ void pack_wxe_kernel(const float* __restrict__ Wx, const float* __res
     float v;
     if (s < KSe) {
         int k = k_off + s * 64 + kc * 8 + e;
-        v = (u < H && k < d_e) ? Wx[(int64_t)row * D + d_t + k] * sc[SC_WXE] : 0.f;
+        v = (u < H && k < d_e) ? Wx[(int64_t)row * D + d_t + k] : 0.f;
     } else {
         int combo = (s - KSe) * 64 + kc * 8 + e;
-        v = combo < ncombo ? Ptr[(int64_t)combo * G4 + gp] * sc[SC_P] : 0.f;
+        v = combo < ncombo ? Ptr[(int64_t)combo * G4 + gp] : 0.f;
     }
     v *= gate_scale(gp);
     bf16 h, l;
-    split16(v, fmt, h, l);
+    split_bf16(v, h, l);
     int64_t base = slab * 2 * B_SLAB_ELEMS + ((kc * 128 + n) << 3) + e;
     out[base] = h;
     out[base + B_SLAB_ELEMS] = l;
@@ -168,8 +102,7 @@ __global__ void pack_wxe_kernel(const float* __restrict__ Wx, const float* __res
 
 // recur B operand: Wh -> slabs [chunk][kslice][hi|lo][kc 8][n 128][8]
 // pair = 1: each slab is stored as two 64-column halves [half][kc 8][n 64][8] (one contiguous 8 KB piece per CTA of a pair)
-__global__ void pack_wh_kernel(const float* __restrict__ Wh, int H, int NCH, int KSh, int pair, bf16* __restrict__ out, int fmt,
-                               const float* __restrict__ sc) {
+__global__ void pack_wh_kernel(const float* __restrict__ Wh, int H, int NCH, int KSh, int pair, bf16* __restrict__ out) {
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t total = (int64_t)NCH * KSh * B_SLAB_ELEMS;
     if (idx >= total) return;
@@ -180,9 +113,9 @@ __global__ void pack_wh_kernel(const float* __restrict__ Wh, int H, int NCH, int
     int s = (int)(slab % KSh), j = (int)(slab / KSh);
     int gp = j * 128 + n, k = s * 64 + kc * 8 + e, u;
     int row = perm_to_row(gp, H, u);
-    float v = (u < H && k < H) ? Wh[(int64_t)row * H + k] * gate_scale(gp) * sc[SC_WH] : 0.f;
+    float v = (u < H && k < H) ? Wh[(int64_t)row * H + k] * gate_scale(gp) : 0.f;
     bf16 h, l;
-    split16(v, fmt, h, l);
+    split_bf16(v, h, l);
     int64_t within = pair ? (int64_t)(n >> 6) * (B_SLAB_ELEMS / 2) + ((kc * 64 + (n & 63)) << 3) + e : ((kc * 128 + n) << 3) + e;
     int64_t base = slab * 2 * B_SLAB_ELEMS + within;
     out[base] = h;
@@ -231,7 +164,6 @@ struct ProjArgs {
     const int32_t* n_dev;      // when set: the row count lives on the device (distinct step inputs, see dedup below); T is 1
     int k_base;                // first entity column of this launch (d_e > 256 runs as two launches over column halves)
     int accumulate;            // the epilogue adds to XW (second half) instead of storing
-    int fmt; const float* sc;  // operand split format and the per-tensor scales (tc_state.cuh)
 };
 
 // the projection of a deduplicated step list learns its size on the device (no host round trip): N = *n_dev rows, T = 1
@@ -289,7 +221,7 @@ proj3_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ 
     const int64_t my_tiles = pair < n_tp ? (n_tp - pair + npairs - 1) / npairs : 0;
     auto tile_of = [&](int64_t it) { int64_t m = 2 * (pair + it * npairs) + rank; return m < a.num_tiles ? m : a.num_tiles - 1; };
     const int NP = a.NCH / 2;
-    const uint32_t idesc = ptx::make_idesc_f16(a.fmt, 256, 256);
+    const uint32_t idesc = ptx::make_idesc_f16(1, 256, 256);
     const int parts = a.passes == 3 ? 2 : 1;
 
     if (warp == 0) {
@@ -380,7 +312,6 @@ proj3_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ 
         // ===== TMA gather warp: lane l owns rows 4l..4l+3 of this CTA's tile =====
         const uint32_t dHi = ptx::smem_u32(sA_hi), dLo = ptx::smem_u32(sA_lo);
         const uint32_t afull_leader = ptx::mapa(BAR(B_AFULL), 0);
-        const uint32_t oh_bits = bits16(a.sc[SC_OH], a.fmt);      // SC_OH * SC_P = SC_E * SC_WXE: one accumulator scale for all slices
         int32_t eid[4];
         int combo[4];
         auto load_ids = [&](int64_t it) {
@@ -418,7 +349,7 @@ proj3_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ 
 #pragma unroll
                         for (int kc = 0; kc < 8; ++kc) {
                             uint32_t w[4] = {0u, 0u, 0u, 0u};
-                            if ((combo[b] >> 3) == o * 8 + kc) w[(combo[b] & 7) >> 1] = oh_bits << (16 * (combo[b] & 1));   // the one-hot value
+                            if ((combo[b] >> 3) == o * 8 + kc) w[(combo[b] & 7) >> 1] = 0x3F80u << (16 * (combo[b] & 1));   // bf16 1.0
                             asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dHi + (s * 8 + kc) * 2048 + r * 16),
                                          "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
                         }
@@ -446,7 +377,6 @@ proj3_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ 
         const int q4 = warp & 3;
         const int r = q4 * 32 + lane;
         const uint32_t acce_leader = ptx::mapa(BAR(B_ACCE), 0);
-        const float inv = a.sc[SC_INV_PROJ];
         const int64_t total_uses = my_tiles * NP;
         for (int64_t au = wg; au < total_uses; au += 2) {
             const int64_t it = au / NP;
@@ -463,8 +393,6 @@ proj3_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ 
                 float v[32];
                 ptx::tmem_ld32(tbase + blk * 32, v);
                 ptx::tc_wait_ld();
-#pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] *= inv;          // exact: a power of two (1 in FMT_BF16)
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     float* dstp = xw + (int64_t)(blk * 4 + i) * TILE_M * 8;
@@ -518,13 +446,28 @@ struct RecurArgs {
     //   hcache [tile][t][hi|lo][kc Hp/8][row 128][8] bf16: h_t in the UMMA operand layout (what the next step's MMAs read, and the
     //          B operand of the weight-gradient product dG^T h_{t-1}); replaces the per-CTA scratch
     float* cache; bf16* hcache;
-    int fmt; const float* sc;       // operand split format and the per-tensor scales (tc_state.cuh)
 };
 
 __device__ __forceinline__ float ex2f(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcpf(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 __device__ __forceinline__ float fast_tanh(float x) { return 1.f - __fdividef(2.f, __expf(2.f * x) + 1.f); }
+
+__device__ __forceinline__ void pack_split8(const float* v, uint4& hi, uint4& lo) {
+    uint32_t wh[4], wl[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        // packed cvt.rn.bf16x2.f32 for the hi pair, exact fp32 residuals, packed conversion for the lo pair
+        const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h2);
+        const float r0 = v[2 * i] - __uint_as_float(hb << 16), r1 = v[2 * i + 1] - __uint_as_float(hb & 0xFFFF0000u);
+        const __nv_bfloat162 l2 = __floats2bfloat162_rn(r0, r1);
+        wh[i] = hb;
+        wl[i] = *reinterpret_cast<const uint32_t*>(&l2);
+    }
+    hi = make_uint4(wh[0], wh[1], wh[2], wh[3]);
+    lo = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+}
 
 // recur_kernel<HP, PAIR, TRAIN>.  PAIR = true: launched as clusters of two CTAs (cta_group::2).  Each CTA still owns one 128-path
 // tile (its own h in shared memory, c and accumulators in its own TMEM, its own epilogue), but one MMA multiplies both
@@ -594,7 +537,7 @@ __global__ void __launch_bounds__(RECUR_THREADS, 1) recur_kernel(RecurArgs a) {
         return m < a.num_tiles ? m : a.num_tiles - 1;
     };
     const int T = a.T;
-    const uint32_t idesc = ptx::make_idesc_f16(a.fmt, PAIR ? 2 * TILE_M : TILE_M, 128);
+    const uint32_t idesc = ptx::make_idesc_f16(1, PAIR ? 2 * TILE_M : TILE_M, 128);
     const int slabs_per_k = a.passes == 3 ? 2 : 1;
     uint8_t* const scratch0 = reinterpret_cast<uint8_t*>(a.hscratch) + (size_t)blockIdx.x * 2 * H_BYTES;   // [hi | lo] image of sH
     // where h_t of (tile, t) lives in global memory: the per-CTA L2-resident scratch, or (training) its slot of the h cache
@@ -741,8 +684,6 @@ __global__ void __launch_bounds__(RECUR_THREADS, 1) recur_kernel(RecurArgs a) {
         const uint32_t acce_leader = PAIR ? ptx::mapa(BAR(B_ACCE), 0) : BAR(B_ACCE);
         const bool h_vec4 = (a.H & 3) == 0;
         const bool wo_vec4 = h_vec4 && (reinterpret_cast<uintptr_t>(a.wo) & 15) == 0;    // the flat parameter vector aligns nothing
-        const float s_h = a.sc[SC_H], inv_r = a.sc[SC_INV_RECUR];
-        const uint64_t inv2 = ptx::pack2(inv_r, inv_r);
         uint32_t ug0 = 0, ug1 = 0;
         // XW of (chunk j, this sub-block), gate q: the 8 columns j*128 + q*32 + sb*8 .. +7 = column group j*16 + q*4 + sb.
         // XW layout [tile][column group (4Hp/8)][row 128][8 floats]: the two 128-bit loads of a thread share one 32-byte sector
@@ -807,11 +748,11 @@ __global__ void __launch_bounds__(RECUR_THREADS, 1) recur_kernel(RecurArgs a) {
                         }
                         ++ug;
 #pragma unroll
-                        for (int e = 0; e < 8; e += 2) {      // pre-activation = XW + accumulator / (s_h s_Wh)
-                            ptx::unpack2(ptx::fma2(ptx::pack2(ai[e], ai[e + 1]), inv2, ptx::pack2(xc[e], xc[e + 1])), xc[e], xc[e + 1]);
-                            ptx::unpack2(ptx::fma2(ptx::pack2(ag[e], ag[e + 1]), inv2, ptx::pack2(xc[8 + e], xc[9 + e])), xc[8 + e], xc[9 + e]);
-                            ptx::unpack2(ptx::fma2(ptx::pack2(af[e], af[e + 1]), inv2, ptx::pack2(xc[16 + e], xc[17 + e])), xc[16 + e], xc[17 + e]);
-                            ptx::unpack2(ptx::fma2(ptx::pack2(ao[e], ao[e + 1]), inv2, ptx::pack2(xc[24 + e], xc[25 + e])), xc[24 + e], xc[25 + e]);
+                        for (int e = 0; e < 8; e += 2) {
+                            ptx::unpack2(ptx::add2(ptx::pack2(xc[e], xc[e + 1]), ptx::pack2(ai[e], ai[e + 1])), xc[e], xc[e + 1]);
+                            ptx::unpack2(ptx::add2(ptx::pack2(xc[8 + e], xc[9 + e]), ptx::pack2(ag[e], ag[e + 1])), xc[8 + e], xc[9 + e]);
+                            ptx::unpack2(ptx::add2(ptx::pack2(xc[16 + e], xc[17 + e]), ptx::pack2(af[e], af[e + 1])), xc[16 + e], xc[17 + e]);
+                            ptx::unpack2(ptx::add2(ptx::pack2(xc[24 + e], xc[25 + e]), ptx::pack2(ao[e], ao[e + 1])), xc[24 + e], xc[25 + e]);
                         }
                     } else {
 #pragma unroll
@@ -860,10 +801,7 @@ __global__ void __launch_bounds__(RECUR_THREADS, 1) recur_kernel(RecurArgs a) {
                     ptx::tmem_st8(cst + sb * 8, cn);
                     if (!last) {
                         uint4 hi, lo;
-                        float hs[8];
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) hs[e] = hv[e] * s_h;
-                        split16x8(hs, a.fmt, hi, lo);
+                        pack_split8(hv, hi, lo);
                         const int kc = 4 * j + sb;
                         *reinterpret_cast<uint4*>(scratch + kc * 2048 + r * 16) = hi;
                         *reinterpret_cast<uint4*>(scratch + H_BYTES + kc * 2048 + r * 16) = lo;
@@ -1132,41 +1070,28 @@ static int tc_pack(kprn_ctx* ctx) {
         }
         s->have_tmaps = make_entity_tensor_maps(s, c.V_e);
     }
-    if (!s->scales) {
-        KPRN_CUDA(cudaMalloc(&s->scales, sizeof(float) * SC_COUNT));
-        KPRN_CUDA(cudaMemsetAsync(s->scales, 0, sizeof(float) * SC_COUNT, ctx->stream));
-    }
-    // hoisted table first (fp32), then the per-tensor scales (they look at it), then the packed operands
-    ptr_table_kernel<<<(unsigned)s->G4, 128, 0, ctx->stream>>>(ctx->d_params, l, c.d_t, c.d_e, c.d_r, c.H, (int)c.V_t, (int)c.V_r, s->G4, s->Ptr);
-    KPRN_LAUNCH_CHECK(ctx);
-    if (full && s->fmt == FMT_F16) {        // the entity table's scale follows its magnitude at every full split
-        KPRN_CUDA(cudaMemsetAsync(s->scales + SC_EMAX, 0, sizeof(float), ctx->stream));
-        absmax_kernel<<<148 * 8, 256, 0, ctx->stream>>>(ctx->d_params + l.E_e, (int64_t)c.V_e * c.d_e, s->scales + SC_EMAX);
-        KPRN_LAUNCH_CHECK(ctx);
-    }
-    tc_scales_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->d_params, l, c.d_t, c.d_e, c.H, 4 * c.H, s->Ptr, (int)(c.V_t * c.V_r), s->G4, s->fmt, s->scales);
-    KPRN_LAUNCH_CHECK(ctx);
     if (full) {
         int64_t ne = c.V_e * (int64_t)s->KE;
-        split_entity_kernel<<<(unsigned)cdiv(ne, 256), 256, 0, ctx->stream>>>(ctx->d_params + l.E_e, c.V_e, c.d_e, s->KE, s->E_hi, s->E_lo, s->fmt, s->scales);
+        split_entity_kernel<<<(unsigned)cdiv(ne, 256), 256, 0, ctx->stream>>>(ctx->d_params + l.E_e, c.V_e, c.d_e, s->KE, s->E_hi, s->E_lo);
         KPRN_LAUNCH_CHECK(ctx);
     }
     if (s->Hp > 256) {      // per-step recurrence (tc_wide.cu): 256-column blocks x 64-wide k slices; same byte count as the slab form
-        KPRN_TRY(pack_wh_wide(ctx, ctx->d_params + l.Wh, c.H, s->Hp, s->Wh, s->fmt, s->scales));
+        KPRN_TRY(pack_wh_wide(ctx, ctx->d_params + l.Wh, c.H, s->Hp, s->Wh));
     } else {
         int64_t nh = (int64_t)s->NCH * s->KSh * B_SLAB_ELEMS;
-        pack_wh_kernel<<<(unsigned)cdiv(nh, 256), 256, 0, ctx->stream>>>(ctx->d_params + l.Wh, c.H, s->NCH, s->KSh, s->recur_pairs ? 1 : 0, s->Wh,
-                                                                         s->fmt, s->scales);
+        pack_wh_kernel<<<(unsigned)cdiv(nh, 256), 256, 0, ctx->stream>>>(ctx->d_params + l.Wh, c.H, s->NCH, s->KSh, s->recur_pairs ? 1 : 0, s->Wh);
         KPRN_LAUNCH_CHECK(ctx);
     }
+    ptr_table_kernel<<<(unsigned)s->G4, 128, 0, ctx->stream>>>(ctx->d_params, l, c.d_t, c.d_e, c.d_r, c.H, (int)c.V_t, (int)c.V_r, s->G4, s->Ptr);
+    KPRN_LAUNCH_CHECK(ctx);
     int64_t nw = (int64_t)s->NCH * s->NS * B_SLAB_ELEMS;
     pack_wxe_kernel<<<(unsigned)cdiv(nw, 256), 256, 0, ctx->stream>>>(ctx->d_params + l.Wx, s->Ptr, c.H, l.D, c.d_t, c.d_e, s->NCH,
-                                                                      s->KSe, s->NS, (int)(c.V_t * c.V_r), s->G4, 0, s->WxE, s->fmt, s->scales);
+                                                                      s->KSe, s->NS, (int)(c.V_t * c.V_r), s->G4, 0, s->WxE);
     KPRN_LAUNCH_CHECK(ctx);
     if (s->KSe1 > 0) {      // entity columns 256.. : a second projection launch accumulates them into XW
         int64_t nw1 = (int64_t)s->NCH * s->KSe1 * B_SLAB_ELEMS;
         pack_wxe_kernel<<<(unsigned)cdiv(nw1, 256), 256, 0, ctx->stream>>>(ctx->d_params + l.Wx, s->Ptr, c.H, l.D, c.d_t, c.d_e, s->NCH,
-                                                                           s->KSe1, s->KSe1, 0, s->G4, 256, s->WxE2, s->fmt, s->scales);
+                                                                           s->KSe1, s->KSe1, 0, s->G4, 256, s->WxE2);
         KPRN_LAUNCH_CHECK(ctx);
     }
     s->packed_version = ctx->params_version;
@@ -1175,11 +1100,11 @@ static int tc_pack(kprn_ctx* ctx) {
 }
 
 // the packed bf16 copies of the entity table, when they mirror the fp32 table (the sparse optimizer keeps them in step row by row)
-void tc_packed_entity(kprn_ctx* ctx, bf16** hi, bf16** lo, int* KE, int* fmt, const float** scale) {
-    *hi = nullptr; *lo = nullptr; *KE = 0; *fmt = FMT_BF16; *scale = nullptr;
+void tc_packed_entity(kprn_ctx* ctx, bf16** hi, bf16** lo, int* KE) {
+    *hi = nullptr; *lo = nullptr; *KE = 0;
     TcState* s = ctx->tc;
     if (!s || !s->E_hi || !s->E_lo || s->packed_version != ctx->params_version) return;
-    *hi = s->E_hi; *lo = s->E_lo; *KE = s->KE; *fmt = s->fmt; *scale = s->scales + SC_E;
+    *hi = s->E_hi; *lo = s->E_lo; *KE = s->KE;
 }
 
 static size_t proj_smem(int KE, int NOH) { return (size_t)(KE / 8 + 8 * NOH) * 2048 + (size_t)(KE / 8) * 2048 + PROJ_RING * B_SLAB_ELEMS * 2 + 512; }
@@ -1218,7 +1143,6 @@ int tc_forward(kprn_ctx* ctx, const int32_t* d_ids, const int32_t* d_seg, int64_
         s->num_sms = prop.multiProcessorCount;
         { const char* d = getenv("KPRN_TC_DEBUG"); s->debug = d && d[0] == '1'; }
         { const char* d = getenv("KPRN_TC_RECUR_PAIRS"); s->recur_pairs = !(d && d[0] == '0'); }
-        { const char* d = getenv("KPRN_TC_FP16"); s->fmt = (d && d[0] == '0') ? FMT_BF16 : FMT_F16; }
         if (prop.major != 10) {
             delete ctx->tc; ctx->tc = nullptr;      // a retry must meet this check again
             set_error("tensor-core path needs sm_100 (found sm_%d%d)", prop.major, prop.minor);
@@ -1248,7 +1172,7 @@ int tc_forward(kprn_ctx* ctx, const int32_t* d_ids, const int32_t* d_seg, int64_
         a.ids = d_ids; a.N = N; a.T = c.T; a.V_e = c.V_e; a.V_t = (int)c.V_t; a.V_r = (int)c.V_r;
         a.E_hi = s->E_hi; a.E_lo = s->E_lo; a.W = s->WxE; a.XW = s->xw.as<float>();
         a.KE = s->KE0; a.KSe = s->KSe; a.NOH = s->NOH; a.NS = s->NS; a.NCH = s->NCH; a.G4 = s->G4; a.num_tiles = ptiles * c.T; a.passes = passes; a.dbg = dbg;
-        a.n_dev = nullptr; a.k_base = 0; a.accumulate = 0; a.fmt = s->fmt; a.sc = s->scales;
+        a.n_dev = nullptr; a.k_base = 0; a.accumulate = 0;
         cudaEvent_t e0;
         KPRN_TRY(prof_begin(ctx, &e0));
         const int64_t n_steps = N * c.T, n_order = ptiles * c.T * TILE_M;       // n_order: read-order indices incl. the ragged tail
@@ -1286,7 +1210,7 @@ int tc_forward(kprn_ctx* ctx, const int32_t* d_ids, const int32_t* d_seg, int64_
         const bool dd = s->dedup && ptiles * c.T * TILE_M < (1ll << 30);
         a.pos = dd ? s->dd.pos.as<uint32_t>() : nullptr; a.slot_of = dd ? s->dd.slot_of.as<uint32_t>() : nullptr;
         ctx->head_part4 = nullptr;
-        a.cache = nullptr; a.hcache = nullptr; a.fmt = s->fmt; a.sc = s->scales;
+        a.cache = nullptr; a.hcache = nullptr;
         if (tc_train) KPRN_TRY(tc_train_buffers(ctx, N, &a.cache, &a.hcache));
         if (ctx->cls_only && c.pool == KPRN_POOL_LSE) {      // the pool kernel finishes the head: sum of 4 partials + bias
             KPRN_TRY(ensure(s->part4, sizeof(float) * 4 * (size_t)a.npad));
@@ -1305,7 +1229,7 @@ int tc_forward(kprn_ctx* ctx, const int32_t* d_ids, const int32_t* d_seg, int64_
             RecurWide w;
             w.XW = a.XW; w.W = s->Wh; w.h0 = s->wide_h0.as<bf16>(); w.h1 = s->wide_h1.as<bf16>(); w.c = s->wide_c.as<float>();
             w.N = N; w.T = c.T; w.H = c.H; w.Hp = s->Hp; w.num_sms = s->num_sms; w.pos = a.pos; w.slot_of = a.slot_of;
-            w.wo = a.wo; w.part4 = a.part4; w.npad = a.npad; w.hT = a.part4 ? nullptr : a.hT; w.fmt = s->fmt; w.sc = s->scales;
+            w.wo = a.wo; w.part4 = a.part4; w.npad = a.npad; w.hT = a.part4 ? nullptr : a.hT;
             KPRN_TRY(wide_recurrence(ctx, w));
         } else if (tc_train) {           // CTA pairs, epilogue also writes the activation caches of the backward
             grid_r = 2 * ((ptiles + 1) / 2 < s->num_sms / 2 ? (ptiles + 1) / 2 : s->num_sms / 2);
@@ -1361,7 +1285,6 @@ void tc_destroy(kprn_ctx* ctx) {
     if (s->Wh) cudaFree(s->Wh);
     if (s->Ptr) cudaFree(s->Ptr);
     if (s->WxE2) cudaFree(s->WxE2);
-    if (s->scales) cudaFree(s->scales);
     for (DBuf* b : {&s->xw, &s->hT, &s->hscratch, &s->dbg, &s->part4, &s->wide_h0, &s->wide_h1, &s->wide_c})
         if (b->p) { cudaFree(b->p); b->p = nullptr; b->cap = 0; }
     dedup_free(s->dd);

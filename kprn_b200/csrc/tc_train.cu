@@ -33,7 +33,6 @@ struct TcTrain {
     bf16* WT = nullptr;               // bgemm B operand: [part 2][ks G4/64][hi|lo][half 2][kc 8][n Nh][8]
     DBuf cache, hcache, dgop, dh, dc, wpart, gP, cls;
     DBuf dX, eg_keys, eg_vals, eg_tmp, eg_part, eg_flags;     // entity-gradient staging + sorted segment reduce
-    DBuf dyn;                         // per-backward dynamic scales of dG (see CellBwdArgs)
     DBuf xop, hop, ohop, dbg;         // gathered entity rows / h / one-hot slice in the weight-gradient kernel's stage layout
     // a second stream for the memory-bound side work of the backward (operand staging, entity-gradient segment reduce): it runs
     // beside the tensor-bound kernels of the main stream; fork / join with events, so the caller's stream semantics are unchanged
@@ -49,7 +48,7 @@ struct TcTrain {
 // part 0: Wh^T as B of dh = dG Wh     -> element (n = hidden unit k, K index gp) = Wh[row(gp)][n]
 // part 1: Wx_e^T as B of dX = dG Wx_e -> element (n = entity column,  K index gp) = Wx[row(gp)][d_t + n]
 __global__ void pack_wt_kernel(const float* __restrict__ Wh, const float* __restrict__ Wx, int H, int D, int d_t, int d_e, int G4,
-                               int N0, int N1, bf16* __restrict__ out, int fmt, const float* __restrict__ sc) {
+                               int N0, int N1, bf16* __restrict__ out) {
     const int KSg = G4 / 64;
     const int64_t per0 = (int64_t)KSg * 2 * 8 * N0 * 8, per1 = (int64_t)KSg * 2 * 8 * N1 * 8;     // elements of a part (hi + lo)
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -69,11 +68,11 @@ __global__ void pack_wt_kernel(const float* __restrict__ Wh, const float* __rest
     const int row = perm_to_row(gp, H, u);
     float v = 0.f;
     if (u < H) {
-        if (part == 0) { if (nn < H) v = Wh[(int64_t)row * H + nn] * sc[SC_WT0]; }
-        else if (nn < d_e) v = Wx[(int64_t)row * D + d_t + nn] * sc[SC_WT1];
+        if (part == 0) { if (nn < H) v = Wh[(int64_t)row * H + nn]; }
+        else if (nn < d_e) v = Wx[(int64_t)row * D + d_t + nn];
     }
     bf16 h, l;
-    split16(v, fmt, h, l);
+    split_bf16(v, h, l);
     bf16* base = out + (part ? per0 : 0) + (((int64_t)ks * 2 + 0) * 2 + half) * (8 * Nh * 8) + ((int64_t)kc * Nh + n) * 8 + e;
     base[0] = h;
     base[(int64_t)2 * 8 * Nh * 8] = l;          // the lo block follows the two halves of hi
@@ -90,38 +89,20 @@ struct CellBwdArgs {
     float* dc;                // [tile][Hp/8][row 128][8] in/out (first step: treated as 0)
     bf16* dgop;               // [tile][t][hi|lo][kc G4/8][row 128][8]
     int G4;
-    // FMT_F16: dG_t is stored as fp16 halves of dG * s_t.  s_t comes from a bound on |dG_t| -- (max|dc| + max|dh|) max(1, T/4), the
-    // maxima taken where dc and dh are produced -- so no pass over dG is needed.  dyn = [ds_max, wo_max, then per step t:
-    // amax_dh[t], amax_dc[t], scale[t]] (device floats, zeroed per backward).
-    int fmt; float* dyn;
 };
 
-__device__ __forceinline__ float pow2_scale_dev(float amax, float target) {
-    if (!(amax > 0.f)) return 1.f;
-    int e;
-    frexpf(target / amax, &e);
-    e -= 1;
-    e = e < -100 ? -100 : (e > 100 ? 100 : e);
-    return ldexpf(1.f, e);
-}
-__device__ __forceinline__ void warp_amax(float m, float* dst) {
-    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(reinterpret_cast<int*>(dst), __float_as_int(m));
-}
-__global__ void absmax2_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ out) {
-    float m = 0.f;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) m = fmaxf(m, fabsf(x[i]));
-    warp_amax(m, out);
-}
-
-__device__ __forceinline__ void split8_store(const float* v, float scale, int fmt, bf16* hi, bf16* lo) {
-    float w[8];
+__device__ __forceinline__ void split8_store(const float* v, bf16* hi, bf16* lo) {
+    uint32_t wh[4], wl[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) w[i] = v[i] * scale;
-    uint4 h, l;
-    split16x8(w, fmt, h, l);
-    *reinterpret_cast<uint4*>(hi) = h;
-    *reinterpret_cast<uint4*>(lo) = l;
+    for (int i = 0; i < 4; ++i) {
+        const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h2);
+        const float r0 = v[2 * i] - __uint_as_float(hb << 16), r1 = v[2 * i + 1] - __uint_as_float(hb & 0xFFFF0000u);
+        const __nv_bfloat162 l2 = __floats2bfloat162_rn(r0, r1);
+        wh[i] = hb; wl[i] = *reinterpret_cast<const uint32_t*>(&l2);
+    }
+    *reinterpret_cast<uint4*>(hi) = make_uint4(wh[0], wh[1], wh[2], wh[3]);
+    *reinterpret_cast<uint4*>(lo) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
 }
 
 __global__ void __launch_bounds__(512) cell_bwd_kernel(CellBwdArgs a) {
@@ -159,23 +140,13 @@ __global__ void __launch_bounds__(512) cell_bwd_kernel(CellBwdArgs a) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) { const int u = grp * 8 + e; dh[e] = u < a.H ? s * a.wo[u] : 0.f; dc[e] = 0.f; }
     }
-    // scale of this step's dG (every thread derives the same value from the two maxima)
-    float* dyn_t = a.dyn + 2 + 3 * a.t;
-    float scale = 1.f;
-    if (a.fmt == FMT_F16) {
-        const float in_dh = a.dh ? dyn_t[0] : a.dyn[0] * a.dyn[1], in_dc = a.dh ? dyn_t[1] : 0.f;
-        scale = pow2_scale_dev((in_dc + in_dh) * fmaxf(1.f, 0.25f * a.T), 8192.f);
-        if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && threadIdx.y == 0) dyn_t[2] = scale;
-    } else if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && threadIdx.y == 0) dyn_t[2] = 1.f;
     float di[8], dg[8], df[8], dO[8];
-    float dc_max = 0.f;
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
         const float tc = tanhf(cc[e]);
         const float d_o = dh[e] * tc;
         const float dcu = dc[e] + dh[e] * go[e] * (1.f - tc * tc);
         dc[e] = dcu * gf[e];
-        dc_max = fmaxf(dc_max, live ? fabsf(dc[e]) : 0.f);
         di[e] = live ? dcu * gg[e] * gi[e] * (1.f - gi[e]) : 0.f;
         dg[e] = live ? dcu * gi[e] * (1.f - gg[e] * gg[e]) : 0.f;
         df[e] = live ? dcu * cp[e] * gf[e] * (1.f - gf[e]) : 0.f;
@@ -187,11 +158,10 @@ __global__ void __launch_bounds__(512) cell_bwd_kernel(CellBwdArgs a) {
     const size_t hl = (size_t)(a.G4 / 8) * TILE_M * 8;                       // elements of one of hi / lo
     bf16* base = a.dgop + (size_t)(m * a.T + a.t) * 2 * hl + ((size_t)(j * 16 + sb) * TILE_M + r) * 8;
     const size_t gstep = (size_t)4 * TILE_M * 8;                              // next gate = 4 k-chunks further
-    split8_store(di, scale, a.fmt, base, base + hl);
-    split8_store(dg, scale, a.fmt, base + gstep, base + gstep + hl);
-    split8_store(df, scale, a.fmt, base + 2 * gstep, base + 2 * gstep + hl);
-    split8_store(dO, scale, a.fmt, base + 3 * gstep, base + 3 * gstep + hl);
-    if (a.fmt == FMT_F16 && a.t > 0) warp_amax(dc_max, a.dyn + 2 + 3 * (a.t - 1) + 1);      // max |dc| entering step t-1
+    split8_store(di, base, base + hl);
+    split8_store(dg, base + gstep, base + gstep + hl);
+    split8_store(df, base + 2 * gstep, base + 2 * gstep + hl);
+    split8_store(dO, base + 3 * gstep, base + 3 * gstep + hl);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -201,7 +171,6 @@ struct BgArgs {
     const bf16* dgop; const bf16* WT; int T; int t; int G4; int N0, N1; int64_t num_tiles; int64_t N;
     int part_begin;           // 1 at t = 0 (no dh needed)
     float* dh;                // [tile][N0/8][row 128][8]
-    int fmt; const float* sc; float* dyn;      // split format, per-tensor scales, per-step dynamic scales (see CellBwdArgs)
     float* dX;                // [(tile*T + t)*128 + row][N1] fp32: the entity-slice input gradient of every path-step (row index =
                               // the read-order index o of the slot maps); summed per entity row by the sorted segment reduce below
 };
@@ -269,7 +238,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BG_THREADS, 1) bgemm
             const bool issue = ptx::elect_one();
             uint32_t stage = 0, phase = 0;
             constexpr uint32_t DHI = ptx::desc_hi(128);
-            const uint32_t idesc0 = ptx::make_idesc_f16(a.fmt, 256, a.N0), idesc1 = ptx::make_idesc_f16(a.fmt, 256, a.N1);
+            const uint32_t idesc0 = ptx::make_idesc_f16(1, 256, a.N0), idesc1 = ptx::make_idesc_f16(1, 256, a.N1);
             for (int64_t it = 0; it < my_tiles; ++it) {
                 ptx::mbar_wait_cluster(BAR(B_ACCE), (it & 1) ^ 1);
                 ptx::tc_fence_after();
@@ -317,9 +286,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BG_THREADS, 1) bgemm
         // ===== epilogue: warps 4-7 drain part 0 (dh), warps 8-11 part 1 (dX); a warp owns the 32 rows of its TMEM lane quarter =====
         const int part = (warp - 4) >> 2, q4 = warp & 3, r = q4 * 32 + lane;
         const uint32_t acce_leader = ptx::mapa(BAR(B_ACCE), 0);
-        // accumulator = (s_t dG)(s_W W): descale is exact (powers of two); s_t was written by this step's cell_bwd
-        const float inv = 1.f / (a.dyn[2 + 3 * a.t + 2] * a.sc[part ? SC_WT1 : SC_WT0]);
-        float dh_max = 0.f;
         for (int64_t it = 0; it < my_tiles; ++it) {
             const int64_t m = tile_of(it);
             ptx::mbar_wait(BAR(B_ACCF), it & 1);
@@ -333,8 +299,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BG_THREADS, 1) bgemm
                         ptx::tmem_ld32(tb + blk * 32, v);
                         ptx::tc_wait_ld();
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) { v[i] *= inv; dh_max = fmaxf(dh_max, fabsf(v[i])); }
-#pragma unroll
                         for (int i = 0; i < 4; ++i) ptx::stg256(dst + (size_t)(blk * 4 + i) * TILE_M * 8, v + 8 * i);
                     }
                 }
@@ -345,8 +309,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BG_THREADS, 1) bgemm
                     ptx::tmem_ld32(tb + blk * 32, v);
                     ptx::tc_wait_ld();
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] *= inv;
-#pragma unroll
                     for (int i = 0; i < 4; ++i) ptx::stg256(dst + blk * 32 + 8 * i, v + 8 * i);     // one full 32-byte sector per store
                 }
             }
@@ -354,7 +316,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BG_THREADS, 1) bgemm
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive_cluster(acce_leader);
         }
-        if (part == 0 && a.part_begin == 0 && a.fmt == FMT_F16 && a.t > 0) warp_amax(dh_max, a.dyn + 2 + 3 * (a.t - 1));      // max |dh| entering step t-1
     }
     ptx::tc_fence_before();
     ptx::cluster_sync();
@@ -373,7 +334,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BG_THREADS, 1) bgemm
 __global__ void __launch_bounds__(128) prep_operands_kernel(const int32_t* __restrict__ ids, int64_t N, int T, int64_t V_e, int V_t, int V_r,
                                                             const bf16* __restrict__ E_hi, const bf16* __restrict__ E_lo, int KE,
                                                             const bf16* __restrict__ hcache, int Hp,
-                                                            bf16* __restrict__ xop, bf16* __restrict__ hop, bf16* __restrict__ ohop, int fmt) {
+                                                            bf16* __restrict__ xop, bf16* __restrict__ hop, bf16* __restrict__ ohop) {
     const int64_t b = blockIdx.x;                 // tile*T + t
     const int r = threadIdx.x, rh = r >> 6, rr = r & 63;
     const int64_t m = b / T;
@@ -411,11 +372,10 @@ __global__ void __launch_bounds__(128) prep_operands_kernel(const int32_t* __res
         }
     }
     uint4* doh = reinterpret_cast<uint4*>(ohop) + ((size_t)(b * 2 + rh) * 8) * 64 + rr;
-    const uint32_t one_bits = fmt == FMT_BF16 ? 0x3F80u : 0x3C00u;
 #pragma unroll
     for (int kc = 0; kc < 8; ++kc) {
         uint32_t w[4] = {0u, 0u, 0u, 0u};
-        if (combo >= 0 && (combo >> 3) == kc) w[(combo & 7) >> 1] = one_bits << (16 * (combo & 1));      // 1.0 in the operand format
+        if (combo >= 0 && (combo >> 3) == kc) w[(combo & 7) >> 1] = 0x3F80u << (16 * (combo & 1));      // bf16 1.0
         doh[(size_t)kc * 64] = make_uint4(w[0], w[1], w[2], w[3]);
     }
 }
@@ -435,10 +395,8 @@ struct WgArgs {
     unsigned long long* dbg;                      // optional wait-cycle counters (KPRN_TC_DEBUG=1)
     int T; int64_t num_tiles;
     int G4, N0, KE;
-    int64_t tiles_per_q;            // K-split sp = q * T + t covers step t of tiles [q * tiles_per_q, +tiles_per_q): one step per split,
-                                    // because FMT_F16 stores dG_t with a per-step scale (the partial tiles are descaled by wgrad_reduce)
+    int64_t blocks_per_split;       // (tile, t) blocks per K-split
     float* part;                    // [split][part 2][gp G4][n 320] fp32
-    int fmt;
 };
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WG_THREADS, 1) wgrad_kernel(WgArgs a) {
@@ -472,8 +430,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WG_THREADS, 1) wgrad
     ptx::tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    const int t = split % a.T;
-    const int64_t m0 = (int64_t)(split / a.T) * a.tiles_per_q, m1 = (m0 + a.tiles_per_q < a.num_tiles) ? m0 + a.tiles_per_q : a.num_tiles;
+    const int64_t nblocks = a.num_tiles * a.T;
+    const int64_t b0 = split * a.blocks_per_split, b1 = (b0 + a.blocks_per_split < nblocks) ? b0 + a.blocks_per_split : nblocks;
     const int kc_rows = a.G4 / 8;                                    // k-chunk rows of one of hi / lo of a dgop step
     const int bk_rows = (part ? a.KE : a.N0) / 8;                    // ... of an hcache / xop step
     const int kcA = (mp * 2 + (int)rank) * 16;                       // first k-chunk of this CTA's 128 gate columns
@@ -487,8 +445,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WG_THREADS, 1) wgrad
         const uint8_t* b8 = reinterpret_cast<const uint8_t*>(part ? a.xop : a.hop);
         const uint8_t* oh8 = reinterpret_cast<const uint8_t*>(a.ohop);
         const int hlx = lane >> 4, kc = lane & 15;
-        for (int64_t m = m0; m < m1; ++m) {
-            const int64_t b = m * a.T + t;
+        for (int64_t b = b0; b < b1; ++b) {
+            const int t = (int)(b % a.T);
             const int64_t bsrc = part ? b : b - 1;                   // h_{t-1} of the same tile (t > 0), x_e of the step itself
             const bool has_b = part == 1 || t > 0;
             for (int half = 0; half < 2; ++half) {
@@ -520,10 +478,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WG_THREADS, 1) wgrad
             // MN-major no-swizzle operand [k-chunk (8 mn)][row (k)][16 B]: LBO = 128 B between 8-row k groups, SBO = 1024 B
             // between 8-element mn groups (tools/umma_probe.cu); a K=16 step = 16 rows = 256 B
             constexpr uint32_t DHI_MN = ptx::desc_hi(1024);
-            const uint32_t idesc_main = ptx::make_idesc_f16(a.fmt, 256, Nmain) | (1u << 15) | (1u << 16);
-            const uint32_t idesc_oh = ptx::make_idesc_f16(a.fmt, 256, 64) | (1u << 15) | (1u << 16);
+            const uint32_t idesc_main = ptx::make_idesc_f16(1, 256, Nmain) | (1u << 15) | (1u << 16);
+            const uint32_t idesc_oh = ptx::make_idesc_f16(1, 256, 64) | (1u << 15) | (1u << 16);
             bool first_main = true, first_oh = true;
-            for (int64_t m = m0; m < m1; ++m) {
+            for (int64_t b = b0; b < b1; ++b) {
+                const int t = (int)(b % a.T);
                 const bool has_main = part == 1 || t > 0;
                 for (int half = 0; half < 2; ++half) {
                     if (a.dbg) {
@@ -571,7 +530,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WG_THREADS, 1) wgrad
         } else if (lane == 0) {
             uint32_t stage = 0, phase = 0;
             const uint32_t remote = ptx::mapa(BAR(B_PEER), 0);
-            for (int64_t m = m0; m < m1; ++m)
+            for (int64_t b = b0; b < b1; ++b)
                 for (int half = 0; half < 2; ++half) {
                     ptx::mbar_wait(BAR(stage), phase);
                     ptx::mbar_arrive_cluster(remote + 8u * stage);
@@ -586,7 +545,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WG_THREADS, 1) wgrad
         const int gp = mp * 256 + (int)rank * 128 + r;
         float* dst = a.part + (((size_t)split * 2 + part) * a.G4 + gp) * 320;
         const uint32_t tb = tmem + ((uint32_t)(q4 * 32) << 16);
-        const bool any_main = m1 > m0 && (part == 1 || t > 0);
+        const bool any_main = b1 > b0 && (part == 1 || (a.T > 1 && (b1 - b0 > 1 || (b0 % a.T) != 0)));
         for (int blk = 0; blk < Nmain / 32; ++blk) {
             float v[32];
             if (any_main) { ptx::tmem_ld32(tb + blk * 32, v); ptx::tc_wait_ld(); }
@@ -600,7 +559,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WG_THREADS, 1) wgrad
         if (part == 0) {
             for (int blk = 0; blk < 2; ++blk) {
                 float v[32];
-                if (m1 > m0) { ptx::tmem_ld32(tb + 256 + blk * 32, v); ptx::tc_wait_ld(); }
+                if (b1 > b0) { ptx::tmem_ld32(tb + 256 + blk * 32, v); ptx::tc_wait_ld(); }
                 else {
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] = 0.f;
@@ -619,8 +578,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WG_THREADS, 1) wgrad
 // fixed-order sum of the K-split partials into the flat gradient (accumulating, as accGradParameters does):
 //   part 0, n < N0        -> gWh[row(gp)][n]          part 0, n in [256, 320) -> gP[n - 256][gp] (temporary, overwritten)
 //   part 1, n < KE        -> gWx[row(gp)][d_t + n]
-__global__ void wgrad_reduce_kernel(const float* __restrict__ part, int splits, int T, int G4, int H, int D, int d_t, int d_e, int N0, int KE,
-                                    const float* __restrict__ sc, const float* __restrict__ dyn,
+__global__ void wgrad_reduce_kernel(const float* __restrict__ part, int splits, int G4, int H, int D, int d_t, int d_e, int N0, int KE,
                                     float* __restrict__ gWh, float* __restrict__ gWx, float* __restrict__ gP) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (int64_t)2 * G4 * 320) return;
@@ -629,10 +587,8 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ part, int splits, 
     const int pt = (int)(idx / ((int64_t)320 * G4));
     if (pt == 0 && n >= N0 && n < 256) return;
     if (pt == 1 && n >= KE) return;
-    // split sp holds step sp % T: accumulator = (s_t dG)^T (s_B B) with s_B = SC_H (h), SC_E (x_e) or 1 (the one-hot slice)
-    const float sB = pt == 1 ? sc[SC_E] : (n >= 256 ? 1.f : sc[SC_H]);
     float acc = 0.f;
-    for (int sp = 0; sp < splits; ++sp) acc += part[(((size_t)sp * 2 + pt) * G4 + gp) * 320 + n] * (1.f / (dyn[2 + 3 * (sp % T) + 2] * sB));
+    for (int sp = 0; sp < splits; ++sp) acc += part[(((size_t)sp * 2 + pt) * G4 + gp) * 320 + n];
     int u;
     const int row = perm_to_row(gp, H, u);
     if (pt == 0 && n >= 256) { gP[(size_t)(n - 256) * G4 + gp] = acc; return; }
@@ -876,7 +832,7 @@ int tc_train_pack(kprn_ctx* ctx) {
     if (!tt->WT) KPRN_CUDA(cudaMalloc(&tt->WT, sizeof(bf16) * (size_t)elems));
     if (tt->packed_small == ctx->small_version + ctx->params_version * 1000003ull) return KPRN_OK;
     pack_wt_kernel<<<(unsigned)cdiv(elems / 2, 256), 256, 0, ctx->stream>>>(ctx->d_params + l.Wh, ctx->d_params + l.Wx, c.H, l.D, c.d_t, c.d_e,
-                                                                           s->G4, s->Hp, s->KE, tt->WT, s->fmt, s->scales);
+                                                                           s->G4, s->Hp, s->KE, tt->WT);
     KPRN_LAUNCH_CHECK(ctx);
     tt->packed_small = ctx->small_version + ctx->params_version * 1000003ull;
     return KPRN_OK;
@@ -918,37 +874,18 @@ int tc_backward(kprn_ctx* ctx, float scale) {
     }
     KPRN_TRY(head_backward_cls(ctx, scale, s->hT.as<float>(), c.H));
     const float* ds_c = ctx->ws_ds.as<float>();
-    KPRN_TRY(ensure(tt->dyn, sizeof(float) * (size_t)(2 + 3 * (T + 1))));
-    float* dyn = tt->dyn.as<float>();
-    KPRN_CUDA(cudaMemsetAsync(dyn, 0, sizeof(float) * (size_t)(2 + 3 * (T + 1)), ctx->stream));
-    if (s->fmt == FMT_F16) {      // max |ds_c| and max |Wo[classId,:]|: the bound on dh of the last step
-        absmax2_kernel<<<148, 256, 0, ctx->stream>>>(ds_c, N, dyn);
-        KPRN_LAUNCH_CHECK(ctx);
-        absmax2_kernel<<<1, 256, 0, ctx->stream>>>(P + l.Wo + (int64_t)(c.class_id - 1) * c.H, c.H, dyn + 1);
-        KPRN_LAUNCH_CHECK(ctx);
-    }
     // ---- buffers ----
     const size_t dg_bytes = (size_t)ptiles * T * 2 * (G4 / 8) * 2048;
     KPRN_TRY(ensure(tt->dgop, dg_bytes));
     KPRN_TRY(ensure(tt->dh, sizeof(float) * (size_t)ptiles * Hp * TILE_M));
     KPRN_TRY(ensure(tt->dc, sizeof(float) * (size_t)ptiles * Hp * TILE_M));
     const int items = (G4 / 256) * 2;
+    int splits = (s->num_sms / 2) / items;
+    if (splits < 1) splits = 1;
     const int64_t nblocks = ptiles * T;
-    // K-splits of the weight-gradient kernel: one step t per split (per-step dG scale), Q tile ranges per step; Q fills the
-    // machine's CTA pairs in whole waves as well as it can
-    int Q = 1;
-    {
-        const int pairs_hw = s->num_sms / 2;
-        double best = -1.0;
-        for (int q = 1; q <= 8 && q <= ptiles; ++q) {
-            const int total = items * T * q;
-            const double util = (double)total / (double)(cdiv(total, pairs_hw) * pairs_hw);
-            if (util > best + 1e-9) { best = util; Q = q; }
-        }
-    }
-    const int64_t tiles_per_q = cdiv(ptiles, Q);
-    Q = (int)cdiv(ptiles, tiles_per_q);
-    const int splits = T * Q;
+    if (splits > nblocks) splits = (int)nblocks;
+    const int64_t bps = cdiv(nblocks, splits);
+    splits = (int)cdiv(nblocks, bps);
     KPRN_TRY(ensure(tt->wpart, sizeof(float) * (size_t)splits * 2 * G4 * 320));
     KPRN_TRY(ensure(tt->gP, sizeof(float) * (size_t)(64 + c.V_t + c.V_r) * G4));
     // entity-row gradients: bgemm stages dX per path-step; the sorted segment reduce below adds them per distinct row into the
@@ -970,7 +907,7 @@ int tc_backward(kprn_ctx* ctx, float scale) {
         if (tt->use_side) { KPRN_CUDA(cudaEventRecord(tt->ev_fork, ctx->stream)); KPRN_CUDA(cudaStreamWaitEvent(side, tt->ev_fork, 0)); }
         prep_operands_kernel<<<(unsigned)nblocks, 128, 0, side>>>(ctx->d_ids, N, T, c.V_e, (int)c.V_t, (int)c.V_r, s->E_hi, s->E_lo, KE,
                                                                   tt->hcache.as<bf16>(), Hp, tt->xop.as<bf16>(), tt->hop.as<bf16>(),
-                                                                  tt->ohop.as<bf16>(), s->fmt);
+                                                                  tt->ohop.as<bf16>());
         KPRN_LAUNCH_CHECK(ctx);
         if (tt->use_side) KPRN_CUDA(cudaEventRecord(tt->ev_prep, side));
     }
@@ -982,13 +919,13 @@ int tc_backward(kprn_ctx* ctx, float scale) {
         CellBwdArgs ca;
         ca.cache = tt->cache.as<float>(); ca.T = T; ca.t = t; ca.NCH = s->NCH; ca.H = c.H; ca.N = N;
         ca.dh = t == T - 1 ? nullptr : tt->dh.as<float>(); ca.ds_c = ds_c; ca.wo = P + l.Wo + (int64_t)(c.class_id - 1) * c.H;
-        ca.dc = tt->dc.as<float>(); ca.dgop = tt->dgop.as<bf16>(); ca.G4 = G4; ca.fmt = s->fmt; ca.dyn = dyn;
+        ca.dc = tt->dc.as<float>(); ca.dgop = tt->dgop.as<bf16>(); ca.G4 = G4;
         cell_bwd_kernel<<<dim3((unsigned)ptiles, (unsigned)s->NCH), dim3(TILE_M, 4), 0, ctx->stream>>>(ca);
         KPRN_LAUNCH_CHECK(ctx);
         BgArgs ba;
         ba.dgop = tt->dgop.as<bf16>(); ba.WT = tt->WT; ba.T = T; ba.t = t; ba.G4 = G4; ba.N0 = Hp; ba.N1 = KE; ba.num_tiles = ptiles; ba.N = N;
         ba.part_begin = t == 0 ? 1 : 0; ba.dh = tt->dh.as<float>();
-        ba.dX = tt->dX.as<float>(); ba.fmt = s->fmt; ba.sc = s->scales; ba.dyn = dyn;
+        ba.dX = tt->dX.as<float>();
         bgemm_kernel<<<bg_grid, BG_THREADS, bg_smem, ctx->stream>>>(ba);
         KPRN_LAUNCH_CHECK(ctx);
     }
@@ -1037,8 +974,7 @@ int tc_backward(kprn_ctx* ctx, float scale) {
             KPRN_CUDA(cudaMemsetAsync(tt->dbg.p, 0, 8 * sizeof(unsigned long long), ctx->stream));
             wa.dbg = tt->dbg.as<unsigned long long>();
         }
-        wa.T = T; wa.num_tiles = ptiles; wa.G4 = G4; wa.N0 = Hp; wa.KE = KE; wa.tiles_per_q = tiles_per_q; wa.part = tt->wpart.as<float>();
-        wa.fmt = s->fmt;
+        wa.T = T; wa.num_tiles = ptiles; wa.G4 = G4; wa.N0 = Hp; wa.KE = KE; wa.blocks_per_split = bps; wa.part = tt->wpart.as<float>();
         const size_t wg_smem = (size_t)WG_STAGES * (2 * 16384 + 2 * 16384 + 4096) + 256;
         KPRN_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wg_smem));
         wgrad_kernel<<<dim3((unsigned)(items * 2), (unsigned)splits), WG_THREADS, wg_smem, ctx->stream>>>(wa);
@@ -1055,8 +991,8 @@ int tc_backward(kprn_ctx* ctx, float scale) {
     float* gP = tt->gP.as<float>();
     float* Tsum = gP + (size_t)64 * G4;
     float* Rsum = Tsum + (size_t)c.V_t * G4;
-    wgrad_reduce_kernel<<<(unsigned)cdiv((int64_t)2 * G4 * 320, 256), 256, 0, ctx->stream>>>(tt->wpart.as<float>(), splits, T, G4, c.H, l.D, c.d_t,
-                                                                                          c.d_e, Hp, KE, s->scales, dyn, gr + l.Wh, gr + l.Wx, gP);
+    wgrad_reduce_kernel<<<(unsigned)cdiv((int64_t)2 * G4 * 320, 256), 256, 0, ctx->stream>>>(tt->wpart.as<float>(), splits, G4, c.H, l.D, c.d_t, c.d_e,
+                                                                                          Hp, KE, gr + l.Wh, gr + l.Wx, gP);
     KPRN_LAUNCH_CHECK(ctx);
     ptr_sums_kernel<<<(unsigned)cdiv(G4, 128), 128, 0, ctx->stream>>>(gP, G4, c.H, (int)c.V_t, (int)c.V_r, Tsum, Rsum, gr + l.bx);
     KPRN_LAUNCH_CHECK(ctx);
@@ -1084,7 +1020,7 @@ void tc_train_destroy(kprn_ctx* ctx) {
         cudaStreamDestroy(tt->side);
     }
     for (DBuf* b : {&tt->cache, &tt->hcache, &tt->dgop, &tt->dh, &tt->dc, &tt->wpart, &tt->gP, &tt->cls, &tt->dX, &tt->eg_keys, &tt->eg_vals,
-                    &tt->eg_tmp, &tt->eg_part, &tt->eg_flags, &tt->xop, &tt->hop, &tt->ohop, &tt->dbg, &tt->dyn})
+                    &tt->eg_tmp, &tt->eg_part, &tt->eg_flags, &tt->xop, &tt->hop, &tt->ohop, &tt->dbg})
         if (b->p) { cudaFree(b->p); b->p = nullptr; b->cap = 0; }
     dedup_free(tt->es);
     delete tt;

@@ -21,7 +21,6 @@ struct WideArgs {
     int64_t N; int T; int t; int H; int Hp; int G4; int64_t num_tiles;
     const uint32_t* pos; const uint32_t* slot_of;
     const float* wo; float* part4; int64_t npad; float* hT;      // last step: fused head partials (scores-only) and / or h_T
-    int fmt; const float* sc;
 };
 
 __device__ __forceinline__ float wex2f(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -83,7 +82,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WS_THREADS, 1) wide_
             const bool issue = ptx::elect_one();
             uint32_t stage = 0, phase = 0, ug[2] = {0, 0};
             constexpr uint32_t DHI = ptx::desc_hi(128);
-            const uint32_t idesc = ptx::make_idesc_f16(a.fmt, 256, 256);
+            const uint32_t idesc = ptx::make_idesc_f16(1, 256, 256);
             for (int64_t it = 0; it < my_tiles; ++it)
                 for (int blk = 0; blk < NB; ++blk) {
                     const int g = blk & 1;
@@ -129,7 +128,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WS_THREADS, 1) wide_
         const int64_t tile_xw = (int64_t)(a.G4 / 8) * TILE_M * 8;
         const bool last = a.t == a.T - 1;
         const bool h_vec4 = (a.H & 3) == 0;
-        const float s_h = a.sc[SC_H], inv_r = a.sc[SC_INV_RECUR];
         uint32_t ug[2] = {0, 0};
         for (int64_t it = 0; it < my_tiles; ++it) {
             const int64_t m = tile_of(it);
@@ -166,10 +164,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WS_THREADS, 1) wide_
                             cp[0] = c0.x; cp[1] = c0.y; cp[2] = c0.z; cp[3] = c0.w; cp[4] = c1.x; cp[5] = c1.y; cp[6] = c1.z; cp[7] = c1.w;
                             ptx::tc_wait_ld();
 #pragma unroll
-                            for (int e = 0; e < 8; ++e) {
-                                xc[e] = fmaf(ai[e], inv_r, xc[e]); xc[8 + e] = fmaf(ag[e], inv_r, xc[8 + e]);
-                                xc[16 + e] = fmaf(af[e], inv_r, xc[16 + e]); xc[24 + e] = fmaf(ao[e], inv_r, xc[24 + e]);
-                            }
+                            for (int e = 0; e < 8; ++e) { xc[e] += ai[e]; xc[8 + e] += ag[e]; xc[16 + e] += af[e]; xc[24 + e] += ao[e]; }
                         } else {
 #pragma unroll
                             for (int e = 0; e < 8; ++e) cp[e] = 0.f;
@@ -203,14 +198,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WS_THREADS, 1) wide_
                         } else if (!last) {
                             *reinterpret_cast<float4*>(cptr) = make_float4(cn[0], cn[1], cn[2], cn[3]);
                             *reinterpret_cast<float4*>(cptr + 4) = make_float4(cn[4], cn[5], cn[6], cn[7]);
-                            float hs[8];
+                            uint32_t wh[4], wl[4];
 #pragma unroll
-                            for (int e = 0; e < 8; ++e) hs[e] = hv[e] * s_h;
-                            uint4 whi, wlo;
-                            split16x8(hs, a.fmt, whi, wlo);
+                            for (int i = 0; i < 4; ++i) {
+                                const __nv_bfloat162 h2b = __floats2bfloat162_rn(hv[2 * i], hv[2 * i + 1]);
+                                const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h2b);
+                                const float r0 = hv[2 * i] - __uint_as_float(hb << 16), r1 = hv[2 * i + 1] - __uint_as_float(hb & 0xFFFF0000u);
+                                const __nv_bfloat162 l2b = __floats2bfloat162_rn(r0, r1);
+                                wh[i] = hb; wl[i] = *reinterpret_cast<const uint32_t*>(&l2b);
+                            }
                             bf16* hd = a.h_out + (size_t)m * 2 * hl + ((size_t)(j * 4 + sb) * TILE_M + r) * 8;
-                            *reinterpret_cast<uint4*>(hd) = whi;
-                            *reinterpret_cast<uint4*>(hd + hl) = wlo;
+                            *reinterpret_cast<uint4*>(hd) = make_uint4(wh[0], wh[1], wh[2], wh[3]);
+                            *reinterpret_cast<uint4*>(hd + hl) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
                         } else {
                             const int u0 = j * 32 + sb * 8;
                             if (a.part4) {
@@ -246,8 +245,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WS_THREADS, 1) wide_
 }
 
 // recurrent weights for wide_step_kernel: [blk G4/256][ks Hp/64][hi|lo][half 2][kc 8][n 128][8], gate-scaled like pack_wh_kernel
-__global__ void pack_wh_wide_kernel(const float* __restrict__ Wh, int H, int Hp, int G4, bf16* __restrict__ out, int fmt,
-                                    const float* __restrict__ scl) {
+__global__ void pack_wh_wide_kernel(const float* __restrict__ Wh, int H, int Hp, int G4, bf16* __restrict__ out) {
     const int KS = Hp / 64;
     const int64_t total = (int64_t)(G4 / 256) * KS * 2 * 8 * 128 * 8;       // (hi, lo) pairs
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -263,9 +261,9 @@ __global__ void pack_wh_wide_kernel(const float* __restrict__ Wh, int H, int Hp,
     const int row = perm_to_row(gp, H, u);
     const int q = (gp >> 5) & 3;
     const float sc = q == 1 ? 2.8853900817779268f : -1.4426950408889634f;
-    const float v = (u < H && k < H) ? Wh[(int64_t)row * H + k] * sc * scl[SC_WH] : 0.f;
+    const float v = (u < H && k < H) ? Wh[(int64_t)row * H + k] * sc : 0.f;
     bf16 h, l;
-    split16(v, fmt, h, l);
+    split_bf16(v, h, l);
     bf16* base = out + ((((int64_t)blk * KS + ks) * 2 + 0) * 2 + half) * (8 * 128 * 8) + ((int64_t)kc * 128 + n) * 8 + e;
     base[0] = h;
     base[(int64_t)2 * 8 * 128 * 8] = l;
@@ -275,7 +273,7 @@ __global__ void pack_wh_wide_kernel(const float* __restrict__ Wh, int H, int Hp,
 int wide_recurrence(kprn_ctx* ctx, const RecurWide& w) {
     WideArgs a;
     a.XW = w.XW; a.W = w.W; a.c = w.c; a.N = w.N; a.T = w.T; a.H = w.H; a.Hp = w.Hp; a.G4 = 4 * w.Hp; a.num_tiles = cdiv(w.N, TILE_M);
-    a.pos = w.pos; a.slot_of = w.slot_of; a.wo = w.wo; a.part4 = w.part4; a.npad = w.npad; a.hT = w.hT; a.fmt = w.fmt; a.sc = w.sc;
+    a.pos = w.pos; a.slot_of = w.slot_of; a.wo = w.wo; a.part4 = w.part4; a.npad = w.npad; a.hT = w.hT;
     const size_t smem = (size_t)WS_STAGES * WS_STAGE + 256;
     KPRN_CUDA(cudaFuncSetAttribute(wide_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t n_tp = (a.num_tiles + 1) / 2;
@@ -290,9 +288,9 @@ int wide_recurrence(kprn_ctx* ctx, const RecurWide& w) {
     return KPRN_OK;
 }
 
-int pack_wh_wide(kprn_ctx* ctx, const float* Wh, int H, int Hp, bf16* out, int fmt, const float* sc) {
+int pack_wh_wide(kprn_ctx* ctx, const float* Wh, int H, int Hp, bf16* out) {
     const int64_t total = (int64_t)(4 * Hp / 256) * (Hp / 64) * 2 * 8 * 128 * 8;
-    pack_wh_wide_kernel<<<(unsigned)cdiv(total, 256), 256, 0, ctx->stream>>>(Wh, H, Hp, 4 * Hp, out, fmt, sc);
+    pack_wh_wide_kernel<<<(unsigned)cdiv(total, 256), 256, 0, ctx->stream>>>(Wh, H, Hp, 4 * Hp, out);
     KPRN_LAUNCH_CHECK(ctx);
     return KPRN_OK;
 }

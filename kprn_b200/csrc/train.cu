@@ -18,8 +18,6 @@
 
 #include <vector>
 
-#include <cuda_fp16.h>
-
 #include "adam.cuh"
 #include "common.cuh"
 
@@ -60,20 +58,10 @@ __device__ __forceinline__ void adam_replay(float& x, float& m, float& v, int64_
     if (m == 0.f && v == 0.f) return;                 // the update is exactly zero while m = v = 0
     for (int64_t k = t0 + 1; k <= t1; ++k) adam_elem(x, m, v, 0.f, steps[k], b1, b2, eps);
 }
-// refresh of one element of the packed 16-bit entity tables (same split as tc_state.cuh: fmt 1 = bf16 halves, 0 = fp16 halves of
-// v * scale, saturating)
-__device__ __forceinline__ void split_store(float v, __nv_bfloat16* hi, __nv_bfloat16* lo, int64_t idx, int fmt, float scale) {
-    if (fmt) {
-        const __nv_bfloat16 h = __float2bfloat16_rn(v);
-        hi[idx] = h;
-        lo[idx] = __float2bfloat16_rn(v - __bfloat162float(h));
-    } else {
-        const float w = fminf(fmaxf(v * scale, -65504.f), 65504.f);
-        const __half h = __float2half_rn(w);
-        const __half l = __float2half_rn(w - __half2float(h));
-        reinterpret_cast<__half*>(hi)[idx] = h;
-        reinterpret_cast<__half*>(lo)[idx] = l;
-    }
+__device__ __forceinline__ void split_store(float v, __nv_bfloat16* hi, __nv_bfloat16* lo, int64_t idx) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    hi[idx] = h;
+    lo[idx] = __float2bfloat16_rn(v - __bfloat162float(h));
 }
 
 struct RowsArgs {
@@ -88,8 +76,7 @@ struct RowsArgs {
     const float* gscale;        // optional device scalar multiplying every gradient (global-norm clip)
     const float* steps; float b1, b2, eps;
     int d_e; int KE;
-    __nv_bfloat16* E_hi; __nv_bfloat16* E_lo;       // packed 16-bit copies of the entity table (tensor-core forward), or null
-    int fmt; const float* escale;                   // their split format and scale
+    __nv_bfloat16* E_hi; __nv_bfloat16* E_lo;       // packed bf16 copies of the entity table (tensor-core forward), or null
 };
 
 // one WARP per slot (grid-stride over slots): catch the row up, optionally apply this step's gradient, refresh the packed
@@ -102,7 +89,6 @@ __global__ void __launch_bounds__(256) adam_rows_kernel(RowsArgs a) {
     const int lane = threadIdx.x & 31;
     const int warps = (gridDim.x * blockDim.x) >> 5;
     const float gs = a.gscale ? *a.gscale : 1.f;
-    const float es = a.E_hi ? *a.escale : 1.f;
     for (int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; slot < K; slot += warps) {
         const int64_t row = (int64_t)a.rows[slot] - 1;
         const int32_t lt = a.last_t[row];                  // every lane reads it before lane 0 rewrites it (the __syncwarp below)
@@ -155,7 +141,7 @@ __global__ void __launch_bounds__(256) adam_rows_kernel(RowsArgs a) {
                 *reinterpret_cast<float4*>(pv + q * 128 + lane * 4) = v[q];
                 if (a.E_hi) {
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) split_store(xs[e], a.E_hi, a.E_lo, row * a.KE + q * 128 + lane * 4 + e, a.fmt, es);
+                    for (int e = 0; e < 4; ++e) split_store(xs[e], a.E_hi, a.E_lo, row * a.KE + q * 128 + lane * 4 + e);
                 }
             }
         } else {
@@ -178,7 +164,7 @@ __global__ void __launch_bounds__(256) adam_rows_kernel(RowsArgs a) {
                     adam_elem(x, m, v, g, a.steps[a.t_now], a.b1, a.b2, a.eps);
                 }
                 a.x[i] = x; a.m[i] = m; a.v[i] = v;
-                if (a.E_hi) split_store(x, a.E_hi, a.E_lo, row * a.KE + k, a.fmt, es);
+                if (a.E_hi) split_store(x, a.E_hi, a.E_lo, row * a.KE + k);
             }
         }
         __syncwarp();
@@ -189,9 +175,7 @@ __global__ void __launch_bounds__(256) adam_rows_kernel(RowsArgs a) {
 // flush: every row that is behind t_now is replayed up to t_now (a block per row, grid-stride over the table)
 __global__ void adam_flush_kernel(float* __restrict__ x, float* __restrict__ m, float* __restrict__ v, int32_t* __restrict__ last_t,
                                   int64_t V, int d_e, int64_t base_t, int dense_ever, int64_t t_now, const float* __restrict__ steps,
-                                  float b1, float b2, float eps, int KE, __nv_bfloat16* E_hi, __nv_bfloat16* E_lo, int fmt,
-                                  const float* __restrict__ escale) {
-    const float es = E_hi ? *escale : 1.f;
+                                  float b1, float b2, float eps, int KE, __nv_bfloat16* E_hi, __nv_bfloat16* E_lo) {
     for (int64_t row = blockIdx.x; row < V; row += gridDim.x) {
         const int32_t lt = last_t[row];
         const int64_t t0 = lt > base_t ? lt : base_t;
@@ -201,7 +185,7 @@ __global__ void adam_flush_kernel(float* __restrict__ x, float* __restrict__ m, 
             float xi = x[i], mi = m[i], vi = v[i];
             adam_replay(xi, mi, vi, t0, t_now, steps, b1, b2, eps);
             x[i] = xi; m[i] = mi; v[i] = vi;
-            if (E_hi) split_store(xi, E_hi, E_lo, row * KE + k, fmt, es);
+            if (E_hi) split_store(xi, E_hi, E_lo, row * KE + k);
         }
     }
 }
@@ -349,21 +333,19 @@ int train_note_dense_step(kprn_ctx* ctx, float step) {
     return steps_push(ctx, tr, step);
 }
 
-static void packed_entity(kprn_ctx* ctx, __nv_bfloat16** hi, __nv_bfloat16** lo, int* KE, int* fmt, const float** sc) {
-    tc_packed_entity(ctx, hi, lo, KE, fmt, sc);
-}
+static void packed_entity(kprn_ctx* ctx, __nv_bfloat16** hi, __nv_bfloat16** lo, int* KE) { tc_packed_entity(ctx, hi, lo, KE); }
 static int zero_pad_rows(kprn_ctx* ctx, const int64_t* pads);
 
 int train_flush(kprn_ctx* ctx) {
     TrainState* tr = ctx->tr;
     if (!tr || !tr->pending) return KPRN_OK;
     const kprn_config& c = ctx->cfg;
-    __nv_bfloat16 *hi = nullptr, *lo = nullptr; int KE = 0, fmt = 1; const float* esc = nullptr;
-    packed_entity(ctx, &hi, &lo, &KE, &fmt, &esc);
+    __nv_bfloat16 *hi = nullptr, *lo = nullptr; int KE = 0;
+    packed_entity(ctx, &hi, &lo, &KE);
     const int threads = c.d_e >= 256 ? 256 : (c.d_e >= 128 ? 128 : 64);
     adam_flush_kernel<<<148 * 8, threads, 0, ctx->stream>>>(ctx->d_params + ctx->lay.E_e, ctx->d_m + ctx->lay.E_e, ctx->d_v + ctx->lay.E_e,
                                                            tr->last_t, c.V_e, c.d_e, tr->base_t, tr->dense_ever ? 1 : 0, ctx->adam_t,
-                                                           tr->steps.as<float>(), tr->b1, tr->b2, tr->eps, KE, hi, lo, fmt, esc);
+                                                           tr->steps.as<float>(), tr->b1, tr->b2, tr->eps, KE, hi, lo);
     KPRN_LAUNCH_CHECK(ctx);
     tr->base_t = ctx->adam_t;
     tr->pending = false;
@@ -421,8 +403,8 @@ static int zero_pad_rows(kprn_ctx* ctx, const int64_t* pads) {
     if (pads[1] > 0) {
         if (pads[1] > c.V_e) { set_error("pad row (entity) out of range"); return KPRN_EINVAL; }
         KPRN_CUDA(cudaMemsetAsync(ctx->d_params + l.E_e + (pads[1] - 1) * c.d_e, 0, sizeof(float) * c.d_e, ctx->stream));
-        __nv_bfloat16 *hi = nullptr, *lo = nullptr; int KE = 0, fmt = 1; const float* esc = nullptr;
-        packed_entity(ctx, &hi, &lo, &KE, &fmt, &esc);
+        __nv_bfloat16 *hi = nullptr, *lo = nullptr; int KE = 0;
+        packed_entity(ctx, &hi, &lo, &KE);
         if (hi) {
             KPRN_CUDA(cudaMemsetAsync(hi + (pads[1] - 1) * KE, 0, sizeof(__nv_bfloat16) * KE, ctx->stream));
             KPRN_CUDA(cudaMemsetAsync(lo + (pads[1] - 1) * KE, 0, sizeof(__nv_bfloat16) * KE, ctx->stream));
@@ -441,8 +423,8 @@ static int rows_launch(kprn_ctx* ctx, TrainState* tr, const int32_t* rows, const
     a.last_t = tr->last_t; a.base_t = tr->base_t; a.dense_ever = tr->dense_ever ? 1 : 0;
     a.t_now = t_now; a.apply = apply; a.g = g; a.g_stride = c.d_e; a.recv_g = recv_g; a.contrib = contrib; a.world = ctx->world; a.maxK = maxK;
     a.gscale = gscale; a.steps = tr->steps.as<float>(); a.b1 = tr->b1; a.b2 = tr->b2; a.eps = tr->eps; a.d_e = c.d_e;
-    a.E_hi = nullptr; a.E_lo = nullptr; a.KE = 0; a.fmt = 1; a.escale = nullptr;
-    packed_entity(ctx, &a.E_hi, &a.E_lo, &a.KE, &a.fmt, &a.escale);
+    a.E_hi = nullptr; a.E_lo = nullptr; a.KE = 0;
+    packed_entity(ctx, &a.E_hi, &a.E_lo, &a.KE);
     int64_t grid = cdiv(grid_hint, 8) < 148 * 8 ? (grid_hint < 1 ? 1 : cdiv(grid_hint, 8)) : 148 * 8;      // 8 warps per block, a warp per row
     if (c.d_e == 256) adam_rows_kernel<2><<<(unsigned)grid, 256, 0, ctx->stream>>>(a);
     else if (c.d_e == 128) adam_rows_kernel<1><<<(unsigned)grid, 256, 0, ctx->stream>>>(a);
