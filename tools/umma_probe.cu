@@ -130,5 +130,25 @@ int main() {
         run(v ? "MN-major A', SW128 MN-major B (LBO=1024 k, SBO=16384 panel)" : "MN-major A', SW128 MN-major B (LBO=16384 panel, SBO=1024 k)", Xi, Ys, a,
             [&](int m, int n) { double s = 0; for (int k = 0; k < 128; ++k) s += X[k * 128 + m] * Y[k * 256 + n]; return s; });
     }
+    // 4. how the tensor core adds a K=16 block to the fp32 accumulator: acc = 1.0, then seven blocks of +0.75 ulp(1.0) each.
+    //    round-to-nearest per block -> 1 + 7 ulp;  exact / wide accumulator -> 1 + 5 ulp (5.25 rounded);  truncation -> 1.0
+    {
+        std::vector<bf16> Aq(128 * 128, __float2bfloat16(0.f)), Bq(128 * 256, __float2bfloat16(0.f));
+        auto seti = [&](std::vector<bf16>& v, int r, int c, float x) { v[((c / 8) * 128 + r) * 8 + c % 8] = __float2bfloat16(x); };
+        for (int r = 0; r < 128; ++r) {
+            seti(Aq, r, 0, 1.0f); seti(Bq, r, 0, 1.0f);
+            for (int kb = 1; kb < 8; ++kb) { seti(Aq, r, kb * 16, 1.5f); seti(Bq, r, kb * 16, 5.9604644775390625e-08f); }     // 2^-24
+        }
+        Args a = {}; a.a_mode = 0; a.b_mode = 0; a.a_lbo = 2048; a.a_sbo = 128; a.b_lbo = 2048; a.b_sbo = 128; a.N = 128; a.nk16 = 8; a.a_k16 = 4096; a.b_k16 = 4096;
+        cudaMemcpy(dA, Aq.data(), 32768, cudaMemcpyHostToDevice);
+        cudaMemcpy(dB, Bq.data(), 65536, cudaMemcpyHostToDevice);
+        a.A = dA; a.B = dB; a.D = dD;
+        probe_kernel<<<1, 128, 100 * 1024>>>(a);
+        cudaDeviceSynchronize();
+        cudaMemcpy(D.data(), dD, 128 * 128 * 4, cudaMemcpyDeviceToHost);
+        const double ulp = 1.1920928955078125e-07;
+        printf("fp32 accumulation of 1.0 + 7 x 0.75 ulp: (D - 1) / ulp = %.3f   [7 = round-to-nearest per block, 5 = exact sum rounded once, 0 = truncation]\n",
+               ((double)D[0] - 1.0) / ulp);
+    }
     return 0;
 }
