@@ -39,6 +39,11 @@ struct TcTrain {
     cudaStream_t side = nullptr;
     bool use_side = true;
     cudaEvent_t ev_fork = nullptr, ev_loop = nullptr, ev_prep = nullptr, ev_eg = nullptr;
+    // the BPTT loop walks the batch as two tile groups on two streams: cell_bwd (HBM-bound, 256-thread blocks) of one group runs
+    // on the SMs beside the resident bgemm CTAs (tensor-bound, registers capped) of the other
+    cudaStream_t side2 = nullptr;
+    cudaEvent_t ev_g0 = nullptr, ev_g1 = nullptr;
+    bool use_groups = true;
     DedupBufs es;                     // distinct entity rows of the batch when the caller (a sparse training step) did not build them
 };
 
@@ -89,6 +94,7 @@ struct CellBwdArgs {
     float* dc;                // [tile][Hp/8][row 128][8] in/out (first step: treated as 0)
     bf16* dgop;               // [tile][t][hi|lo][kc G4/8][row 128][8]
     int G4;
+    int64_t m_begin;          // first tile of this launch (the backward walks the batch in tile groups on two streams)
 };
 
 __device__ __forceinline__ void split8_store(const float* v, bf16* hi, bf16* lo) {
@@ -105,9 +111,11 @@ __device__ __forceinline__ void split8_store(const float* v, bf16* hi, bf16* lo)
     *reinterpret_cast<uint4*>(lo) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
 }
 
-__global__ void __launch_bounds__(512) cell_bwd_kernel(CellBwdArgs a) {
-    const int64_t m = blockIdx.x;
-    const int j = blockIdx.y, r = threadIdx.x, sb = threadIdx.y;
+// grid (tiles of the group, NCH, 2), block (128 rows, 2 sub-blocks): 256-thread blocks of ~21 k registers, so that they fit on an SM
+// beside a resident bgemm CTA of the other tile group (see tc_backward)
+__global__ void __launch_bounds__(256) cell_bwd_kernel(CellBwdArgs a) {
+    const int64_t m = a.m_begin + blockIdx.x;
+    const int j = blockIdx.y, r = threadIdx.x, sb = blockIdx.z * 2 + threadIdx.y;
     const int64_t n = m * TILE_M + r;
     const bool live = n < a.N;
     const size_t step_floats = (size_t)a.NCH * 20480;
@@ -169,13 +177,15 @@ __global__ void __launch_bounds__(512) cell_bwd_kernel(CellBwdArgs a) {
 
 struct BgArgs {
     const bf16* dgop; const bf16* WT; int T; int t; int G4; int N0, N1; int64_t num_tiles; int64_t N;
+    int64_t m_begin;          // tiles [m_begin, m_begin + num_tiles) of the batch
     int part_begin;           // 1 at t = 0 (no dh needed)
     float* dh;                // [tile][N0/8][row 128][8]
     float* dX;                // [(tile*T + t)*128 + row][N1] fp32: the entity-slice input gradient of every path-step (row index =
                               // the read-order index o of the slot maps); summed per entity row by the sorted segment reduce below
 };
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BG_THREADS, 1) bgemm_kernel(BgArgs a) {
+// __maxnreg__(112): 384 x 112 registers leave room on the SM for a 256-thread cell_bwd block of the other tile group
+__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(112) bgemm_kernel(BgArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = ptx::cluster_ctarank();
@@ -204,7 +214,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BG_THREADS, 1) bgemm
 
     const int64_t npairs = gridDim.x / 2, pair = blockIdx.x / 2, n_tp = (a.num_tiles + 1) / 2;
     const int64_t my_tiles = pair < n_tp ? (n_tp - pair + npairs - 1) / npairs : 0;
-    auto tile_of = [&](int64_t it) -> int64_t { const int64_t m = 2 * (pair + it * npairs) + rank; return m < a.num_tiles ? m : a.num_tiles - 1; };
+    auto tile_of = [&](int64_t it) -> int64_t { const int64_t m = 2 * (pair + it * npairs) + rank; return a.m_begin + (m < a.num_tiles ? m : a.num_tiles - 1); };
     const int KSg = a.G4 / 64;
     const size_t hl = (size_t)(a.G4 / 8) * TILE_M * 8;               // elements of one of hi / lo of a dgop tile
     const int64_t per0 = (int64_t)KSg * 2 * 8 * a.N0 * 8;            // elements of part 0 of WT
@@ -862,8 +872,10 @@ int tc_backward(kprn_ctx* ctx, float scale) {
     KPRN_TRY(tc_train_pack(ctx));
     if (!tt->side) {
         KPRN_CUDA(cudaStreamCreateWithFlags(&tt->side, cudaStreamNonBlocking));
-        for (cudaEvent_t* e : {&tt->ev_fork, &tt->ev_loop, &tt->ev_prep, &tt->ev_eg}) KPRN_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+        KPRN_CUDA(cudaStreamCreateWithFlags(&tt->side2, cudaStreamNonBlocking));
+        for (cudaEvent_t* e : {&tt->ev_fork, &tt->ev_loop, &tt->ev_prep, &tt->ev_eg, &tt->ev_g0, &tt->ev_g1}) KPRN_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     }
+    { const char* d = getenv("KPRN_TC_GROUPS"); tt->use_groups = !(d && d[0] == '0'); }
     { const char* d = getenv("KPRN_TC_SIDE"); tt->use_side = !(d && d[0] == '0'); }
     cudaStream_t side = tt->use_side ? tt->side : ctx->stream;
     // ---- pool / head gradients on the fp32 kernels (kernels_simple.cu): ds_c[p], gbo[c], gWo[c,:] ----
@@ -913,22 +925,31 @@ int tc_backward(kprn_ctx* ctx, float scale) {
     }
     const size_t bg_smem = BG_STAGES * (2 * 16384 + 2 * 8 * (Hp / 2) * 16 + 2 * 8 * (KE / 2) * 16) + 256;
     KPRN_CUDA(cudaFuncSetAttribute(bgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bg_smem));
-    const int64_t n_tp = (ptiles + 1) / 2;
-    const unsigned bg_grid = (unsigned)(2 * (n_tp < s->num_sms / 2 ? n_tp : s->num_sms / 2));
+    const int groups = (tt->use_groups && ptiles >= 8) ? 2 : 1;
+    const int64_t half = groups == 2 ? (ptiles / 2 + 1) / 2 * 2 : ptiles;          // even: no duplicated tail tile inside a group
+    cudaStream_t gstream[2] = {ctx->stream, tt->side2};
+    if (groups == 2) { KPRN_CUDA(cudaEventRecord(tt->ev_g0, ctx->stream)); KPRN_CUDA(cudaStreamWaitEvent(tt->side2, tt->ev_g0, 0)); }
     for (int t = T - 1; t >= 0; --t) {
-        CellBwdArgs ca;
-        ca.cache = tt->cache.as<float>(); ca.T = T; ca.t = t; ca.NCH = s->NCH; ca.H = c.H; ca.N = N;
-        ca.dh = t == T - 1 ? nullptr : tt->dh.as<float>(); ca.ds_c = ds_c; ca.wo = P + l.Wo + (int64_t)(c.class_id - 1) * c.H;
-        ca.dc = tt->dc.as<float>(); ca.dgop = tt->dgop.as<bf16>(); ca.G4 = G4;
-        cell_bwd_kernel<<<dim3((unsigned)ptiles, (unsigned)s->NCH), dim3(TILE_M, 4), 0, ctx->stream>>>(ca);
-        KPRN_LAUNCH_CHECK(ctx);
-        BgArgs ba;
-        ba.dgop = tt->dgop.as<bf16>(); ba.WT = tt->WT; ba.T = T; ba.t = t; ba.G4 = G4; ba.N0 = Hp; ba.N1 = KE; ba.num_tiles = ptiles; ba.N = N;
-        ba.part_begin = t == 0 ? 1 : 0; ba.dh = tt->dh.as<float>();
-        ba.dX = tt->dX.as<float>();
-        bgemm_kernel<<<bg_grid, BG_THREADS, bg_smem, ctx->stream>>>(ba);
-        KPRN_LAUNCH_CHECK(ctx);
+        for (int g = 0; g < groups; ++g) {
+            const int64_t mb = g ? half : 0, cnt = groups == 2 ? (g ? ptiles - half : half) : ptiles;
+            CellBwdArgs ca;
+            ca.cache = tt->cache.as<float>(); ca.T = T; ca.t = t; ca.NCH = s->NCH; ca.H = c.H; ca.N = N;
+            ca.dh = t == T - 1 ? nullptr : tt->dh.as<float>(); ca.ds_c = ds_c; ca.wo = P + l.Wo + (int64_t)(c.class_id - 1) * c.H;
+            ca.dc = tt->dc.as<float>(); ca.dgop = tt->dgop.as<bf16>(); ca.G4 = G4; ca.m_begin = mb;
+            cell_bwd_kernel<<<dim3((unsigned)cnt, (unsigned)s->NCH, 2), dim3(TILE_M, 2), 0, gstream[g]>>>(ca);
+            KPRN_LAUNCH_CHECK(ctx);
+            BgArgs ba;
+            ba.dgop = tt->dgop.as<bf16>(); ba.WT = tt->WT; ba.T = T; ba.t = t; ba.G4 = G4; ba.N0 = Hp; ba.N1 = KE; ba.num_tiles = cnt; ba.N = N;
+            ba.m_begin = mb;
+            ba.part_begin = t == 0 ? 1 : 0; ba.dh = tt->dh.as<float>();
+            ba.dX = tt->dX.as<float>();
+            const int64_t n_tp = (cnt + 1) / 2;
+            const unsigned bg_grid = (unsigned)(2 * (n_tp < s->num_sms / 2 ? n_tp : s->num_sms / 2));
+            bgemm_kernel<<<bg_grid, BG_THREADS, bg_smem, gstream[g]>>>(ba);
+            KPRN_LAUNCH_CHECK(ctx);
+        }
     }
+    if (groups == 2) { KPRN_CUDA(cudaEventRecord(tt->ev_g1, tt->side2)); KPRN_CUDA(cudaStreamWaitEvent(ctx->stream, tt->ev_g1, 0)); }
     // ---- entity-table gradient: sorted segment reduce of the staged dX rows (side stream, beside the weight-gradient kernel) ----
     {
         if (tt->use_side) { KPRN_CUDA(cudaEventRecord(tt->ev_loop, ctx->stream)); KPRN_CUDA(cudaStreamWaitEvent(side, tt->ev_loop, 0)); }
@@ -1016,7 +1037,8 @@ void tc_train_destroy(kprn_ctx* ctx) {
     if (tt->WT) cudaFree(tt->WT);
     if (tt->side) {
         cudaStreamSynchronize(tt->side);
-        for (cudaEvent_t e : {tt->ev_fork, tt->ev_loop, tt->ev_prep, tt->ev_eg}) if (e) cudaEventDestroy(e);
+        if (tt->side2) { cudaStreamSynchronize(tt->side2); cudaStreamDestroy(tt->side2); }
+        for (cudaEvent_t e : {tt->ev_fork, tt->ev_loop, tt->ev_prep, tt->ev_eg, tt->ev_g0, tt->ev_g1}) if (e) cudaEventDestroy(e);
         cudaStreamDestroy(tt->side);
     }
     for (DBuf* b : {&tt->cache, &tt->hcache, &tt->dgop, &tt->dh, &tt->dc, &tt->wpart, &tt->gP, &tt->cls, &tt->dX, &tt->eg_keys, &tt->eg_vals,
