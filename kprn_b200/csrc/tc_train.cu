@@ -332,6 +332,281 @@ __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(112) bgemm_kernel(BgArgs a
     if (warp == 2) ptx::tmem_dealloc2(tmem, 512);
 }
 
+// ---------------------------------------------------------------------------------------------
+// bptt_kernel: the whole time loop of the backward in ONE persistent launch -- cell_bwd_kernel's arithmetic as the producer of
+// bgemm_kernel's A operand.  A CTA pair keeps a pair of path tiles for all T steps:
+//   cell warps (16; thread = path row x 8 hidden units, the mapping of the recurrence epilogue)
+//       read cache_t / c_{t-1} / dh_t / dc, write dG_t as bf16 hi/lo straight into the shared-memory stage the MMAs read (and to
+//       dgop for the weight-gradient kernel), a 64-column K slice at a time: slice 2j = gates i,g of units [32j, 32j+32), slice
+//       2j+1 = gates f,o of the same units
+//   warp 0 streams the matching [Wh^T | Wx_e^T] slices (TMA bulk), warp 1 of the leader issues the cta_group::2 MMAs
+//   after the 16 slices of a step the cell warps drain TMEM: dh_{t-1} -> a tile-private fp32 buffer (written and re-read by the
+//       same thread 20-30 us later: it lives in L2), dX_t -> the staged entity-gradient rows
+// Against the cell_bwd + bgemm pair of launches per step this removes bgemm's read of dgop and the DRAM round trips of dh and dc
+// (10 KB instead of 18.7 KB of DRAM traffic per path-step) and every launch boundary of the loop.
+constexpr int BP_THREADS = 640;       // warp 0 TMA producer, 1 MMA issuer / peer forwarder, 2 TMEM alloc, 3 idle, 4-19 cell + drain
+
+struct BpArgs {
+    const float* cache; const bf16* WT; bf16* dgop; float* dh; float* dc; float* dX;
+    const float* ds_c; const float* wo;
+    int T, NCH, H, G4, N0, N1; int64_t num_tiles, N;
+};
+
+__device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
+    uint32_t wh[4], wl[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h2);
+        const float r0 = v[2 * i] - __uint_as_float(hb << 16), r1 = v[2 * i + 1] - __uint_as_float(hb & 0xFFFF0000u);
+        const __nv_bfloat162 l2 = __floats2bfloat162_rn(r0, r1);
+        wh[i] = hb; wl[i] = *reinterpret_cast<const uint32_t*>(&l2);
+    }
+    hi = make_uint4(wh[0], wh[1], wh[2], wh[3]);
+    lo = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+}
+__device__ __forceinline__ void ld8(const float* p, float* v) {
+    const float4 a = __ldcg(reinterpret_cast<const float4*>(p)), b = __ldcg(reinterpret_cast<const float4*>(p) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+// one cache array of a thread's 8 units: [half 2][row 128][4]; streaming (read once) / c (read by two consecutive steps)
+__device__ __forceinline__ void ld_cache8c(const float* p, float* v) {
+    const float4 a = __ldcg(reinterpret_cast<const float4*>(p)), b = __ldcg(reinterpret_cast<const float4*>(p + 512));
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void ld_cache8(const float* p, float* v) {
+    const float4 a = __ldcs(reinterpret_cast<const float4*>(p)), b = __ldcs(reinterpret_cast<const float4*>(p + 512));
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BP_THREADS, 1) bptt_kernel(BpArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = ptx::cluster_ctarank();
+    const bool leader = rank == 0;
+    constexpr int S = BG_STAGES;
+    const int Nh0 = a.N0 / 2, Nh1 = a.N1 / 2;
+    const uint32_t A_BYTES = 16384;                                   // one of hi / lo of a 64-wide k-slice: [kc 8][row 128][16 B]
+    const uint32_t B0_BYTES = 8u * Nh0 * 16, B1_BYTES = 8u * Nh1 * 16;
+    const uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B0_BYTES + 2 * B1_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * STAGE_BYTES);
+    const uint32_t bar0 = ptx::smem_u32(bars);
+    auto BAR = [&](int i) { return bar0 + 8u * i; };
+    // [0,S) full (B bytes + 16 cell warps)  [S,2S) empty  [2S,3S) peer_full (leader)  3S acc_full  3S+1 acc_empty (leader)
+    constexpr int B_PEER = 2 * S, B_ACCF = 3 * S, B_ACCE = 3 * S + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_ACCE + 1);
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < S; ++i) { ptx::mbar_init(BAR(i), 17); ptx::mbar_init(BAR(S + i), 1); ptx::mbar_init(BAR(B_PEER + i), 1); }
+        ptx::mbar_init(BAR(B_ACCF), 1); ptx::mbar_init(BAR(B_ACCE), 32);
+        ptx::fence_mbar_init();
+    }
+    if (warp == 2) { ptx::tmem_alloc2(ptx::smem_u32(tmem_slot), 512); ptx::tmem_relinquish2(); }
+    ptx::tc_fence_before();
+    ptx::cluster_sync();
+    ptx::tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    const int64_t npairs = gridDim.x / 2, pair = blockIdx.x / 2, n_tp = (a.num_tiles + 1) / 2;
+    const int64_t my_tiles = pair < n_tp ? (n_tp - pair + npairs - 1) / npairs : 0;
+    const int KSg = a.G4 / 64, T = a.T;
+    const size_t hl = (size_t)(a.G4 / 8) * TILE_M * 8;               // elements of one of hi / lo of a dgop tile
+    const int64_t per0 = (int64_t)KSg * 2 * 8 * a.N0 * 8;            // elements of part 0 of WT
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int64_t it = 0; it < my_tiles; ++it)
+                for (int t = T - 1; t >= 0; --t)
+                    for (int ks = 0; ks < KSg; ++ks) {
+                        ptx::mbar_wait(BAR(S + stage), phase ^ 1);
+                        ptx::mbar_arrive_expect_tx(BAR(stage), (t > 0 ? 2 * B0_BYTES : 0) + 2 * B1_BYTES);
+                        const uint32_t sb0 = ptx::smem_u32(smem + stage * STAGE_BYTES) + 2 * A_BYTES;
+                        if (t > 0) {
+                            const bf16* W0 = a.WT + (((int64_t)ks * 2 + 0) * 2 + rank) * (8 * Nh0 * 8);
+                            ptx::tma_bulk_g2s(sb0, W0, B0_BYTES, BAR(stage));
+                            ptx::tma_bulk_g2s(sb0 + B0_BYTES, W0 + (int64_t)2 * 8 * Nh0 * 8, B0_BYTES, BAR(stage));
+                        }
+                        const bf16* W1 = a.WT + per0 + (((int64_t)ks * 2 + 0) * 2 + rank) * (8 * Nh1 * 8);
+                        ptx::tma_bulk_g2s(sb0 + 2 * B0_BYTES, W1, B1_BYTES, BAR(stage));
+                        ptx::tma_bulk_g2s(sb0 + 2 * B0_BYTES + B1_BYTES, W1 + (int64_t)2 * 8 * Nh1 * 8, B1_BYTES, BAR(stage));
+                        if (++stage == S) { stage = 0; phase ^= 1; }
+                    }
+        }
+    } else if (warp == 1) {
+        if (leader) {
+            const bool issue = ptx::elect_one();
+            uint32_t stage = 0, phase = 0, e = 0;
+            constexpr uint32_t DHI = ptx::desc_hi(128);
+            const uint32_t idesc0 = ptx::make_idesc_f16(1, 256, a.N0), idesc1 = ptx::make_idesc_f16(1, 256, a.N1);
+            for (int64_t it = 0; it < my_tiles; ++it)
+                for (int t = T - 1; t >= 0; --t, ++e) {
+                    ptx::mbar_wait_cluster(BAR(B_ACCE), (e & 1) ^ 1);
+                    ptx::tc_fence_after();
+                    for (int ks = 0; ks < KSg; ++ks) {
+                        ptx::mbar_wait(BAR(stage), phase);
+                        ptx::mbar_wait_cluster(BAR(B_PEER + stage), phase);
+                        ptx::tc_fence_after();
+                        const uint32_t sb0 = ptx::smem_u32(smem + stage * STAGE_BYTES);
+                        const uint32_t ah = ptx::desc_lo(sb0, 2048), al = ptx::desc_lo(sb0 + A_BYTES, 2048);
+                        if (issue) {
+                            for (int part = (t > 0 ? 0 : 1); part < 2; ++part) {
+                                const uint32_t Nh = part ? Nh1 : Nh0;
+                                const uint32_t boff = 2 * A_BYTES + (part ? 2 * B0_BYTES : 0), bbytes = part ? B1_BYTES : B0_BYTES;
+                                const uint32_t bh = ptx::desc_lo(sb0 + boff, Nh * 16), bl = ptx::desc_lo(sb0 + boff + bbytes, Nh * 16);
+                                const uint32_t k16b = (2 * Nh * 16) >> 4;
+                                const uint32_t d = tmem + part * 256;
+                                const uint32_t idesc = part ? idesc1 : idesc0;
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)
+                                    ptx::umma2_f16(d, ptx::desc_join(DHI, ah + k * 256u), ptx::desc_join(DHI, bh + k * k16b), idesc, (ks | k) != 0);
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)
+                                    ptx::umma2_f16(d, ptx::desc_join(DHI, al + k * 256u), ptx::desc_join(DHI, bh + k * k16b), idesc, 1);
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)
+                                    ptx::umma2_f16(d, ptx::desc_join(DHI, ah + k * 256u), ptx::desc_join(DHI, bl + k * k16b), idesc, 1);
+                            }
+                            ptx::umma2_commit(BAR(S + stage), 3);
+                        }
+                        if (++stage == S) { stage = 0; phase ^= 1; }
+                    }
+                    if (issue) ptx::umma2_commit(BAR(B_ACCF), 3);
+                }
+        } else if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            const uint32_t remote = ptx::mapa(BAR(B_PEER), 0);
+            for (int64_t it = 0; it < my_tiles; ++it)
+                for (int64_t q = 0; q < (int64_t)T * KSg; ++q) {
+                    ptx::mbar_wait(BAR(stage), phase);
+                    ptx::mbar_arrive_cluster(remote + 8u * stage);
+                    if (++stage == S) { stage = 0; phase ^= 1; }
+                }
+        }
+    } else if (warp >= 4) {
+        // ===== cell warps: warp (q4, sb) owns path rows q4*32 + lane (its TMEM lane quarter) and the sb-th 8-unit group of a round =====
+        const int q4 = warp & 3, sb = (warp - 4) >> 2, r = q4 * 32 + lane;
+        const uint32_t acce_leader = ptx::mapa(BAR(B_ACCE), 0);
+        const size_t step_floats = (size_t)a.NCH * 20480;
+        const uint32_t tb = tmem + ((uint32_t)(q4 * 32) << 16);
+        const int xcols = a.N1 / 4;                                   // dX columns this warp drains
+        uint32_t stage = 0, phase = 0, e = 0;
+        for (int64_t it = 0; it < my_tiles; ++it) {
+            const int64_t mraw = 2 * (pair + it * npairs) + rank;
+            const bool dup = mraw >= a.num_tiles;                     // odd tile count: the pair's second CTA recomputes the last tile, stores nothing
+            const int64_t m = dup ? a.num_tiles - 1 : mraw;
+            const int64_t n = m * TILE_M + r;
+            const bool live = n < a.N;
+            const float s_c = live ? a.ds_c[n] : 0.f;
+            for (int t = T - 1; t >= 0; --t, ++e) {
+                const float* cstep = a.cache + (size_t)(m * T + t) * step_floats + r * 4;
+                bf16* gbase = a.dgop + (size_t)(m * T + t) * 2 * hl + (size_t)r * 8;
+                for (int j = 0; j < a.NCH; ++j) {
+                    const int grp = j * 4 + sb;
+                    const float* ct = cstep + (size_t)grp * 5120;
+                    const size_t gi8 = ((size_t)(m * (a.G4 / 32) + grp) * TILE_M + r) * 8;
+                    float dcu[8], dO[8], di[8], dg[8];
+                    {
+                        float gi[8], gg[8], go[8], cc[8], dh[8], dc[8];
+                        ld_cache8(ct, gi); ld_cache8(ct + 1024, gg); ld_cache8(ct + 3072, go); ld_cache8c(ct + 4096, cc);
+                        if (t < T - 1) { ld8(a.dh + gi8, dh); ld8(a.dc + gi8, dc); }
+                        else {
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) { const int u = grp * 8 + q; dh[q] = u < a.H ? s_c * a.wo[u] : 0.f; dc[q] = 0.f; }
+                        }
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const float tc = tanhf(cc[q]);
+                            const float d_o = dh[q] * tc;
+                            dcu[q] = dc[q] + dh[q] * go[q] * (1.f - tc * tc);
+                            di[q] = live ? dcu[q] * gg[q] * gi[q] * (1.f - gi[q]) : 0.f;
+                            dg[q] = live ? dcu[q] * gi[q] * (1.f - gg[q] * gg[q]) : 0.f;
+                            dO[q] = live ? d_o * go[q] * (1.f - go[q]) : 0.f;
+                        }
+                    }
+                    float gf[8], cp[8];
+                    ld_cache8(ct + 2048, gf);
+                    if (t > 0) ld_cache8c(ct - step_floats + 4096, cp);
+                    else {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) cp[q] = 0.f;
+                    }
+                    // ---- slice 2j: gates i, g ----
+                    uint4 h0, l0, h1, l1;
+                    split8(di, h0, l0); split8(dg, h1, l1);
+                    ptx::mbar_wait(BAR(S + stage), phase ^ 1);
+                    {
+                        uint8_t* sA = smem + stage * STAGE_BYTES + ((size_t)sb * TILE_M + r) * 16;
+                        *reinterpret_cast<uint4*>(sA) = h0; *reinterpret_cast<uint4*>(sA + A_BYTES) = l0;
+                        *reinterpret_cast<uint4*>(sA + 4 * TILE_M * 16) = h1; *reinterpret_cast<uint4*>(sA + 4 * TILE_M * 16 + A_BYTES) = l1;
+                    }
+                    ptx::fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(BAR(stage));
+                    if (++stage == S) { stage = 0; phase ^= 1; }
+                    if (!dup) {
+                        bf16* g0 = gbase + (size_t)(j * 16 + sb) * TILE_M * 8;
+                        *reinterpret_cast<uint4*>(g0) = h0; *reinterpret_cast<uint4*>(g0 + hl) = l0;
+                        *reinterpret_cast<uint4*>(g0 + 4 * TILE_M * 8) = h1; *reinterpret_cast<uint4*>(g0 + 4 * TILE_M * 8 + hl) = l1;
+                    }
+                    // ---- slice 2j+1: gates f, o ----
+                    float df[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        df[q] = live ? dcu[q] * cp[q] * gf[q] * (1.f - gf[q]) : 0.f;
+                        dcu[q] *= gf[q];                                                       // dc for step t-1
+                    }
+                    split8(df, h0, l0); split8(dO, h1, l1);
+                    ptx::mbar_wait(BAR(S + stage), phase ^ 1);
+                    {
+                        uint8_t* sA = smem + stage * STAGE_BYTES + ((size_t)sb * TILE_M + r) * 16;
+                        *reinterpret_cast<uint4*>(sA) = h0; *reinterpret_cast<uint4*>(sA + A_BYTES) = l0;
+                        *reinterpret_cast<uint4*>(sA + 4 * TILE_M * 16) = h1; *reinterpret_cast<uint4*>(sA + 4 * TILE_M * 16 + A_BYTES) = l1;
+                    }
+                    ptx::fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(BAR(stage));
+                    if (++stage == S) { stage = 0; phase ^= 1; }
+                    if (!dup) {
+                        bf16* g0 = gbase + (size_t)(j * 16 + 8 + sb) * TILE_M * 8;
+                        *reinterpret_cast<uint4*>(g0) = h0; *reinterpret_cast<uint4*>(g0 + hl) = l0;
+                        *reinterpret_cast<uint4*>(g0 + 4 * TILE_M * 8) = h1; *reinterpret_cast<uint4*>(g0 + 4 * TILE_M * 8 + hl) = l1;
+                        if (t > 0) ptx::stg256(a.dc + gi8, dcu);
+                    }
+                }
+                // ---- drain: dh_{t-1} (this thread's own groups) and this warp's quarter of the dX_t columns ----
+                ptx::mbar_wait(BAR(B_ACCF), e & 1);
+                ptx::tc_fence_after();
+                if (t > 0) {
+                    for (int j = 0; j < a.NCH; ++j) {
+                        float v[8];
+                        ptx::tmem_ld8(tb + (uint32_t)(j * 4 + sb) * 8, v);
+                        ptx::tc_wait_ld();
+                        if (!dup) ptx::stg256(a.dh + ((size_t)(m * (a.G4 / 32) + j * 4 + sb) * TILE_M + r) * 8, v);
+                    }
+                }
+                {
+                    float* dst = a.dX + ((size_t)(m * T + t) * TILE_M + r) * a.N1 + sb * xcols;
+                    for (int blk = 0; blk < xcols / 32; ++blk) {
+                        float v[32];
+                        ptx::tmem_ld32(tb + 256 + sb * xcols + blk * 32, v);
+                        ptx::tc_wait_ld();
+                        if (!dup) {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) ptx::stg256(dst + blk * 32 + 8 * i, v + 8 * i);
+                        }
+                    }
+                }
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive_cluster(acce_leader);
+            }
+        }
+    }
+    ptx::tc_fence_before();
+    ptx::cluster_sync();
+    if (warp == 2) ptx::tmem_dealloc2(tmem, 512);
+}
+
 
 // Operands of the weight-gradient product, staged once per backward in the layout its stages consume.  A stage of
 // wgrad_kernel is 64 path rows; the TMA unit sustains roughly one contiguous segment per ~55 cycles per SM whatever its size
@@ -925,7 +1200,21 @@ int tc_backward(kprn_ctx* ctx, float scale) {
     }
     const size_t bg_smem = BG_STAGES * (2 * 16384 + 2 * 8 * (Hp / 2) * 16 + 2 * 8 * (KE / 2) * 16) + 256;
     KPRN_CUDA(cudaFuncSetAttribute(bgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bg_smem));
-    const int groups = (tt->use_groups && ptiles >= 8) ? 2 : 1;
+    bool fused = true;
+    { const char* d = getenv("KPRN_TC_FUSED"); if (d && d[0] == '0') fused = false; }
+    if (fused) {
+        // the whole time loop in one persistent launch (bptt_kernel)
+        BpArgs pa;
+        pa.cache = tt->cache.as<float>(); pa.WT = tt->WT; pa.dgop = tt->dgop.as<bf16>(); pa.dh = tt->dh.as<float>(); pa.dc = tt->dc.as<float>();
+        pa.dX = tt->dX.as<float>(); pa.ds_c = ds_c; pa.wo = P + l.Wo + (int64_t)(c.class_id - 1) * c.H;
+        pa.T = T; pa.NCH = s->NCH; pa.H = c.H; pa.G4 = G4; pa.N0 = Hp; pa.N1 = KE; pa.num_tiles = ptiles; pa.N = N;
+        KPRN_CUDA(cudaFuncSetAttribute(bptt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bg_smem));
+        const int64_t n_tp = (ptiles + 1) / 2;
+        const unsigned bp_grid = (unsigned)(2 * (n_tp < s->num_sms / 2 ? n_tp : s->num_sms / 2));
+        bptt_kernel<<<bp_grid, BP_THREADS, bg_smem, ctx->stream>>>(pa);
+        KPRN_LAUNCH_CHECK(ctx);
+    }
+    const int groups = fused ? 0 : (tt->use_groups && ptiles >= 8) ? 2 : 1;
     const int64_t half = groups == 2 ? (ptiles / 2 + 1) / 2 * 2 : ptiles;          // even: no duplicated tail tile inside a group
     cudaStream_t gstream[2] = {ctx->stream, tt->side2};
     if (groups == 2) { KPRN_CUDA(cudaEventRecord(tt->ev_g0, ctx->stream)); KPRN_CUDA(cudaStreamWaitEvent(tt->side2, tt->ev_g0, 0)); }

@@ -132,3 +132,24 @@ def test_tc_training_forward_backward_match_oracle(kw):
     for name in o.shapes():
         assert_rel(o.view(g, name), o.view(g_ref, name), rtol=5e-4, what="grad " + name)
     e.close()
+
+
+@pytest.mark.parametrize("kw", [TRAIN_CASES[1], TRAIN_CASES[3], dict(N=128 * 5 + 17, seed=35, d_t=16, d_e=128, d_r=16, H=200, V_e=900)])
+def test_fused_bptt_kernel_equals_the_per_step_kernels(kw, monkeypatch):
+    """bptt_kernel (one persistent launch for the whole time loop) runs the same arithmetic in the same order as the
+    cell_bwd_kernel + bgemm_kernel launches per step (odd tile counts included); the two compilations may contract the cell
+    arithmetic into FMAs differently, so the gradients agree to fp32 rounding (1e-5 of each tensor's scale), not bitwise."""
+    o, params, ids, seg, labels = make_case(**kw)
+    got = []
+    for fused in ("1", "0"):
+        monkeypatch.setenv("KPRN_TC_FUSED", fused)
+        e = engine_for(o, precision=3)
+        e.set_params(params)
+        e.zero_grad()
+        e.forward(ids, seg, train=True)
+        e.loss_bce(labels)
+        e.backward()
+        got.append(e.get_grads().copy())
+        e.close()
+    for name in o.shapes():
+        assert_rel(o.view(got[0], name), o.view(got[1], name), rtol=1e-5, what="grad " + name)
