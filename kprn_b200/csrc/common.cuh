@@ -86,6 +86,11 @@ struct kprn_ctx {
     const uint32_t* sparse_pos = nullptr;
     const uint32_t* sparse_slot_of = nullptr;
     bool in_train_step = false;
+    // a sparse training step without gradient clipping lets the entity-row optimizer run on the backward's side stream, beside
+    // the weight-gradient kernel: tc_backward then leaves the join of that stream to the caller (eg_stream / eg_event set)
+    bool defer_eg_join = false;
+    cudaStream_t eg_stream = nullptr;
+    cudaEvent_t eg_event = nullptr;
     double* last_loss = nullptr;    // device scalar of the last training step's loss
     int opt_dedup = -1;                 // kprn_set_option("dedup"): -1 = KPRN_TC_DEDUP / default (on), 0 / 1 = forced
 };

@@ -1315,7 +1315,10 @@ int tc_backward(kprn_ctx* ctx, float scale) {
     ptr_wx_kernel<<<(unsigned)G4, 256, 0, ctx->stream>>>(Tsum, Rsum, P + l.E_t, P + l.E_r, G4, c.H, l.D, c.d_t, c.d_e, c.d_r, (int)c.V_t, (int)c.V_r,
                                                         gr + l.Wx);
     KPRN_LAUNCH_CHECK(ctx);
-    if (tt->use_side) KPRN_CUDA(cudaStreamWaitEvent(ctx->stream, tt->ev_eg, 0));      // join: everything after sees the entity gradient
+    if (tt->use_side) {
+        if (ctx->defer_eg_join) { ctx->eg_stream = side; ctx->eg_event = tt->ev_eg; }      // the caller continues on the side stream, then joins
+        else KPRN_CUDA(cudaStreamWaitEvent(ctx->stream, tt->ev_eg, 0));                    // join: everything after sees the entity gradient
+    }
     return KPRN_OK;
 }
 

@@ -415,7 +415,9 @@ static int zero_pad_rows(kprn_ctx* ctx, const int64_t* pads) {
 }
 
 static int rows_launch(kprn_ctx* ctx, TrainState* tr, const int32_t* rows, const int32_t* count, int64_t t_now, int apply, const float* g,
-                       const float* recv_g, const int32_t* contrib, int64_t maxK, const float* gscale, int64_t grid_hint) {
+                       const float* recv_g, const int32_t* contrib, int64_t maxK, const float* gscale, int64_t grid_hint,
+                       cudaStream_t stream = nullptr) {
+    if (!stream) stream = ctx->stream;
     const kprn_config& c = ctx->cfg;
     RowsArgs a;
     a.rows = rows; a.count = count;
@@ -426,9 +428,9 @@ static int rows_launch(kprn_ctx* ctx, TrainState* tr, const int32_t* rows, const
     a.E_hi = nullptr; a.E_lo = nullptr; a.KE = 0;
     packed_entity(ctx, &a.E_hi, &a.E_lo, &a.KE);
     int64_t grid = cdiv(grid_hint, 8) < 148 * 8 ? (grid_hint < 1 ? 1 : cdiv(grid_hint, 8)) : 148 * 8;      // 8 warps per block, a warp per row
-    if (c.d_e == 256) adam_rows_kernel<2><<<(unsigned)grid, 256, 0, ctx->stream>>>(a);
-    else if (c.d_e == 128) adam_rows_kernel<1><<<(unsigned)grid, 256, 0, ctx->stream>>>(a);
-    else adam_rows_kernel<0><<<(unsigned)grid, 256, 0, ctx->stream>>>(a);
+    if (c.d_e == 256) adam_rows_kernel<2><<<(unsigned)grid, 256, 0, stream>>>(a);
+    else if (c.d_e == 128) adam_rows_kernel<1><<<(unsigned)grid, 256, 0, stream>>>(a);
+    else adam_rows_kernel<0><<<(unsigned)grid, 256, 0, stream>>>(a);
     KPRN_LAUNCH_CHECK(ctx);
     return KPRN_OK;
 }
@@ -531,6 +533,7 @@ static int train_step_device(kprn_ctx* ctx, const int32_t* d_ids, const int32_t*
     }
 
     // ---- sparse flow ----
+    static const bool env_defer = !(getenv("KPRN_TRAIN_DEFER") && getenv("KPRN_TRAIN_DEFER")[0] == '0');      // diagnostics (A/B timing)
     if (tr->pending && (tr->b1 != o.beta1 || tr->b2 != o.beta2 || tr->eps != o.eps)) KPRN_TRY(train_flush(ctx));   // the replay uses latched constants
     tr->b1 = o.beta1; tr->b2 = o.beta2; tr->eps = o.eps;
     if (!tr->last_t) {
@@ -542,6 +545,8 @@ static int train_step_device(kprn_ctx* ctx, const int32_t* d_ids, const int32_t*
     KPRN_TRY(ensure(tr->gE, sizeof(float) * (size_t)N * c.T * c.d_e));
     const int64_t t_now = ctx->adam_t + 1;
     // 2. the rows this batch reads must be current before the forward
+    //    (measured: refreshing only the packed copies here and replaying x, m, v in the update kernel instead saves 3 KB of
+    //    traffic per row but runs the replay arithmetic twice -- 0.27 ms slower per step at the benchmark size)
     if (tr->pending) KPRN_TRY(rows_launch(ctx, tr, tr->es.ids.as<int32_t>(), tr->es.count.as<int32_t>(), t_now, 0, nullptr, nullptr, nullptr, 0, nullptr, N * c.T));
     // 3. pad rows, 4. zero the gradients this step writes
     KPRN_TRY(zero_pad_rows(ctx, pads));
@@ -552,10 +557,20 @@ static int train_step_device(kprn_ctx* ctx, const int32_t* d_ids, const int32_t*
     // 5. forward (training caches) -> criterion -> backward; the entity gradient lands in gE[slot]
     ctx->sparse_gE = tr->gE.as<float>(); ctx->sparse_pos = tr->es.pos.as<uint32_t>(); ctx->sparse_slot_of = tr->es.slot_of.as<uint32_t>();
     tr->sparse_grads = true; tr->sparse_N = N;
+    // the step counter and its step size go first: the row optimizer may run on the backward's side stream, which forks from this
+    // one inside the backward (rolled back if the step fails before the update)
+    ctx->adam_t = t_now;
+    struct Roll { kprn_ctx* c; bool done; ~Roll() { if (!done) { c->adam_t--; c->defer_eg_join = false; c->eg_stream = nullptr; } } } roll{ctx, false};
+    const float step = adam_step_size(o.lr, o.beta1, o.beta2, t_now);
+    KPRN_TRY(steps_push(ctx, tr, step));
+    const bool clip = o.regularize && o.use_clip;
+    ctx->defer_eg_join = !clip && ctx->world == 1 && env_defer;
+    ctx->eg_stream = nullptr;
     KPRN_TRY(forward_device_impl(ctx, d_ids, d_seg, N, S, true, false, nullptr, nullptr));
     if (o.loss == 0) KPRN_TRY(loss_bce_device(ctx, d_labels, S, &d_loss));
     else KPRN_TRY(loss_bpr_device(ctx, d_pos, d_neg, n_pairs, o.bpr_on_logits, &d_loss));
     KPRN_TRY(backward_device(ctx, gsc));
+    ctx->defer_eg_join = false;
     // 6. across GPUs: small tensors all-reduced, rows all-gathered
     const float* recv_g = nullptr; const int32_t* contrib = nullptr; int64_t maxK = 0;
     const int32_t* rows = tr->es.ids.as<int32_t>(); const int32_t* count = tr->es.count.as<int32_t>();
@@ -569,7 +584,7 @@ static int train_step_device(kprn_ctx* ctx, const int32_t* d_ids, const int32_t*
     }
     // 7. global-norm clip (MyOptimizer.lua:196-201) as a device scalar folded into the optimizer kernels
     const float* gscale = nullptr;
-    if (o.regularize && o.use_clip) {
+    if (clip) {
         KPRN_TRY(ensure(tr->norm2, 64));
         double* n2 = tr->norm2.as<double>();
         float* gs = reinterpret_cast<float*>(n2 + 1);
@@ -585,15 +600,18 @@ static int train_step_device(kprn_ctx* ctx, const int32_t* d_ids, const int32_t*
         gscale = gs;
     }
     // 8. optim.adam: dense on the small tensors, lazily-dense on the rows that received a gradient
-    ctx->adam_t = t_now;
-    const float step = adam_step_size(o.lr, o.beta1, o.beta2, t_now);
-    KPRN_TRY(steps_push(ctx, tr, step));
     adam_dense_kernel<<<148 * 2, 256, 0, ctx->stream>>>(ctx->d_params, ctx->d_grads, ctx->d_m, ctx->d_v, l.E_e, step, o.beta1, o.beta2, o.eps, gscale);
     KPRN_LAUNCH_CHECK(ctx);
     adam_dense_kernel<<<148 * 8, 256, 0, ctx->stream>>>(ctx->d_params + l.E_r, ctx->d_grads + l.E_r, ctx->d_m + l.E_r, ctx->d_v + l.E_r,
                                                        l.total - l.E_r, step, o.beta1, o.beta2, o.eps, gscale);
     KPRN_LAUNCH_CHECK(ctx);
-    KPRN_TRY(rows_launch(ctx, tr, rows, count, t_now, 1, tr->gE.as<float>(), recv_g, contrib, maxK, gscale, rows_bound));
+    KPRN_TRY(rows_launch(ctx, tr, rows, count, t_now, 1, tr->gE.as<float>(), recv_g, contrib, maxK, gscale, rows_bound, ctx->eg_stream));
+    if (ctx->eg_stream) {          // the rows were updated beside the weight-gradient kernel: join
+        KPRN_CUDA(cudaEventRecord(ctx->eg_event, ctx->eg_stream));
+        KPRN_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->eg_event, 0));
+        ctx->eg_stream = nullptr;
+    }
+    roll.done = true;
     tr->pending = true;                 // rows outside this batch are now one more step behind
     ctx->small_version++;
     // 9. pad rows again
