@@ -262,7 +262,7 @@ def main():
     ap.add_argument("--paths", type=int, default=N_PATHS)
     ap.add_argument("--precision", type=int, default=-1, help="-1 auto (tensor-core split if supported), 0 fp32, 1 split, 2 fast")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-extras", action="store_true", help="skip value_dedup_off / value_uniform_entities / e2e_f64ids")
+    ap.add_argument("--no-extras", action="store_true", help="skip value_dedup_off / value_prefix_off / value_uniform_entities / e2e_f64ids")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step block")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -403,6 +403,21 @@ def main():
             extras["value_dedup_off"] = {"value": n_paths / (ms * 1e-3), "unit": "paths/s", "ms_per_step": ms, "steps": xs,
                                          "note": "KPRN dedup knob off: projection runs on all N*T step inputs"}
             eng.set_option("dedup", -1)
+            # (1b) leading-token reuse off: every path steps through its own pads (and both knobs off: no data-dependent saving at all)
+            eng.set_option("prefix", 0)
+            for i in range(3):
+                step_device(i)
+            ms = time_device(eng, step_device, xs, stream, barrier)
+            extras["value_prefix_off"] = {"value": n_paths / (ms * 1e-3), "unit": "paths/s", "ms_per_step": ms, "steps": xs,
+                                          "note": "kprn_set_option('prefix', 0): the recurrence runs all T-1 products for every tile"}
+            eng.set_option("dedup", 0)
+            for i in range(3):
+                step_device(i)
+            ms = time_device(eng, step_device, xs, stream, barrier)
+            extras["value_dedup_prefix_off"] = {"value": n_paths / (ms * 1e-3), "unit": "paths/s", "ms_per_step": ms, "steps": xs,
+                                                "note": "both data-dependent savings off: N*T projections, N*(T-1) recurrent products"}
+            eng.set_option("dedup", -1)
+            eng.set_option("prefix", -1)
         # (2) uniform entities: no hot rows, worst case for the L2 and for the deduplication
         from kprn_b200 import synth
         ub = []

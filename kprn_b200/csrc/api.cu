@@ -774,6 +774,7 @@ int kprn_train_batch_bpr(kprn_ctx* ctx, const int32_t* ids, const int32_t* seg, 
 int kprn_set_option(kprn_ctx* ctx, const char* key, int64_t value) {
     if (!ctx || !key) { set_error("null argument"); return KPRN_EINVAL; }
     if (!strcmp(key, "dedup")) { ctx->opt_dedup = value < 0 ? -1 : (value != 0); return KPRN_OK; }
+    if (!strcmp(key, "prefix")) { ctx->opt_prefix = value < 0 ? -1 : (value != 0); return KPRN_OK; }
     set_error("set_option: unknown key '%s'", key);
     return KPRN_EINVAL;
 }

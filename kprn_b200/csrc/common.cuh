@@ -93,6 +93,7 @@ struct kprn_ctx {
     cudaEvent_t eg_event = nullptr;
     double* last_loss = nullptr;    // device scalar of the last training step's loss
     int opt_dedup = -1;                 // kprn_set_option("dedup"): -1 = KPRN_TC_DEDUP / default (on), 0 / 1 = forced
+    int opt_prefix = -1;                // kprn_set_option("prefix"): leading-token reuse in the scoring recurrence; -1 = KPRN_TC_PREFIX / default (on)
 };
 
 namespace kprn {

@@ -61,14 +61,6 @@ __global__ void split_entity_kernel(const float* __restrict__ E, int64_t V, int 
     hi[idx] = h; lo[idx] = l;
 }
 
-// The recurrent kernel evaluates the gates as sigmoid(x) = 1/(1+2^(-x log2 e)) and tanh(x) = 1 - 2/(1+2^(2x log2 e)) with
-// ex2.approx; the factor (-log2 e for i,f,o and +2 log2 e for g) is folded into the packed weights, the hoisted table and
-// hence XW and the accumulators, so the cell math needs no multiply in front of the four gate exponentials.
-__device__ __forceinline__ float gate_scale(int gp) {
-    const int q = (gp >> 5) & 3;
-    return q == 1 ? 2.8853900817779268f : -1.4426950408889634f;
-}
-
 // proj B operand, slabs [chunk nt][slice s][hi|lo][kc 8][n 128][8]:
 //   s <  KSe : Wx[:, d_t : d_t+d_e]  (entity columns of the input projection)
 //   s >= KSe : P_tr^T, the hoisted (type,relation) table, multiplied by a one-hot k-slice of the A tile
@@ -446,6 +438,10 @@ struct RecurArgs {
     //   hcache [tile][t][hi|lo][kc Hp/8][row 128][8] bf16: h_t in the UMMA operand layout (what the next step's MMAs read, and the
     //          B operand of the weight-gradient product dG^T h_{t-1}); replaces the per-CTA scratch
     float* cache; bf16* hcache;
+    // leading-token reuse (tc_prefix.cu; scoring only): the batch arrives sorted by the number of leading copies of one token;
+    // a pair of tiles whose first row has ps = t0 starts at step t0 from the chain state: chain_u[t0] = that state's recurrent
+    // pre-activations (accumulator layout and scale), chain_c[t0] its cell state.  perm = sorted position -> path (outputs).
+    const int32_t* perm; const uint8_t* ps; const float* chain_u; const float* chain_c;
 };
 
 __device__ __forceinline__ float ex2f(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -537,6 +533,13 @@ __global__ void __launch_bounds__(RECUR_THREADS, 1) recur_kernel(RecurArgs a) {
         return m < a.num_tiles ? m : a.num_tiles - 1;
     };
     const int T = a.T;
+    // first step of the it-th tile (pair): the fewest leading copies of the shared token among its rows = those of its first row
+    auto t0_of = [&](int64_t it) -> int {
+        if (TRAIN || !a.ps) return 0;
+        int64_t row0 = (PAIR ? 2 * (pair + it * npairs) : (int64_t)blockIdx.x + it * gridDim.x) * TILE_M;
+        if (row0 >= a.N) row0 = a.N - 1;
+        return a.ps[row0];
+    };
     const uint32_t idesc = ptx::make_idesc_f16(1, PAIR ? 2 * TILE_M : TILE_M, 128);
     const int slabs_per_k = a.passes == 3 ? 2 : 1;
     uint8_t* const scratch0 = reinterpret_cast<uint8_t*>(a.hscratch) + (size_t)blockIdx.x * 2 * H_BYTES;   // [hi | lo] image of sH
@@ -549,7 +552,8 @@ __global__ void __launch_bounds__(RECUR_THREADS, 1) recur_kernel(RecurArgs a) {
         // ===== TMA producer: Wh slabs (this CTA's columns); the sequence is identical for every MMA step (t >= 1) =====
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
-            const int64_t steps = my_tiles * (T - 1);
+            int64_t steps = 0;
+            for (int64_t it = 0; it < my_tiles; ++it) steps += T - 1 - t0_of(it);
             for (int64_t st = 0; st < steps; ++st)
                 for (int j = 0; j < NCH; ++j)
                     for (int s = 0; s < KS; ++s)
@@ -583,7 +587,7 @@ __global__ void __launch_bounds__(RECUR_THREADS, 1) recur_kernel(RecurArgs a) {
             };
             uint32_t cnt = 0;                                   // 1-based index of the MMA step
             for (int64_t it = 0; it < my_tiles; ++it) {
-                for (int t = 1; t < T; ++t) {
+                for (int t = t0_of(it) + 1; t < T; ++t) {
                     ++cnt;
 #pragma unroll 1
                     for (int j = 0; j < NCH; ++j) {
@@ -637,7 +641,7 @@ __global__ void __launch_bounds__(RECUR_THREADS, 1) recur_kernel(RecurArgs a) {
             uint32_t stage = 0, phase = 0, cnt = 0;
             const uint32_t pslab = ptx::mapa(BAR(B_PSLAB), 0), ph = ptx::mapa(BAR(B_PH), 0);
             for (int64_t it = 0; it < my_tiles; ++it)
-                for (int t = 1; t < T; ++t) {
+                for (int t = t0_of(it) + 1; t < T; ++t) {
                     ++cnt;
                     for (int j = 0; j < NCH; ++j)
                         for (int s = 0; s < KS; ++s) {
@@ -658,7 +662,7 @@ __global__ void __launch_bounds__(RECUR_THREADS, 1) recur_kernel(RecurArgs a) {
         if (lane == 0) {
             uint32_t idx = 0;                                   // 1-based index of the h vector being loaded
             for (int64_t it = 0; it < my_tiles; ++it) {
-                for (int t = 0; t < T - 1; ++t) {
+                for (int t = t0_of(it); t < T - 1; ++t) {
                     ++idx;
                     const uint8_t* scratch = h_image(tile_of(it), t);
                     // all MMAs that read the previous contents of sH must have retired: that is MMA step idx-1
@@ -698,13 +702,17 @@ __global__ void __launch_bounds__(RECUR_THREADS, 1) recur_kernel(RecurArgs a) {
         for (int64_t it = 0; it < my_tiles; ++it) {
             const int64_t pt = tile_of(it);
             const int64_t n = pt * TILE_M + r;
+            const int64_t n_out = (!TRAIN && a.perm && n < a.N) ? a.perm[n] : n;      // where this row's result goes (sorted batch: its path)
             // row index of this thread's XW row per step (rows past N in a ragged last tile: any valid row)
             auto row_of = [&](int t) -> uint32_t {
                 const uint32_t p = a.pos[(pt * T + t) * TILE_M + r];
                 return p == 0xFFFFFFFFu ? 0u : a.slot_of[p];
             };
-            uint32_t slot_next = a.pos ? row_of(0) : 0u;
-            for (int t = 0; t < T; ++t) {
+            const int t0 = t0_of(it);
+            const float* const cu0 = a.chain_u + (size_t)t0 * a.G4;        // used when t0 > 0
+            const float* const cc0 = a.chain_c + (size_t)t0 * HP;
+            uint32_t slot_next = a.pos ? row_of(t0) : 0u;
+            for (int t = t0; t < T; ++t) {
                 const uint32_t slot = slot_next;
                 if (a.pos && t + 1 < T) slot_next = row_of(t + 1);       // next step's row index, in flight during this step
                 // rows are numbered in the order the recurrence reads them (see the dedup kernels): the first occurrences inside a
@@ -725,14 +733,14 @@ __global__ void __launch_bounds__(RECUR_THREADS, 1) recur_kernel(RecurArgs a) {
                         asm volatile("fence.proxy.async.global;" ::: "memory");
                         ptx::mbar_arrive(BAR(B_HWRIT + ((j - 1) >> 1)));
                     }
-                    if (t > 0) {
+                    if (t > t0) {
                         TWAIT(14, BAR(B_ACCF + g), ug & 1);
                         ptx::tc_fence_after();
                     }
                     const uint32_t acc = tmem + lane_base + g * 128;
                     const uint32_t cst = tmem + lane_base + 256 + j * 32;
                     float cp[8];
-                    if (t > 0) {
+                    if (t > t0) {
                         float ai[8], ag[8], af[8], ao[8];
                         ptx::tmem_ld8(acc + 0 * 32 + sb * 8, ai);
                         ptx::tmem_ld8(acc + 1 * 32 + sb * 8, ag);
@@ -754,9 +762,20 @@ __global__ void __launch_bounds__(RECUR_THREADS, 1) recur_kernel(RecurArgs a) {
                             ptx::unpack2(ptx::add2(ptx::pack2(xc[16 + e], xc[17 + e]), ptx::pack2(af[e], af[e + 1])), xc[16 + e], xc[17 + e]);
                             ptx::unpack2(ptx::add2(ptx::pack2(xc[24 + e], xc[25 + e]), ptx::pack2(ao[e], ao[e + 1])), xc[24 + e], xc[25 + e]);
                         }
-                    } else {
+                    } else if (t0 == 0) {
 #pragma unroll
                         for (int e = 0; e < 8; ++e) cp[e] = 0.f;      // t = 0: h = c = 0 and no MMA ran
+                    } else {
+                        // first step after t0 shared leading tokens: the state every such row would have reached (tc_prefix.cu)
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float4 u0 = *reinterpret_cast<const float4*>(cu0 + (j * 16 + q * 4 + sb) * 8);
+                            const float4 u1 = *reinterpret_cast<const float4*>(cu0 + (j * 16 + q * 4 + sb) * 8 + 4);
+                            xc[q * 8 + 0] += u0.x; xc[q * 8 + 1] += u0.y; xc[q * 8 + 2] += u0.z; xc[q * 8 + 3] += u0.w;
+                            xc[q * 8 + 4] += u1.x; xc[q * 8 + 5] += u1.y; xc[q * 8 + 6] += u1.z; xc[q * 8 + 7] += u1.w;
+                        }
+                        const float4 c0 = *reinterpret_cast<const float4*>(cc0 + j * 32 + sb * 8), c1 = *reinterpret_cast<const float4*>(cc0 + j * 32 + sb * 8 + 4);
+                        cp[0] = c0.x; cp[1] = c0.y; cp[2] = c0.z; cp[3] = c0.w; cp[4] = c1.x; cp[5] = c1.y; cp[6] = c1.z; cp[7] = c1.w;
                     }
                     if (j + 1 < NCH) { KPRN_LOAD_XW(xn, xw_t, j + 1) }     // next chunk's XW, in flight during the cell math
                     float cn[8], hv[8];
@@ -770,18 +789,41 @@ __global__ void __launch_bounds__(RECUR_THREADS, 1) recur_kernel(RecurArgs a) {
 #pragma unroll
                         for (int p = 0; p < 4; ++p) {
                             const int e = 2 * p;
-                            const uint64_t pi = ptx::add2(ptx::pack2(ex2f(xc[e]), ex2f(xc[e + 1])), one2);
-                            const uint64_t pg = ptx::add2(ptx::pack2(ex2f(xc[8 + e]), ex2f(xc[9 + e])), one2);
-                            const uint64_t pf = ptx::add2(ptx::pack2(ex2f(xc[16 + e]), ex2f(xc[17 + e])), one2);
-                            const uint64_t po = ptx::add2(ptx::pack2(ex2f(xc[24 + e]), ex2f(xc[25 + e])), one2);
-                            const uint64_t i_ = ptx::pack2(rcpf(ptx::lo2(pi)), rcpf(ptx::hi2(pi)));
-                            const uint64_t f_ = ptx::pack2(rcpf(ptx::lo2(pf)), rcpf(ptx::hi2(pf)));
-                            const uint64_t o_ = ptx::pack2(rcpf(ptx::lo2(po)), rcpf(ptx::hi2(po)));
-                            const uint64_t g_ = ptx::fma2(ptx::pack2(rcpf(ptx::lo2(pg)), rcpf(ptx::hi2(pg))), mtwo2, one2);
-                            const uint64_t c2 = ptx::fma2(i_, g_, ptx::mul2(f_, ptx::pack2(cp[e], cp[e + 1])));
-                            const uint64_t a2 = ptx::mul2(c2, k2);
-                            const uint64_t pt2 = ptx::add2(ptx::pack2(ex2f(ptx::lo2(a2)), ex2f(ptx::hi2(a2))), one2);
-                            const uint64_t th = ptx::fma2(ptx::pack2(rcpf(ptx::lo2(pt2)), rcpf(ptx::hi2(pt2))), mtwo2, one2);
+                            uint64_t i_, f_, o_, g_, c2, th;
+                            if constexpr (!TRAIN) {
+                                // the XU pipe (16 MUFU lanes / clk / SM) is this kernel's bound: the four gate denominators of a cell
+                                // share ONE reciprocal (batch inversion: 9 packed multiplies on the FMA pipe instead of 3 MUFU.RCP),
+                                // the two tanh(c) denominators of a cell pair share one.  Exponents are clamped at 2^30 (a gate off by
+                                // < 1e-9) and 2^60 so that the products stay finite.
+                                const uint64_t pi = ptx::add2(ptx::pack2(ex2f(fminf(xc[e], 30.f)), ex2f(fminf(xc[e + 1], 30.f))), one2);
+                                const uint64_t pg = ptx::add2(ptx::pack2(ex2f(fminf(xc[8 + e], 30.f)), ex2f(fminf(xc[9 + e], 30.f))), one2);
+                                const uint64_t pf = ptx::add2(ptx::pack2(ex2f(fminf(xc[16 + e], 30.f)), ex2f(fminf(xc[17 + e], 30.f))), one2);
+                                const uint64_t po = ptx::add2(ptx::pack2(ex2f(fminf(xc[24 + e], 30.f)), ex2f(fminf(xc[25 + e], 30.f))), one2);
+                                const uint64_t P2 = ptx::mul2(pi, pg), P3 = ptx::mul2(P2, pf), P4 = ptx::mul2(P3, po);
+                                const uint64_t R4 = ptx::pack2(rcpf(ptx::lo2(P4)), rcpf(ptx::hi2(P4)));
+                                o_ = ptx::mul2(R4, P3); const uint64_t R3 = ptx::mul2(R4, po);
+                                f_ = ptx::mul2(R3, P2); const uint64_t R2 = ptx::mul2(R3, pf);
+                                i_ = ptx::mul2(R2, pg);
+                                g_ = ptx::fma2(ptx::mul2(R2, pi), mtwo2, one2);
+                                c2 = ptx::fma2(i_, g_, ptx::mul2(f_, ptx::pack2(cp[e], cp[e + 1])));
+                                const uint64_t a2 = ptx::mul2(c2, k2);
+                                const float t0_ = 1.f + ex2f(fminf(ptx::lo2(a2), 60.f)), t1_ = 1.f + ex2f(fminf(ptx::hi2(a2), 60.f));
+                                const float rt = rcpf(t0_ * t1_);
+                                th = ptx::fma2(ptx::pack2(rt * t1_, rt * t0_), mtwo2, one2);
+                            } else {        // training forward: HBM-bound on its cache stores, and short of registers -- the plain form
+                                const uint64_t pi = ptx::add2(ptx::pack2(ex2f(xc[e]), ex2f(xc[e + 1])), one2);
+                                const uint64_t pg = ptx::add2(ptx::pack2(ex2f(xc[8 + e]), ex2f(xc[9 + e])), one2);
+                                const uint64_t pf = ptx::add2(ptx::pack2(ex2f(xc[16 + e]), ex2f(xc[17 + e])), one2);
+                                const uint64_t po = ptx::add2(ptx::pack2(ex2f(xc[24 + e]), ex2f(xc[25 + e])), one2);
+                                i_ = ptx::pack2(rcpf(ptx::lo2(pi)), rcpf(ptx::hi2(pi)));
+                                f_ = ptx::pack2(rcpf(ptx::lo2(pf)), rcpf(ptx::hi2(pf)));
+                                o_ = ptx::pack2(rcpf(ptx::lo2(po)), rcpf(ptx::hi2(po)));
+                                g_ = ptx::fma2(ptx::pack2(rcpf(ptx::lo2(pg)), rcpf(ptx::hi2(pg))), mtwo2, one2);
+                                c2 = ptx::fma2(i_, g_, ptx::mul2(f_, ptx::pack2(cp[e], cp[e + 1])));
+                                const uint64_t a2 = ptx::mul2(c2, k2);
+                                const uint64_t pt2 = ptx::add2(ptx::pack2(ex2f(ptx::lo2(a2)), ex2f(ptx::hi2(a2))), one2);
+                                th = ptx::fma2(ptx::pack2(rcpf(ptx::lo2(pt2)), rcpf(ptx::hi2(pt2))), mtwo2, one2);
+                            }
                             const uint64_t h2 = ptx::mul2(o_, th);
                             cn[e] = ptx::lo2(c2); cn[e + 1] = ptx::hi2(c2);
                             hv[e] = ptx::lo2(h2); hv[e + 1] = ptx::hi2(h2);
@@ -824,7 +866,7 @@ __global__ void __launch_bounds__(RECUR_THREADS, 1) recur_kernel(RecurArgs a) {
                       }
                       if ((TRAIN || !a.part4) && n < a.N) {
                         // SelectTable(-1): last hidden state, standard [N,H] layout for the head
-                        float* dst = a.hT + n * a.H + j * 32 + sb * 8;
+                        float* dst = a.hT + n_out * a.H + j * 32 + sb * 8;
                         if (h_vec4 && j * 32 + sb * 8 + 8 <= a.H) {      // full-sector stores (scalar stores cost 8 partial sectors)
                             *reinterpret_cast<float4*>(dst) = make_float4(hv[0], hv[1], hv[2], hv[3]);
                             *reinterpret_cast<float4*>(dst + 4) = make_float4(hv[4], hv[5], hv[6], hv[7]);
@@ -845,7 +887,7 @@ __global__ void __launch_bounds__(RECUR_THREADS, 1) recur_kernel(RecurArgs a) {
                     asm volatile("fence.proxy.async.global;" ::: "memory");
                     ptx::mbar_arrive(BAR(B_HWRIT + ((NCH - 1) >> 1)));
                 }
-                if (last && a.part4 && n < a.N) a.part4[sb * a.npad + n] = dot;     // summed (fixed order) + bias in the pool kernel
+                if (last && a.part4 && n < a.N) a.part4[sb * a.npad + n_out] = dot;     // summed (fixed order) + bias in the pool kernel
                 ptx::tc_wait_st();        // c_t is read back (tcgen05.ld) by this thread in the next step
             }
         }
@@ -1167,6 +1209,10 @@ int tc_forward(kprn_ctx* ctx, const int32_t* d_ids, const int32_t* d_seg, int64_
         dbg = s->dbg.as<unsigned long long>();
         KPRN_CUDA(cudaMemsetAsync(dbg, 0, 2 * 16 * sizeof(unsigned long long), ctx->stream));
     }
+    // leading-token reuse (scoring on the paired recurrence): everything below sees the batch sorted by leading-token count
+    PrefixOut pfx{nullptr, nullptr, nullptr, nullptr, nullptr};
+    const bool use_prefix = !train && s->Hp <= 256 && s->recur_pairs && prefix_enabled(ctx, N);
+    if (use_prefix) { KPRN_TRY(prefix_build(ctx, d_ids, N, &pfx)); d_ids = pfx.ids; }
     {
         ProjArgs a;
         a.ids = d_ids; a.N = N; a.T = c.T; a.V_e = c.V_e; a.V_t = (int)c.V_t; a.V_r = (int)c.V_r;
@@ -1211,6 +1257,8 @@ int tc_forward(kprn_ctx* ctx, const int32_t* d_ids, const int32_t* d_seg, int64_
         a.pos = dd ? s->dd.pos.as<uint32_t>() : nullptr; a.slot_of = dd ? s->dd.slot_of.as<uint32_t>() : nullptr;
         ctx->head_part4 = nullptr;
         a.cache = nullptr; a.hcache = nullptr;
+        a.perm = pfx.perm; a.ps = pfx.ps; a.chain_u = pfx.chain_u; a.chain_c = pfx.chain_c;
+        if (use_prefix) KPRN_TRY(prefix_join(ctx));
         if (tc_train) KPRN_TRY(tc_train_buffers(ctx, N, &a.cache, &a.hcache));
         if (ctx->cls_only && c.pool == KPRN_POOL_LSE) {      // the pool kernel finishes the head: sum of 4 partials + bias
             KPRN_TRY(ensure(s->part4, sizeof(float) * 4 * (size_t)a.npad));
@@ -1279,6 +1327,7 @@ void tc_destroy(kprn_ctx* ctx) {
     TcState* s = ctx->tc;
     if (!s) return;
     tc_train_destroy(ctx);
+    prefix_destroy(ctx);
     if (s->E_hi) cudaFree(s->E_hi);
     if (s->E_lo) cudaFree(s->E_lo);
     if (s->WxE) cudaFree(s->WxE);

@@ -26,12 +26,22 @@ constexpr int RECUR_RING_PAIR = 8;     // 8 KB half-slabs in flight per CTA (CTA
 constexpr int RECUR_BAR_BYTES = 384;   // barrier block at the end of the recurrence's shared memory
 constexpr int MAX_NS = 6;             // k-slices of the proj A tile: KE/64 entity slices + NOH one-hot slices
 constexpr int NUM_THREADS = 384;      // proj: warps 0 TMA producer, 1 MMA issuer, 2-3 gather/alloc, 4-11 epilogue
-constexpr int RECUR_THREADS = 608;    // recur: warps 0 TMA producer, 1 MMA issuer, 2 TMEM alloc + h loader, 3-18 epilogue (4 groups); 19 warps -> 104 registers per thread
+constexpr int RECUR_THREADS = 608;    // recur: warps 0 TMA producer, 1 MMA issuer, 2 TMEM alloc + h loader, 3-18 epilogue (4 groups); 96 registers per thread
+                                      // (setmaxnreg measured: the pool is the launch allocation, 640 x 96: 104 for the epilogue does not remove its spills)
 
 struct TcTrain;   // tc_train.cu
 
+// leading-token reuse of the scoring recurrence (tc_prefix.cu)
+struct PrefixState {
+    DBuf token, hist, p, ps, perm, ids, pre, chain_u, chain_c;
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_tok = nullptr, ev_chain = nullptr;
+};
+struct PrefixOut { const int32_t* ids; const int32_t* perm; const uint8_t* ps; const float* chain_u; const float* chain_c; };
+
 struct TcState {
     TcTrain* tt = nullptr;             // training-side buffers and packed operands
+    PrefixState* px = nullptr;
     uint64_t packed_version = 0;       // ctx->params_version the packed operands (entity tables included) were built from
     uint64_t packed_small = 0;         // ctx->small_version the packed WEIGHTS were built from (a sparse training step leaves the
                                        // entity tables current row by row and only bumps small_version)
@@ -64,6 +74,13 @@ __host__ __device__ __forceinline__ int perm_to_row(int gp, int H, int& u) {
     u = j * 32 + uu;
     return q * H + u;
 }
+// The recurrent kernel evaluates the gates as sigmoid(x) = 1/(1+2^(-x log2 e)) and tanh(x) = 1 - 2/(1+2^(2x log2 e)) with
+// ex2.approx; the factor (-log2 e for i,f,o and +2 log2 e for g) is folded into the packed weights, the hoisted table and
+// hence XW and the accumulators, so the cell math needs no multiply in front of the four gate exponentials.
+__device__ __forceinline__ float gate_scale(int gp) {
+    const int q = (gp >> 5) & 3;
+    return q == 1 ? 2.8853900817779268f : -1.4426950408889634f;
+}
 __device__ __forceinline__ void split_bf16(float v, bf16& hi, bf16& lo) {
     hi = __float2bfloat16_rn(v);
     lo = __float2bfloat16_rn(v - __bfloat162float(hi));
@@ -76,6 +93,12 @@ struct RecurWide {
 };
 int wide_recurrence(kprn_ctx* ctx, const RecurWide& w);
 int pack_wh_wide(kprn_ctx* ctx, const float* Wh, int H, int Hp, bf16* out);
+
+// leading-token reuse (tc_prefix.cu)
+bool prefix_enabled(const kprn_ctx* ctx, int64_t N);
+int prefix_build(kprn_ctx* ctx, const int32_t* d_ids, int64_t N, PrefixOut* out);
+int prefix_join(kprn_ctx* ctx);
+void prefix_destroy(kprn_ctx* ctx);
 
 // training side (tc_train.cu)
 int tc_train_pack(kprn_ctx* ctx);
