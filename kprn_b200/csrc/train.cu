@@ -564,7 +564,7 @@ static int train_step_device(kprn_ctx* ctx, const int32_t* d_ids, const int32_t*
     const float step = adam_step_size(o.lr, o.beta1, o.beta2, t_now);
     KPRN_TRY(steps_push(ctx, tr, step));
     const bool clip = o.regularize && o.use_clip;
-    ctx->defer_eg_join = !clip && ctx->world == 1 && env_defer;
+    ctx->defer_eg_join = !clip && env_defer;
     ctx->eg_stream = nullptr;
     KPRN_TRY(forward_device_impl(ctx, d_ids, d_seg, N, S, true, false, nullptr, nullptr));
     if (o.loss == 0) KPRN_TRY(loss_bce_device(ctx, d_labels, S, &d_loss));
@@ -576,8 +576,16 @@ static int train_step_device(kprn_ctx* ctx, const int32_t* d_ids, const int32_t*
     const int32_t* rows = tr->es.ids.as<int32_t>(); const int32_t* count = tr->es.count.as<int32_t>();
     int64_t rows_bound = N * c.T;
     if (ctx->world > 1) {
+        if (ctx->eg_stream) {
+            // the row exchange (all-gathers, union of the slots) runs on the backward's side stream, beside the weight-gradient
+            // kernel of the main stream; it is issued BEFORE the all-reduce of the small tensors (which has to wait for that kernel):
+            // NCCL serialises the operations of one communicator in issue order.  The helpers launch on ctx->stream: swapped here.
+            struct Swap { kprn_ctx* c; cudaStream_t saved; ~Swap() { c->stream = saved; } } swap{ctx, ctx->stream};
+            ctx->stream = ctx->eg_stream;
+            KPRN_TRY(exchange_rows(ctx, tr, N, &maxK));
+        }
         KPRN_TRY(comm_allreduce_f32_2(ctx, ctx->d_grads, l.E_e, ctx->d_grads + l.E_r, l.total - l.E_r));
-        KPRN_TRY(exchange_rows(ctx, tr, N, &maxK));
+        if (!ctx->eg_stream) KPRN_TRY(exchange_rows(ctx, tr, N, &maxK));
         recv_g = tr->recv_g.as<float>(); contrib = tr->contrib.as<int32_t>() + (int64_t)ctx->world * maxK;
         rows = tr->us.ids.as<int32_t>(); count = tr->us.count.as<int32_t>();
         rows_bound = (int64_t)ctx->world * maxK;
