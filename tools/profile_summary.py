@@ -8,7 +8,8 @@ from collections import defaultdict
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag, launches = sys.argv[1], sys.argv[2]
-rep = sys.argv[3] if len(sys.argv) > 3 else None
+reps = sys.argv[3:]
+rep = reps[0] if reps else None
 out = open(os.path.join(ROOT, "profiles", "%s_summary.md" % tag), "w")
 rows = [r for r in csv.reader(open(launches)) if len(r) > 5]
 hdr = rows[0]
@@ -24,8 +25,25 @@ out.write("| kernel | launches | avg us | share |\n|---|---|---|---|\n")
 for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
     out.write("| %s | %d | %.1f | %.1f %% |\n" % (k, len(v), sum(v) / len(v) / 1e3, 100 * sum(v) / tot))
 if rep:
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    rr = list(csv.reader(raw.splitlines()))
+    rr = None
+    for rp in reps:                     # several reports (e.g. a scoring and a training capture): rows concatenated
+        raw = subprocess.run(["ncu", "-i", rp, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        part = list(csv.reader(raw.splitlines()))
+        if rr is None: rr = part; continue
+        # align by column name and convert to the first report's units (ncu picks a unit per column per report)
+        US = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0,
+              "nsecond": 1e-9, "usecond": 1e-6, "msecond": 1e-3, "second": 1.0}
+        idx = {n: i for i, n in enumerate(part[0])}
+        for r in part[2:]:
+            row = []
+            for ci, n in enumerate(rr[0]):
+                if n not in idx: row.append(""); continue
+                v, u_src, u_dst = r[idx[n]], part[1][idx[n]], rr[1][ci]
+                if u_src != u_dst and u_src in US and u_dst in US:
+                    try: v = "%.6f" % (float(v.replace(",", "")) * US[u_src] / US[u_dst])
+                    except ValueError: pass
+                row.append(v)
+            rr.append(row)
     h = rr[0]
     want = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
             "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
@@ -47,7 +65,13 @@ if rep:
     kern = {}
     for r in rr[2:]:
         nm = r[ni].split("(")[0]
-        key = "proj" if "proj" in nm else ("recur" if "recur" in nm else nm[:32])
+        # recur_kernel<HP, PAIR, TRAIN>: the scoring kernel is "recur", the training forward "recur_train"
+        if "recur" in nm:
+            key = "recur_train" if nm.replace(" ", "").endswith(",1>") else "recur"
+        else:
+            key = "proj" if "proj" in nm else nm.replace("void ", "").replace("kprn::", "")[:32]
+        if key in kern:
+            continue                    # first capture of a name wins (later launches of the same kernel are other steps)
         kern[key] = {"name": nm[:64], "dram_read_bytes": float(r[ri].replace(",", "")) * scale.get(rr[1][ri], 1.0),
                      "dram_write_bytes": float(r[wi].replace(",", "")) * scale.get(rr[1][wi], 1.0)}
     json.dump({"source": "profiles/%s_summary.md (ncu --set full, one launch per kernel)" % tag, "kernels": kern},
