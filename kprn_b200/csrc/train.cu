@@ -84,7 +84,7 @@ struct RowsArgs {
 // row are issued before any arithmetic; NV4 = 0: any width, scalar.  Rows with nothing to replay are skipped by the catch-up
 // pass before any load.
 template <int NV4>
-__global__ void __launch_bounds__(256) adam_rows_kernel(RowsArgs a) {
+__global__ void __launch_bounds__(256, 4) adam_rows_kernel(RowsArgs a) {
     const int K = *a.count;
     const int lane = threadIdx.x & 31;
     const int warps = (gridDim.x * blockDim.x) >> 5;
@@ -127,14 +127,26 @@ __global__ void __launch_bounds__(256) adam_rows_kernel(RowsArgs a) {
                 }
             }
             const float step = a.apply ? a.steps[a.t_now] : 0.f;
+            // replay: the postponed step outermost, the lane's 4 NV elements inside -- independent dependency chains for the
+            // divide / square root of every step (adam_replay's early-out for m = v = 0 is only a shortcut: the zero-gradient
+            // update of such an element is x - step * 0 / (0 + eps) = x, so the unconditional form gives the same bits)
+            if (may_have_state)
+                for (int64_t k = t0 + 1; k <= a.t_now - 1; ++k) {
+                    const float sk = a.steps[k];
+#pragma unroll
+                    for (int q = 0; q < NV; ++q) {
+                        float* xs = reinterpret_cast<float*>(&x[q]); float* ms = reinterpret_cast<float*>(&m[q]); float* vs = reinterpret_cast<float*>(&v[q]);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) adam_elem(xs[e], ms[e], vs[e], 0.f, sk, a.b1, a.b2, a.eps);
+                    }
+                }
 #pragma unroll
             for (int q = 0; q < NV; ++q) {
                 float* xs = reinterpret_cast<float*>(&x[q]); float* ms = reinterpret_cast<float*>(&m[q]); float* vs = reinterpret_cast<float*>(&v[q]);
                 const float* gq = reinterpret_cast<const float*>(&g[q]);
+                if (a.apply) {
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    if (may_have_state) adam_replay(xs[e], ms[e], vs[e], t0, a.t_now - 1, a.steps, a.b1, a.b2, a.eps);
-                    if (a.apply) adam_elem(xs[e], ms[e], vs[e], gq[e], step, a.b1, a.b2, a.eps);
+                    for (int e = 0; e < 4; ++e) adam_elem(xs[e], ms[e], vs[e], gq[e], step, a.b1, a.b2, a.eps);
                 }
                 *reinterpret_cast<float4*>(px + q * 128 + lane * 4) = x[q];
                 *reinterpret_cast<float4*>(pm + q * 128 + lane * 4) = m[q];
