@@ -209,7 +209,9 @@ int kprn_allreduce_grads(kprn_ctx* ctx, int32_t average);               /* dense
 int kprn_allreduce_host_f64(kprn_ctx* ctx, double* vals, int64_t n, int32_t op_max);   /* loss / counters: n <= 64 host doubles, sum or max */
 
 /* engine knobs (no reference counterpart; they never change results).  Keys:
- *   "dedup"  1/0: project each distinct (type, entity, relation) step input once / every step (-1: KPRN_TC_DEDUP env, default on) */
+ *   "dedup"  1/0: project each distinct (type, entity, relation) step input once / every step (-1: KPRN_TC_DEDUP env, default on)
+ *   "prefix" 1/0: scoring recurrence steps through the shared leading (pad) tokens of the batch once / per path
+ *                 (-1: KPRN_TC_PREFIX env, default on for batches of >= 4096 paths; 1 forces it for any size) */
 int kprn_set_option(kprn_ctx* ctx, const char* key, int64_t value);
 
 /* counters for bench.py: kernels launched by this library since the last reset */
