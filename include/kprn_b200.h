@@ -211,7 +211,12 @@ int kprn_allreduce_host_f64(kprn_ctx* ctx, double* vals, int64_t n, int32_t op_m
 /* engine knobs (no reference counterpart; they never change results).  Keys:
  *   "dedup"  1/0: project each distinct (type, entity, relation) step input once / every step (-1: KPRN_TC_DEDUP env, default on)
  *   "prefix" 1/0: scoring recurrence steps through the shared leading (pad) tokens of the batch once / per path
- *                 (-1: KPRN_TC_PREFIX env, default on for batches of >= 4096 paths; 1 forces it for any size) */
+ *                 (-1: KPRN_TC_PREFIX env, default on for batches of >= 4096 paths; 1 forces it for any size)
+ * and one that changes what a multi-GPU call means (BASELINE configs[2] "logit allreduce"):
+ *   "path_sharded" 1/0: with a communicator, the PATHS of each (user,item) segment are spread over the ranks: every rank passes
+ *                 all S segments (its share of each, possibly empty) and the forward combines the pooled logits across ranks as
+ *                 log-sum-exp partials (two small all-reduces), so scores / losses / gradients are those of the whole batch;
+ *                 training then uses grad_scale = 1.  Default 0: ranks own whole segments, no data-path collective. */
 int kprn_set_option(kprn_ctx* ctx, const char* key, int64_t value);
 
 /* counters for bench.py: kernels launched by this library since the last reset */

@@ -249,6 +249,7 @@ int forward_device_impl(kprn_ctx* ctx, const int32_t* d_ids, const int32_t* d_se
     KPRN_TRY(prof_end(ctx, e0, 0));
     ctx->gemm_on_tc = false;
     KPRN_TRY(pool_forward(ctx, d_seg, S, d_out_scores, d_out_logits));
+    if (ctx->opt_path_sharded > 0 && ctx->world > 1) KPRN_TRY(pool_allreduce_lse(ctx, d_seg, S, d_out_scores, d_out_logits));
     ctx->have_fwd = true;
     ctx->have_train_cache = train;
     return KPRN_OK;
@@ -315,6 +316,7 @@ int kprn_destroy(kprn_ctx* ctx) {
     train_destroy(ctx);
     tc_destroy(ctx);
     if (ctx->tmp_comm.p) cudaFree(ctx->tmp_comm.p);
+    if (ctx->tmp_pool.p) cudaFree(ctx->tmp_pool.p);
     DBuf* bufs[] = {&ctx->ids_buf, &ctx->seg_buf, &ctx->path_logits, &ctx->seg_logits, &ctx->scores, &ctx->dscores,
                     &ctx->dseg_logits, &ctx->labels, &ctx->tmp_small, &ctx->act, &ctx->cst, &ctx->hst, &ctx->z1,
                     &ctx->ws_x, &ctx->ws_xw, &ctx->ws_h0, &ctx->ws_h1, &ctx->ws_c, &ctx->ws_dg, &ctx->ws_dx,
@@ -775,6 +777,7 @@ int kprn_set_option(kprn_ctx* ctx, const char* key, int64_t value) {
     if (!ctx || !key) { set_error("null argument"); return KPRN_EINVAL; }
     if (!strcmp(key, "dedup")) { ctx->opt_dedup = value < 0 ? -1 : (value != 0); return KPRN_OK; }
     if (!strcmp(key, "prefix")) { ctx->opt_prefix = value < 0 ? -1 : (value != 0); return KPRN_OK; }
+    if (!strcmp(key, "path_sharded")) { ctx->opt_path_sharded = value > 0; return KPRN_OK; }
     set_error("set_option: unknown key '%s'", key);
     return KPRN_EINVAL;
 }

@@ -96,6 +96,61 @@ int comm_allgather_bytes(kprn_ctx* ctx, const void* send, void* recv, int64_t by
     ctx->comm_calls++;
     return KPRN_OK;
 }
+// ---- path-sharded pooling: LogSumExp over the paths of a (user,item) pair that live on different ranks ----
+// (SP/model/module/LogSumExp.lua:14-30 evaluated on partials: every rank holds (m_r, z_r) of its own paths; the pooled value is
+//  (M + log sum_r z_r e^{m_r - M}) / ig with M = max_r m_r.  Two small all-reduces (max, sum) over S x ncols floats.)
+__global__ void lse_part_max_kernel(const float* __restrict__ seg_logits, const int32_t* __restrict__ seg, int64_t S, int L, int col0, int ncols,
+                                    float ig, float* __restrict__ m) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= S * ncols) return;
+    const int64_t k = i / ncols; const int col = col0 + (int)(i % ncols);
+    m[i] = seg[k + 1] > seg[k] ? seg_logits[k * L + col] * ig : -INFINITY;          // a rank without paths of this pair contributes nothing
+}
+__global__ void lse_part_sum_kernel(const float* __restrict__ seg_logits, const int32_t* __restrict__ seg, int64_t S, int L, int col0, int ncols,
+                                    float ig, const float* __restrict__ M, float* __restrict__ z) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= S * ncols) return;
+    const int64_t k = i / ncols; const int col = col0 + (int)(i % ncols);
+    z[i] = (seg[k + 1] > seg[k] && M[i] > -INFINITY) ? expf(seg_logits[k * L + col] * ig - M[i]) : 0.f;
+}
+__global__ void lse_part_finish_kernel(float* __restrict__ seg_logits, int64_t S, int L, int col0, int ncols, float ig, int cls,
+                                       const float* __restrict__ M, const float* __restrict__ z, float* __restrict__ scores,
+                                       float* __restrict__ out_scores, float* __restrict__ out_logits) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= S * ncols) return;
+    const int64_t k = i / ncols; const int col = col0 + (int)(i % ncols);
+    const float v = M[i] > -INFINITY ? (M[i] + logf(z[i])) / ig : 0.f;             // no path anywhere: 0, as the local pool does
+    seg_logits[k * L + col] = v;
+    if (out_logits) out_logits[k * L + col] = v;
+    if (col == cls) {
+        const float pr = 1.f / (1.f + expf(-v));
+        scores[k] = pr;
+        if (out_scores) out_scores[k] = pr;
+    }
+}
+
+int pool_allreduce_lse(kprn_ctx* ctx, const int32_t* d_seg, int64_t S, float* d_out_scores, float* d_out_logits) {
+    const kprn_config& c = ctx->cfg;
+    if (!ctx->comm || ctx->world <= 1) return KPRN_OK;
+    if (c.pool != KPRN_POOL_LSE) { set_error("path_sharded: only the LogSumExp pool combines across ranks"); return KPRN_EINVAL; }
+    const int col0 = ctx->cls_only ? c.class_id - 1 : 0, ncols = ctx->cls_only ? 1 : c.L;
+    const int64_t n = S * ncols;
+    KPRN_TRY(ensure(ctx->tmp_pool, sizeof(float) * 2 * (size_t)n));
+    float* M = ctx->tmp_pool.as<float>(); float* z = M + n;
+    const float ig = c.inv_gamma == 0.f ? 1.f : c.inv_gamma;
+    const unsigned grid = (unsigned)cdiv(n, 256);
+    lse_part_max_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->seg_logits.as<float>(), d_seg, S, c.L, col0, ncols, ig, M);
+    KPRN_LAUNCH_CHECK(ctx);
+    KPRN_TRY(comm_allreduce_f32(ctx, M, n, true));
+    lse_part_sum_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->seg_logits.as<float>(), d_seg, S, c.L, col0, ncols, ig, M, z);
+    KPRN_LAUNCH_CHECK(ctx);
+    KPRN_TRY(comm_allreduce_f32(ctx, z, n, false));
+    lse_part_finish_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->seg_logits.as<float>(), S, c.L, col0, ncols, ig, c.class_id - 1, M, z,
+                                                          ctx->scores.as<float>(), d_out_scores, d_out_logits);
+    KPRN_LAUNCH_CHECK(ctx);
+    return KPRN_OK;
+}
+
 int comm_broadcast_f32(kprn_ctx* ctx, float* buf, int64_t n, int root) {
     if (ctx->world <= 1) return KPRN_OK;
     KPRN_NCCL(g_nccl.Broadcast(buf, buf, (size_t)n, ncclFloat32, root, (ncclComm_t)ctx->comm, ctx->stream));

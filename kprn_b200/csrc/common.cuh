@@ -80,6 +80,7 @@ struct kprn_ctx {
     int rank = 0, world = 1;
     int64_t comm_bytes = 0, comm_calls = 0;
     kprn::DBuf tmp_comm;
+    kprn::DBuf tmp_pool;                // (m, z) partials of the path-sharded pool
     // sparse training step (train.cu): while set, the backward scatters entity-row gradients into the compact buffer
     // sparse_gE[slot_of[pos[o]]] (o = read-order index of the step) instead of the dense table in d_grads
     float* sparse_gE = nullptr;
@@ -94,6 +95,9 @@ struct kprn_ctx {
     double* last_loss = nullptr;    // device scalar of the last training step's loss
     int opt_dedup = -1;                 // kprn_set_option("dedup"): -1 = KPRN_TC_DEDUP / default (on), 0 / 1 = forced
     int opt_prefix = -1;                // kprn_set_option("prefix"): leading-token reuse in the scoring recurrence; -1 = KPRN_TC_PREFIX / default (on)
+    int opt_path_sharded = 0;           // kprn_set_option("path_sharded", 1): the PATHS of every (user,item) segment are spread over the ranks
+                                        // (every rank passes all S segments, some possibly empty); the pooled logits are combined across
+                                        // ranks as log-sum-exp partials (m, z) right after the local pool -- SURVEY 8e "logit allreduce"
 };
 
 namespace kprn {
@@ -161,6 +165,7 @@ int comm_allreduce_f32_2(kprn_ctx* ctx, float* a, int64_t na, float* b, int64_t 
 int comm_allreduce_i64(kprn_ctx* ctx, int64_t* buf, int64_t n, bool max_op);
 int comm_allgather_bytes(kprn_ctx* ctx, const void* send, void* recv, int64_t bytes);
 int comm_broadcast_f32(kprn_ctx* ctx, float* buf, int64_t n, int root);
+int pool_allreduce_lse(kprn_ctx* ctx, const int32_t* d_seg, int64_t S, float* d_out_scores, float* d_out_logits);
 
 // ---- pieces of the API layer the training step composes (api.cu) ----
 int forward_device_impl(kprn_ctx* ctx, const int32_t* d_ids, const int32_t* d_seg, int64_t N, int64_t S, bool train, bool want_logits,

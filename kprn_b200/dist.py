@@ -32,6 +32,18 @@ def shard(ids, seg, labels, rank, world):
     return np.asarray(ids)[p0:p1], seg_local, lab, (a, b)
 
 
+def shard_paths(ids, seg, rank, world):
+    """Path-sharded view of a CSR batch (kprn_set_option "path_sharded"): path p goes to rank p % world, every rank keeps all S
+    segments (its share of each, possibly empty).  Returns (ids_local, seg_local)."""
+    ids = np.asarray(ids)
+    seg = np.asarray(seg, dtype=np.int64)
+    mine = np.arange(ids.shape[0]) % world == rank
+    counts = np.add.reduceat(mine.astype(np.int64), seg[:-1]) if len(seg) > 1 else np.zeros(0, np.int64)
+    counts[seg[1:] == seg[:-1]] = 0                     # reduceat on an empty segment returns the next element
+    seg_local = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    return ids[mine], seg_local
+
+
 def gather_scores(local_scores, seg_range, n_segments, group=None):
     """All ranks obtain the full score vector [S] (all-gather of the ragged per-rank slices via a zero-padded sum)."""
     import torch

@@ -229,6 +229,13 @@ function Scorer:pullGradients()
    return self._flatGrad
 end
 
+-- engine knobs (include/kprn_b200.h, kprn_set_option): "dedup", "prefix" never change results; "pathSharded" (with a communicator)
+-- spreads the paths of every (user,item) pair over the ranks and combines the pooled logits as log-sum-exp partials
+function Scorer:setOption(key, value)
+   if key == 'pathSharded' then key = 'path_sharded' end
+   check(C.kprn_set_option(self.ctx, key, value and (value == true and 1 or value) or 0))
+   return self
+end
 function Scorer:training() self.train = true; return self end
 function Scorer:evaluate() self.train = false; return self end
 function Scorer:type() return self end

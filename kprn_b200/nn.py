@@ -106,6 +106,11 @@ class KPRNPathScorer:
     def reset(self, stdv=0.1, seed=12345):
         self.engine.init_uniform(stdv, seed)      # param:uniform(-0.1, 0.1), OneModel.lua:306-309
 
+    def setOption(self, key, value):
+        """Engine knobs (kprn_set_option): "dedup", "prefix" (never change results), "pathSharded" (multi-GPU pooling mode)."""
+        self.eng.set_option("path_sharded" if key == "pathSharded" else key, int(value))
+        return self
+
     def training(self):
         self.train = True
         return self

@@ -1,6 +1,6 @@
 """2-GPU tests (skipped with fewer devices): one process per GPU, the NCCL communicator owned by the ctx (kprn_comm_*, the
 same entry points a LuaJIT host binds) -- segment-range sharding of one CSR batch (kprn_b200/dist.py), no data-path
-collective for scoring; training: all-reduce of the small tensors' gradients + all-gather of the entity-row gradients
+collective for scoring; path sharding with the pooled logits combined as log-sum-exp partials ("path_sharded"); training: all-reduce of the small tensors' gradients + all-gather of the entity-row gradients
 (kprn_train_step), and the reference-style dense flow (kprn_allreduce_grads)."""
 import hashlib
 import os
@@ -20,11 +20,11 @@ def _worker(rank, world, id_q, out):
     from tests.util import engine_for, make_case
     torch.cuda.set_device(rank)
     if rank == 0:
-        uid = engine.Engine.comm_unique_id()
+        uid, uid2 = engine.Engine.comm_unique_id(), engine.Engine.comm_unique_id()
         for _ in range(world - 1):
-            id_q.put(uid)
+            id_q.put((uid, uid2))
     else:
-        uid = id_q.get(timeout=120)
+        uid, uid2 = id_q.get(timeout=120)
     V_e = 3000
     o, params, _, _, _ = make_case(N=64, seed=51, d_t=8, d_e=64, d_r=8, H=64, V_e=V_e)
     c = o.cfg
@@ -71,6 +71,28 @@ def _worker(rank, world, id_q, out):
         l_ids, l_seg, l_lab, rng = dist.shard(ids, seg, labels, rank, world)
         e.train_step(l_ids, l_seg, l_lab, pad_rows=pads, grad_scale=len(l_lab) / S)
     res["info"] = e.train_info()
+    # ---- path-sharded pooling: the paths of every segment spread over the ranks, pooled logits combined as LSE partials ----
+    ids, seg, labels = batches[0]
+    f = engine_for(o, precision=1, device=rank)
+    f.comm_init(rank, world, uid2)
+    f.set_params(params)
+    f.set_option("path_sharded", 1)
+    p_ids, p_seg = dist.shard_paths(ids, seg, rank, world)
+    sc = f.forward(p_ids, p_seg)                           # scores-only path (class column)
+    res["ps_score_err"] = float(np.max(np.abs(sc - ref["scores"]) / ref["scores"]))
+    sc2, lg2 = f.forward(p_ids, p_seg, want_logits=True)    # all 46 pooled columns
+    res["ps_logit_err"] = float(np.max(np.abs(lg2 - ref["seg_logits"]) / np.maximum(np.abs(ref["seg_logits"]), np.sqrt(np.mean(ref["seg_logits"] ** 2)))))
+    # training-mode forward + BCE + backward on the shard: the gradient of the WHOLE batch after the all-reduce
+    f.zero_grad()
+    f.forward(p_ids, p_seg, train=True)
+    f.loss_bce(labels)
+    f.backward()
+    f.allreduce_grads()
+    g2 = f.get_grads()
+    res["ps_grad_err"] = float(np.max(np.abs(g2 - g_ref) / np.maximum(np.abs(g_ref), rms)))
+    f.allreduce_host(np.zeros(1))
+    f.comm_destroy()
+    f.close()
     res["comm"] = e.comm_info()
     p = e.get_params()
     res["hash"] = hashlib.sha1(p.tobytes()).hexdigest()
@@ -108,3 +130,5 @@ def test_two_gpu_sharded_scoring_dense_allreduce_and_sparse_row_exchange():
     assert r0["hash"] == r1["hash"], "replicas diverged"
     assert r0["param_q999"] <= 2e-6 and r0["param_max"] <= 2e-4, r0
     assert r0["info"]["rows_union"] >= r0["info"]["rows_local"] > 0 and r0["comm"]["bytes"] > 0, r0
+    for r in (r0, r1):
+        assert r["ps_score_err"] < 1e-4 and r["ps_logit_err"] < 1e-4 and r["ps_grad_err"] < 1e-4, r
