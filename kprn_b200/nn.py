@@ -108,7 +108,7 @@ class KPRNPathScorer:
 
     def setOption(self, key, value):
         """Engine knobs (kprn_set_option): "dedup", "prefix" (never change results), "pathSharded" (multi-GPU pooling mode)."""
-        self.eng.set_option("path_sharded" if key == "pathSharded" else key, int(value))
+        self.engine.set_option("path_sharded" if key == "pathSharded" else key, int(value))
         return self
 
     def training(self):

@@ -151,3 +151,13 @@ def test_get_parameters_refuses_to_hand_out_a_stale_alias():
         model.getParameters()
     p, g = model.getParameters(mirror=True)
     assert p.shape == g.shape
+
+
+def test_set_option_knobs_and_unknown_key():
+    """Scorer:setOption mirrors kprn_set_option: result-neutral knobs are accepted, an unknown key raises."""
+    from kprn_b200 import nn
+    from kprn_b200.engine import KprnError
+    model = nn.KPRNPathScorer(6, 8, 300, 16, 9, 8, 16, precision=1)
+    model.setOption("dedup", 0).setOption("prefix", 1).setOption("pathSharded", 1)      # without a communicator the last is inert
+    with pytest.raises(KprnError):
+        model.setOption("no_such_knob", 1)
