@@ -535,8 +535,8 @@ def main():
                 teng.comm_destroy()
             if teng is not eng:
                 teng.close()
-        except engine.KprnError as err:
-            train = {"error": str(err)}
+        except Exception as err:              # the scoring line must still print
+            train = {"error": "%s: %s" % (type(err).__name__, err)}
     time.sleep(0.2)
     sampler.stop()
 
