@@ -226,6 +226,23 @@ def workload_config(d, n_paths, gpus, dims=None):
             "l2": "8 rotating input batches; per-step working set (gathered rows + activations) exceeds the 126 MB L2"}
 
 
+def prefix_recur_products(ids):
+    """Host replay of csrc/tc_prefix.cu's bookkeeping: path-steps of recurrent products the scoring recurrence executes when the
+    batch is sorted by leading-token count and every pair of 128-path tiles starts at the count of its first row."""
+    N, Tt = ids.shape[0], ids.shape[1]
+    lim = min(N, 4096)
+    rep = np.nonzero((ids[:lim, 0] == ids[:lim, 1]).all(axis=1))[0]
+    X = ids[rep[0] if len(rep) else 0, 0]
+    eq = (ids == X).all(axis=2)
+    p = np.where(eq.all(axis=1), Tt - 1, np.argmin(eq, axis=1))
+    p = np.minimum(p, Tt - 1)
+    ps = np.sort(p)
+    total = 0
+    for r0 in range(0, N, 256):
+        total += (Tt - 1 - int(ps[r0])) * min(256, N - r0)
+    return total
+
+
 def profile_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum per launch, read from the newest committed `ncu --set full` capture
     (profiles/*_traffic.json, written by tools/profile_summary.py from the .ncu-rep). Returns ({kernel: bytes}, source)."""
@@ -309,6 +326,7 @@ def main():
     k0 = batches[0][0].reshape(-1, 3).astype(np.int64)
     distinct_rows = int(len(np.unique((k0[:, 1] * 64 + k0[:, 0]) * 64 + k0[:, 2])))      # distinct (type, entity, relation) step inputs
     distinct_frac = distinct_rows / float(k0.shape[0])
+    recur_products = prefix_recur_products(batches[0][0])      # recurrent tile-steps the scoring kernel runs with leading-token reuse
     dev = []
     for ids, seg in batches:
         dev.append((torch.from_numpy(ids).cuda(), torch.from_numpy(seg).cuda(), len(seg) - 1))
@@ -556,7 +574,9 @@ def main():
         ke, hp = -(-d_e // 64) * 64, (64 if d <= 64 else 128 if d <= 128 else 256)
         dedup_on = os.environ.get("KPRN_TC_DEDUP", "1") != "0"
         rows = distinct_rows if dedup_on else n_paths * T
-        exe = {"proj": rows * 2 * (3 * ke + 2 * 64) * 4 * hp, "recur": n_paths * (T - 1) * 2 * hp * 4 * hp * 3}
+        prefix_on = os.environ.get("KPRN_TC_PREFIX", "1") != "0" and d <= 256 and n_paths >= 4096
+        exe = {"proj": rows * 2 * (3 * ke + 2 * 64) * 4 * hp,
+               "recur": (recur_products if prefix_on else n_paths * (T - 1)) * 2 * hp * 4 * hp * 3}
         kern = {}
         for slot, name in ((1, "proj"), (2, "recur"), (0, "gate_phase")):
             if prof_n[slot] > 0 and prof_ms[slot] > 0:
@@ -578,9 +598,11 @@ def main():
                 "mode": mode, "mma_multiplicity": mult,
                 "traffic": None, "kernels": kern,
                 "distinct_step_inputs": {"rows_per_batch": distinct_rows, "fraction_of_steps": distinct_frac, "dedup": dedup_on},
+                "recurrent_products": {"path_steps_executed": recur_products if prefix_on else n_paths * (T - 1),
+                                       "path_steps_dense": n_paths * (T - 1), "leading_token_reuse": prefix_on},
                 "note": "achieved = algorithmic flops (what the reference computes: every step of every path, dense D+H columns) / "
                         "CUDA-event launch time. The fused path executes fewer: type/relation lookups are hoisted into a 54-row table, "
-                        "the projection runs once per distinct step input, t=0 has no recurrent product -- and %dx more per executed "
+                        "the projection runs once per distinct step input, t=0 and the shared pad prefix of a tile have no recurrent product -- and %dx more per executed "
                         "product (bf16 hi/lo split); executed_mma_tflops gives the tensor cores' own rate. 'proj' times the "
                         "deduplication kernels + proj3_kernel" % mult}
         if dom:

@@ -44,6 +44,26 @@ def shard_paths(ids, seg, rank, world):
     return ids[mine], seg_local
 
 
+def allreduce_lse(seg_logits_local, seg_local, inv_gamma=1.0, group=None):
+    """Host mirror of pool_allreduce_lse (csrc/comm.cu): combines per-rank pooled logits [S, L] of a path-sharded batch as
+    log-sum-exp partials -- all-reduce(max) of m_r = ig * pooled_r (-inf where the rank holds no path of the segment), then
+    all-reduce(sum) of exp(m_r - M)."""
+    import torch
+    import torch.distributed as dist
+    x = np.asarray(seg_logits_local, dtype=np.float64) * inv_gamma
+    seg_local = np.asarray(seg_local)
+    empty = seg_local[1:] == seg_local[:-1]
+    x = np.where(empty[:, None], -np.inf, x)
+    M = torch.from_numpy(x.copy())
+    dist.all_reduce(M, op=dist.ReduceOp.MAX, group=group)
+    Mn = M.numpy()
+    with np.errstate(invalid="ignore"):
+        z = torch.from_numpy(np.where(np.isfinite(x), np.exp(x - Mn), 0.0))
+    dist.all_reduce(z, op=dist.ReduceOp.SUM, group=group)
+    with np.errstate(divide="ignore"):
+        return np.where(np.isfinite(Mn), (Mn + np.log(z.numpy())) / inv_gamma, 0.0)
+
+
 def gather_scores(local_scores, seg_range, n_segments, group=None):
     """All ranks obtain the full score vector [S] (all-gather of the ragged per-rank slices via a zero-padded sum)."""
     import torch

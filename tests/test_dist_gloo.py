@@ -1,5 +1,6 @@
 """world_size-2 gloo test (CPU) of the N>1 host logic: shard by segment range, score shards independently (no
-data-path collective), gather scores; all-reduce of the shard gradients reproduces the full-batch gradient."""
+data-path collective), gather scores; all-reduce of the shard gradients reproduces the full-batch gradient; path sharding
+with the pooled logits combined as log-sum-exp partials (the host mirror of pool_allreduce_lse) reproduces the full pool."""
 import os
 import socket
 import sys
@@ -34,8 +35,14 @@ def _worker(rank, world, port, out):
     _, dsc = o.bce(fwd["scores"], l_lab.astype(np.float64))
     dsc *= len(l_lab) / S
     g = dist.allreduce_host(o.backward(params, l_ids, l_seg, fwd, dsc))
+    # path sharding: the paths of every segment spread over the ranks, pooled logits combined as log-sum-exp partials
+    p_ids, p_seg = dist.shard_paths(ids, seg, rank, world)
+    assert len(p_seg) == len(seg) and p_seg[-1] == len(p_ids)
+    pf = o.forward(params, p_ids, p_seg)
+    pooled = dist.allreduce_lse(pf["seg_logits"], p_seg, o.cfg.inv_gamma if o.cfg.inv_gamma else 1.0)
     if rank == 0:
         full = o.forward(params, ids, seg, cache=True)
+        out.put(("lse", float(np.abs(pooled - full["seg_logits"]).max())))
         _, dfull = o.bce(full["scores"], labels.astype(np.float64))
         gfull = o.backward(params, ids, seg, full, dfull)
         out.put((float(np.abs(scores - full["scores"]).max()), float(np.abs(g - gfull).max() / np.abs(gfull).max())))
@@ -50,9 +57,12 @@ def test_two_rank_sharding_matches_single_rank():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, out)) for r in range(2)]
     for p in procs:
         p.start()
-    res = out.get(timeout=120)
+    got = [out.get(timeout=120) for _ in range(2)]
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
+    lse = [g for g in got if g[0] == "lse"][0]
+    res = [g for g in got if g[0] != "lse"][0]
+    assert lse[1] < 1e-10      # path-sharded pooling == pooling of the whole batch
     assert res[0] < 1e-6       # fp32 transport of the gathered scores
     assert res[1] < 1e-12

@@ -106,3 +106,19 @@ def test_formatter_port_reproduces_reference_script_outputs(tmp_path):
     p.write_text("\n".join(got["train/train.txt.2.int"]) + "\n")
     labels, data = io.read_int_file(str(p))
     assert data.shape[1:] == (2, 6, 3) and data.min() >= 1 and set(np.unique(labels)) <= {0.0, 1.0}
+
+
+def test_bench_prefix_bookkeeping_matches_the_sort_rule():
+    """bench.prefix_recur_products replays tc_prefix.cu on the host: paths sorted by leading-token count, a pair of tiles
+    (256 rows) starts at the count of its first row."""
+    import bench
+    from kprn_b200 import synth
+    ids = synth.make_paths(1000, T=6, V_e=500, seed=5, length_mode="realistic")          # 70 % two pads, 30 % none
+    got = bench.prefix_recur_products(ids)
+    dense = len(ids) * 5
+    assert 0 < got <= dense
+    n0 = int((ids[:, 0, 1] != ids[:, 1, 1]).sum())                                          # paths without a repeated leading token
+    # rows [0, n0) have no shared prefix; the tile pair that straddles the boundary runs all 5 products
+    expect = sum((5 - (0 if r0 < n0 else 2)) * min(256, 1000 - r0) for r0 in range(0, 1000, 256))
+    assert got == expect
+    assert bench.prefix_recur_products(synth.make_paths(300, T=6, V_e=500, seed=6, length_mode=6)) == 300 * 5
