@@ -507,8 +507,13 @@ def main():
             ts = max(3, min(args.steps, 10))
             topts = [teng.train_opts(grad_scale=float(gscale[b])) for b in range(NB)]
 
+            use_hint = os.environ.get("KPRN_BENCH_HINT", "1") != "0"
+
             def step_train(i):
                 ids_t, seg_t, S = dev[i % NB]
+                # what a host with a look-ahead batcher does (BatcherFileList stages the next bucket while one trains): name the next batch
+                if use_hint:
+                    teng.train_prefetch_device(dev[(i + 1) % NB][0].data_ptr(), n_paths)
                 teng.train_step_device(ids_t.data_ptr(), seg_t.data_ptr(), n_paths, S, d_labels=d_lab[i % NB].data_ptr(), pad_rows=pads,
                                        opts=topts[i % NB])
             losses = []
@@ -540,8 +545,9 @@ def main():
             e2e_ms = 1e3 * float(te2.item()) / ts
             train = {"ms_per_step": t_ms, "value": world * n_paths / (t_ms * 1e-3), "unit": "paths/s", "steps": ts,
                      "e2e": {"value": world * n_paths / (e2e_ms * 1e-3), "unit": "paths/s", "ms_per_step": e2e_ms},
-                     "mode": "kprn_train_step_device, precision %d, BCE, row-sparse evaluation of dense optim.adam "
-                             "(%d params; %d distinct entity rows in the last batch)" % (tprec, teng.n_params, info["rows_local"]),
+                     "mode": "kprn_train_step_device%s, precision %d, BCE, row-sparse evaluation of dense optim.adam "
+                             "(%d params; %d distinct entity rows in the last batch)" % (
+                                 " (+ kprn_train_prefetch_device hint of the next batch)" if use_hint else "", tprec, teng.n_params, info["rows_local"]),
                      "gpu_launches_per_step": tl / float(ts), "loss_first": losses[0], "loss_last": losses[-1],
                      "fwd_bwd_flops_per_path": 3 * flops_per_path(d_t, d_e, d_r, d),
                      "algorithmic_tflops": 3 * flops_per_path(d_t, d_e, d_r, d) * n_paths / (t_ms * 1e-3) / 1e12,

@@ -180,6 +180,11 @@ typedef struct kprn_train_opts {
     int32_t dense;          /* 1 = reference-literal dense flow */
     int32_t reserved[4];
 } kprn_train_opts;
+/* Optional hint from a host with a look-ahead batcher (BatcherFileList.lua:53-96 stages the next bucket while one trains): the
+ * device-resident ids [N_next, T, 3] of the batch the NEXT kprn_train_step* call will get.  The step running in between brings
+ * that batch's entity rows up to date at its tail, beside its weight-gradient kernel, instead of at the head of the next step.
+ * Purely a scheduling hint: a wrong or missing hint changes no result.  The buffer must stay valid until that step returns. */
+int kprn_train_prefetch_device(kprn_ctx* ctx, const int32_t* d_ids_next, int64_t N_next);
 int kprn_train_step(kprn_ctx* ctx, const int32_t* ids, const int32_t* seg_offsets, int64_t N, int64_t S, const float* labels,
                     const int32_t* pos_seg, const int32_t* neg_seg, int64_t n_pairs, const int64_t* pad_rows3,
                     const kprn_train_opts* opts, float* loss);

@@ -317,6 +317,7 @@ int kprn_destroy(kprn_ctx* ctx) {
     tc_destroy(ctx);
     if (ctx->tmp_comm.p) cudaFree(ctx->tmp_comm.p);
     if (ctx->tmp_pool.p) cudaFree(ctx->tmp_pool.p);
+    if (ctx->ws_part.p) cudaFree(ctx->ws_part.p);
     DBuf* bufs[] = {&ctx->ids_buf, &ctx->seg_buf, &ctx->path_logits, &ctx->seg_logits, &ctx->scores, &ctx->dscores,
                     &ctx->dseg_logits, &ctx->labels, &ctx->tmp_small, &ctx->act, &ctx->cst, &ctx->hst, &ctx->z1,
                     &ctx->ws_x, &ctx->ws_xw, &ctx->ws_h0, &ctx->ws_h1, &ctx->ws_c, &ctx->ws_dg, &ctx->ws_dx,

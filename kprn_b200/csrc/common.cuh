@@ -80,6 +80,7 @@ struct kprn_ctx {
     int rank = 0, world = 1;
     int64_t comm_bytes = 0, comm_calls = 0;
     kprn::DBuf tmp_comm;
+    kprn::DBuf ws_part;                 // per-block partial sums of the column-sum / scalar-sum reductions (summed in block order: deterministic)
     kprn::DBuf tmp_pool;                // (m, z) partials of the path-sharded pool
     // sparse training step (train.cu): while set, the backward scatters entity-row gradients into the compact buffer
     // sparse_gE[slot_of[pos[o]]] (o = read-order index of the step) instead of the dense table in d_grads

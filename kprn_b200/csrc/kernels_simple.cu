@@ -436,7 +436,24 @@ __global__ void wcolsum_kernel(const float* __restrict__ X, int64_t ld, const fl
     int64_t r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
     float acc = 0.f;
     for (int64_t r = r0; r < r1; ++r) acc += (w ? w[r] : 1.f) * X[r * ld + j];
-    atomicAdd(out + j, acc);
+    out[(int64_t)blockIdx.y * cols + j] = acc;          // partial of this row range; summed in range order by the kernel below
+}
+// out[j] += sum over the row ranges, in range order: no float atomics, the same bits on every run
+// block (32 columns, 8 groups of row ranges): a thread sums every 8th range, the 8 group sums are combined in group order
+__global__ void wcolsum_fin_kernel(const float* __restrict__ part, int nparts, int cols, float* __restrict__ out) {
+    __shared__ float red[8][32];
+    const int j = blockIdx.x * 32 + threadIdx.x;
+    float acc = 0.f;
+    if (j < cols)
+        for (int b = threadIdx.y; b < nparts; b += 8) acc += part[(int64_t)b * cols + j];
+    red[threadIdx.y][threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.y == 0 && j < cols) {
+        float t = 0.f;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) t += red[g][threadIdx.x];
+        out[j] += t;
+    }
 }
 
 static int wcolsum(kprn_ctx* ctx, const float* X, int64_t ld, const float* w, int64_t rows, int cols, float* out) {
@@ -444,16 +461,32 @@ static int wcolsum(kprn_ctx* ctx, const float* X, int64_t ld, const float* w, in
     int64_t rpb = cdiv(rows, 296);
     if (rpb < 64) rpb = 64;
     dim3 grid((unsigned)cdiv(cols, 128), (unsigned)cdiv(rows, rpb));
-    wcolsum_kernel<<<grid, 128, 0, ctx->stream>>>(X, ld, w, rows, cols, rpb, out);
+    KPRN_TRY(ensure(ctx->ws_part, sizeof(float) * (size_t)grid.y * cols));
+    wcolsum_kernel<<<grid, 128, 0, ctx->stream>>>(X, ld, w, rows, cols, rpb, ctx->ws_part.as<float>());
+    KPRN_LAUNCH_CHECK(ctx);
+    wcolsum_fin_kernel<<<(unsigned)cdiv(cols, 32), dim3(32, 8), 0, ctx->stream>>>(ctx->ws_part.as<float>(), (int)grid.y, cols, out);
     KPRN_LAUNCH_CHECK(ctx);
     return KPRN_OK;
 }
 
-__global__ void sum_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ out) {
+// out += sum(x): ONE block, fixed assignment of elements to threads and a fixed reduction tree (no float atomics)
+__global__ void __launch_bounds__(1024) sum_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ out) {
+    __shared__ float wsum[32];
     float acc = 0.f;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) acc += x[i];
+    const int64_t n4 = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) ? n / 4 : 0;      // 128-bit loads over the aligned body
+    for (int64_t i = threadIdx.x; i < n4; i += blockDim.x) {
+        const float4 v = reinterpret_cast<const float4*>(x)[i];
+        acc += (v.x + v.y) + (v.z + v.w);
+    }
+    for (int64_t i = n4 * 4 + threadIdx.x; i < n; i += blockDim.x) acc += x[i];
     for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = threadIdx.x < (blockDim.x >> 5) ? wsum[threadIdx.x] : 0.f;
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (threadIdx.x == 0) *out += v;
+    }
 }
 
 // FastLSTM BPTT step.  dG is written step-major [t][p][4H].
@@ -555,7 +588,7 @@ int head_backward_cls(kprn_ctx* ctx, float scale, const float* hT, int64_t ldh) 
         ctx->path_logits.as<float>(), ctx->seg_logits.as<float>(), ctx->d_seg, S, c.L, c.pool, c.topk, ig, cls,
         ctx->dscores.as<float>(), scale, ds_c);
     KPRN_LAUNCH_CHECK(ctx);
-    sum_kernel<<<296, 256, 0, ctx->stream>>>(ds_c, N, gr + l.bo + cls);
+    sum_kernel<<<1, 1024, 0, ctx->stream>>>(ds_c, N, gr + l.bo + cls);
     KPRN_LAUNCH_CHECK(ctx);
     KPRN_TRY(wcolsum(ctx, hT, ldh, ds_c, N, c.H, gr + l.Wo + (int64_t)cls * c.H));
     return KPRN_OK;
@@ -584,7 +617,7 @@ int simple_backward(kprn_ctx* ctx, float scale) {
         ctx->dscores.as<float>(), scale, ds_c);
     KPRN_LAUNCH_CHECK(ctx);
     // gbo[c] += sum ds_c
-    sum_kernel<<<296, 256, 0, ctx->stream>>>(ds_c, N, gr + l.bo + cls);
+    sum_kernel<<<1, 1024, 0, ctx->stream>>>(ds_c, N, gr + l.bo + cls);
     KPRN_LAUNCH_CHECK(ctx);
     float* X = ctx->ws_x.as<float>();
     float* dG = ctx->ws_dg.as<float>();

@@ -1003,16 +1003,40 @@ __device__ __forceinline__ int dedup_flags(const uint32_t* __restrict__ pos, con
 // Row of every first occurrence: consecutive inside a block of 1024 read-order indices (what the recurrence's warp loads
 // need), blocks placed by one atomicAdd each (their order varies from run to run; the values computed do not).  The
 // first-occurrence thread records the row for its key and writes the triple to the list the projection reads.
+// mode 1 (slots of the entity gradient): the block bases come from a count pass instead (block_counts != null), so the slots are
+// numbered strictly by first occurrence -- the sorted segment reduce of the entity gradient then splits its runs at the same
+// places on every run, i.e. training is bit-reproducible.
+__global__ void dedup_count_kernel(const uint32_t* __restrict__ pos, const uint32_t* __restrict__ first, int64_t n_order, int32_t* __restrict__ block_counts) {
+    bool f[4];
+    int tot;
+    const int64_t o0 = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4;
+    dedup_block_scan(dedup_flags(pos, first, n_order, o0, f), &tot);
+    if (threadIdx.x == 0) block_counts[blockIdx.x] = tot;
+}
 __global__ void dedup_assign_kernel(const int32_t* __restrict__ ids, const uint32_t* __restrict__ pos, const uint32_t* __restrict__ first,
                                     int64_t n_order, int64_t N, int T, int32_t* count, uint32_t* __restrict__ slot_of,
-                                    int32_t* __restrict__ ids_d, int mode) {
+                                    int32_t* __restrict__ ids_d, int mode, const int32_t* __restrict__ block_counts) {
     __shared__ int base_s;
+    __shared__ int red_s[8];
     bool f[4];
     int tot;
     const int64_t o0 = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4;
     const int c = dedup_flags(pos, first, n_order, o0, f);
     const int ex = dedup_block_scan(c, &tot);
-    if (threadIdx.x == 0) base_s = tot ? atomicAdd(count, tot) : 0;
+    if (block_counts) {
+        int part = 0;
+        for (int i = threadIdx.x; i < (int)blockIdx.x; i += 256) part += block_counts[i];
+        for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        __syncthreads();                                   // dedup_block_scan's shared scratch is done with
+        if ((threadIdx.x & 31) == 0) red_s[threadIdx.x >> 5] = part;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int b = 0;
+            for (int w = 0; w < 8; ++w) b += red_s[w];
+            base_s = b;
+            if (blockIdx.x == gridDim.x - 1) *count = b + tot;
+        }
+    } else if (threadIdx.x == 0) base_s = tot ? atomicAdd(count, tot) : 0;
     __syncthreads();
     int row = base_s + ex;
 #pragma unroll
@@ -1043,7 +1067,8 @@ int dedup_build(kprn_ctx* ctx, DedupBufs& b, int mode, const int32_t* ids, int64
     KPRN_TRY(ensure(b.slot_of, sizeof(uint32_t) * (size_t)M));
     KPRN_TRY(ensure(b.pos, sizeof(uint32_t) * (size_t)n_order));
     KPRN_TRY(ensure(b.ids, sizeof(int32_t) * (mode == 0 ? 3 : 1) * (size_t)n_max));
-    KPRN_TRY(ensure(b.count, 256));
+    const unsigned nblk = (unsigned)cdiv(n_order, DEDUP_BLOCK);
+    KPRN_TRY(ensure(b.count, 256 + sizeof(int32_t) * (size_t)nblk));        // [0] = number of slots; [64 ..) = per-block counts (mode 1)
     unsigned long long* table = b.table.as<unsigned long long>();
     uint32_t* first = reinterpret_cast<uint32_t*>(table + M);
     int32_t* count = b.count.as<int32_t>();
@@ -1052,8 +1077,14 @@ int dedup_build(kprn_ctx* ctx, DedupBufs& b, int mode, const int32_t* ids, int64
     dedup_insert_kernel<<<(unsigned)cdiv(n_order, 256), 256, 0, ctx->stream>>>(ids, n_order, N, T, c.V_t, c.V_e, c.V_r, table, first, M - 1,
                                                                               b.pos.as<uint32_t>(), ctx->d_err, mode);
     KPRN_LAUNCH_CHECK(ctx);
-    dedup_assign_kernel<<<(unsigned)cdiv(n_order, DEDUP_BLOCK), 256, 0, ctx->stream>>>(ids, b.pos.as<uint32_t>(), first, n_order, N, T, count,
-                                                                                      b.slot_of.as<uint32_t>(), b.ids.as<int32_t>(), mode);
+    int32_t* block_counts = nullptr;
+    if (mode == 1) {
+        block_counts = count + 64;
+        dedup_count_kernel<<<nblk, 256, 0, ctx->stream>>>(b.pos.as<uint32_t>(), first, n_order, block_counts);
+        KPRN_LAUNCH_CHECK(ctx);
+    }
+    dedup_assign_kernel<<<nblk, 256, 0, ctx->stream>>>(ids, b.pos.as<uint32_t>(), first, n_order, N, T, count,
+                                                      b.slot_of.as<uint32_t>(), b.ids.as<int32_t>(), mode, block_counts);
     KPRN_LAUNCH_CHECK(ctx);
     b.n_order = n_order;
     return KPRN_OK;

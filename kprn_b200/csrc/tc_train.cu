@@ -904,7 +904,8 @@ __global__ void ptr_sums_kernel(const float* __restrict__ gP, int G4, int H, int
     if (u < H) gbx[row] += all;
 }
 // gE_type[a][k] += sum_gp Tsum[a][gp] Wx[row(gp)][k];  gE_rel[b][k] += sum_gp Rsum[b][gp] Wx[row(gp)][d_t + d_e + k]
-// grid (V_t + V_r, column chunks of 64, 8 gate-column ranges): threads = columns (coalesced weight reads), one atomicAdd per range
+// grid (V_t + V_r, column chunks of 64), block (64 columns, 8 gate-column ranges): coalesced weight reads, the 8 range partials of
+// an output element are combined through shared memory in range order (no float atomics: the same bits on every run)
 __global__ void ptr_embed_kernel(const float* __restrict__ Tsum, const float* __restrict__ Rsum, const float* __restrict__ Wx, int G4, int H,
                                  int D, int d_t, int d_e, int d_r, int V_t, float* __restrict__ gEt, float* __restrict__ gEr) {
     const int which = blockIdx.x;                // [0, V_t): type rows; then relation rows
@@ -912,16 +913,24 @@ __global__ void ptr_embed_kernel(const float* __restrict__ Tsum, const float* __
     const int rowi = is_t ? which : which - V_t;
     const int width = is_t ? d_t : d_r, coff = is_t ? 0 : d_t + d_e;
     const float* S = (is_t ? Tsum : Rsum) + (size_t)rowi * G4;
+    __shared__ float part[8][64];
     const int k = blockIdx.y * 64 + threadIdx.x;
-    if (k >= width) return;
-    const int g0 = blockIdx.z * (G4 / 8), g1 = g0 + G4 / 8;
+    const int g0 = threadIdx.y * (G4 / 8), g1 = g0 + G4 / 8;
     float acc = 0.f;
-    for (int gp = g0; gp < g1; ++gp) {
-        int u;
-        const int row = perm_to_row(gp, H, u);
-        if (u < H) acc = fmaf(S[gp], Wx[(size_t)row * D + coff + k], acc);
+    if (k < width)
+        for (int gp = g0; gp < g1; ++gp) {
+            int u;
+            const int row = perm_to_row(gp, H, u);
+            if (u < H) acc = fmaf(S[gp], Wx[(size_t)row * D + coff + k], acc);
+        }
+    part[threadIdx.y][threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.y == 0 && k < width) {
+        float t = 0.f;
+#pragma unroll
+        for (int z = 0; z < 8; ++z) t += part[z][threadIdx.x];
+        ((is_t ? gEt : gEr) + (size_t)rowi * width)[k] += t;
     }
-    atomicAdd((is_t ? gEt : gEr) + (size_t)rowi * width + k, acc);
 }
 // gWx[row(gp)][k] += sum_a Tsum[a][gp] E_t[a][k]  (type columns)  and the same with Rsum / E_r for the relation columns
 __global__ void ptr_wx_kernel(const float* __restrict__ Tsum, const float* __restrict__ Rsum, const float* __restrict__ Et, const float* __restrict__ Er,
@@ -1308,7 +1317,7 @@ int tc_backward(kprn_ctx* ctx, float scale) {
     KPRN_LAUNCH_CHECK(ctx);
     {
         const int wmax = c.d_t > c.d_r ? c.d_t : c.d_r;
-        ptr_embed_kernel<<<dim3((unsigned)(c.V_t + c.V_r), (unsigned)cdiv(wmax, 64), 8), 64, 0, ctx->stream>>>(
+        ptr_embed_kernel<<<dim3((unsigned)(c.V_t + c.V_r), (unsigned)cdiv(wmax, 64)), dim3(64, 8), 0, ctx->stream>>>(
             Tsum, Rsum, P + l.Wx, G4, c.H, l.D, c.d_t, c.d_e, c.d_r, (int)c.V_t, gr + l.E_t, gr + l.E_r);
     }
     KPRN_LAUNCH_CHECK(ctx);

@@ -39,6 +39,11 @@ struct TrainState {
     // multi-GPU exchange
     DBuf send_ids, recv_ids, recv_g, contrib, norm2;
     DedupBufs us;                 // union of the ranks' row lists
+    // kprn_train_prefetch_device: the ids of the NEXT batch, known early to a host with a look-ahead batcher.  The step that is
+    // running when the hint is pending brings that batch's rows up to date at its own tail, on the side stream beside the
+    // weight-gradient kernel, so the next step's catch-up (critical path: the projection reads those rows) finds nothing to do.
+    const int32_t* hint_ids = nullptr; int64_t hint_N = 0;
+    DedupBufs hs;                 // distinct entity rows of the hinted batch
     int64_t last_K = 0, last_U = 0, last_maxK = 0;
     int64_t pads[3] = {0, 0, 0};  // pad rows of the last training step: re-zeroed after a flush (they are zero after every step)
     bool have_pads = false;
@@ -368,7 +373,7 @@ int train_flush(kprn_ctx* ctx) {
 void train_destroy(kprn_ctx* ctx) {
     TrainState* tr = ctx->tr;
     if (!tr) return;
-    dedup_free(tr->es); dedup_free(tr->us);
+    dedup_free(tr->es); dedup_free(tr->us); dedup_free(tr->hs);
     for (DBuf* b : {&tr->gE, &tr->steps, &tr->send_ids, &tr->recv_ids, &tr->recv_g, &tr->contrib, &tr->norm2})
         if (b->p) { cudaFree(b->p); b->p = nullptr; b->cap = 0; }
     if (tr->last_t) cudaFree(tr->last_t);
@@ -626,6 +631,17 @@ static int train_step_device(kprn_ctx* ctx, const int32_t* d_ids, const int32_t*
                                                        l.total - l.E_r, step, o.beta1, o.beta2, o.eps, gscale);
     KPRN_LAUNCH_CHECK(ctx);
     KPRN_TRY(rows_launch(ctx, tr, rows, count, t_now, 1, tr->gE.as<float>(), recv_g, contrib, maxK, gscale, rows_bound, ctx->eg_stream));
+    if (tr->hint_ids) {
+        // the hinted next batch: its rows are replayed up to this step now (same kernel, same arithmetic as the catch-up of the next
+        // step, which then skips them), on whichever stream the row update ran on
+        struct Swap { kprn_ctx* c; cudaStream_t saved; ~Swap() { c->stream = saved; } } swap{ctx, ctx->stream};
+        if (ctx->eg_stream) ctx->stream = ctx->eg_stream;
+        const int32_t* hid = tr->hint_ids; const int64_t hn = tr->hint_N;
+        tr->hint_ids = nullptr;
+        KPRN_TRY(dedup_build(ctx, tr->hs, 1, hid, hn, c.T, 0));
+        KPRN_TRY(rows_launch(ctx, tr, tr->hs.ids.as<int32_t>(), tr->hs.count.as<int32_t>(), t_now + 1, 0, nullptr, nullptr, nullptr, 0, nullptr, hn * c.T,
+                             ctx->stream));
+    }
     if (ctx->eg_stream) {          // the rows were updated beside the weight-gradient kernel: join
         KPRN_CUDA(cudaEventRecord(ctx->eg_event, ctx->eg_stream));
         KPRN_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->eg_event, 0));
@@ -652,6 +668,15 @@ int kprn_train_step_device(kprn_ctx* ctx, const int32_t* d_ids, const int32_t* d
     if (!ctx || !opts || !d_ids || !d_seg) { set_error("train_step_device: null argument"); return KPRN_EINVAL; }
     KPRN_CUDA(cudaSetDevice(ctx->device));
     return train_step_device(ctx, d_ids, d_seg, N, S, d_labels, d_pos_seg, d_neg_seg, n_pairs, pad_rows3, *opts);
+}
+
+int kprn_train_prefetch_device(kprn_ctx* ctx, const int32_t* d_ids_next, int64_t N_next) {
+    if (!ctx) { set_error("null ctx"); return KPRN_EINVAL; }
+    TrainState* tr = tr_get(ctx);
+    if (!d_ids_next || N_next <= 0) { tr->hint_ids = nullptr; tr->hint_N = 0; return KPRN_OK; }
+    if (N_next * (int64_t)ctx->cfg.T >= (1ll << 30)) { set_error("train_prefetch: batch too large"); return KPRN_EINVAL; }
+    tr->hint_ids = d_ids_next; tr->hint_N = N_next;
+    return KPRN_OK;
 }
 
 int kprn_last_loss(kprn_ctx* ctx, float* loss) {

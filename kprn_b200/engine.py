@@ -85,6 +85,7 @@ ABI = {
                         C.POINTER(KprnTrainOpts), _F32P],
     "kprn_train_step_device": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                C.c_int64, _I64P, C.POINTER(KprnTrainOpts)],
+    "kprn_train_prefetch_device": [C.c_void_p, C.c_void_p, C.c_int64],
     "kprn_last_loss": [C.c_void_p, _F32P],
     "kprn_train_info": [C.c_void_p, _I64P, _I64P, _I64P],
     "kprn_comm_unique_id": [C.c_void_p],
@@ -341,6 +342,10 @@ class Engine:
         _chk(self.lib.kprn_train_step_device(self.h, C.c_void_p(d_ids), C.c_void_p(d_seg), N, S, C.c_void_p(d_labels) if d_labels else None,
                                              C.c_void_p(d_pos) if d_pos else None, C.c_void_p(d_neg) if d_neg else None, n_pairs, pads,
                                              C.byref(o)))
+
+    def train_prefetch_device(self, d_ids_next, N_next):
+        """Scheduling hint (kprn_train_prefetch_device): device pointer of the ids the NEXT train_step* call will get."""
+        _chk(self.lib.kprn_train_prefetch_device(self.h, C.c_void_p(d_ids_next) if d_ids_next else None, int(N_next)))
 
     def last_loss(self):
         v = C.c_float()

@@ -76,6 +76,7 @@ int kprn_train_step(kprn_ctx* ctx, const int32_t* ids, const int32_t* seg_offset
 int kprn_train_step_device(kprn_ctx* ctx, const int32_t* d_ids, const int32_t* d_seg_offsets, int64_t N, int64_t S,
                            const float* d_labels, const int32_t* d_pos_seg, const int32_t* d_neg_seg, int64_t n_pairs,
                            const int64_t* pad_rows3, const kprn_train_opts* opts);
+int kprn_train_prefetch_device(kprn_ctx* ctx, const int32_t* d_ids_next, int64_t N_next);
 int kprn_last_loss(kprn_ctx* ctx, float* loss);
 int kprn_train_info(kprn_ctx* ctx, int64_t* rows_local, int64_t* rows_union, int64_t* rows_gathered);
 int kprn_comm_unique_id(void* id128);

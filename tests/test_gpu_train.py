@@ -170,3 +170,32 @@ def test_clip_in_sparse_step_matches_dense_flow():
         e.close()
     d = np.abs(outs[0] - outs[1])
     assert np.quantile(d, 0.999) <= 2e-6 and d.max() <= 2e-4, (np.quantile(d, 0.999), d.max())
+
+
+def test_training_is_bit_reproducible_and_the_next_batch_hint_changes_no_result():
+    """Two identical runs of 6 training steps leave bit-identical parameters (no float atomics on the tensor-core training path:
+    sorted segment reduce with slots numbered by first occurrence, fixed-order split-K and column sums), and
+    kprn_train_prefetch_device is a pure scheduling hint: with the right hint or a wrong one the bits are the same again (the
+    hinted rows are replayed at the tail of the running step by the same kernel that would replay them at the head of the next)."""
+    import torch
+    V_e = 4000
+    o, params, _, _, _ = make_case(N=64, seed=90, d_t=8, d_e=128, d_r=8, H=128, V_e=V_e)      # the fused tensor-core training kernels
+    c = o.cfg
+    pads = (c.V_t, c.V_e, c.V_r)
+    batches = _batches(o, 3, 700, 900, V_e)
+    dev = [(torch.from_numpy(i).cuda(), torch.from_numpy(s).cuda(), torch.from_numpy(l.astype(np.float32)).cuda(), len(s) - 1) for i, s, l in batches]
+    out = []
+    for mode in ("none", "none", "right", "wrong"):
+        e = engine_for(o, precision=3)
+        e.set_params(params)
+        for t in range(6):
+            ids_t, seg_t, lab_t, S = dev[t % 3]
+            if mode == "right":
+                e.train_prefetch_device(dev[(t + 1) % 3][0].data_ptr(), 700)
+            elif mode == "wrong":
+                e.train_prefetch_device(dev[(t + 2) % 3][0].data_ptr(), 700)
+            e.train_step_device(ids_t.data_ptr(), seg_t.data_ptr(), 700, S, d_labels=lab_t.data_ptr(), pad_rows=pads)
+        out.append(e.get_params().copy())
+        e.close()
+    assert np.array_equal(out[0], out[1]), "two identical runs differ"
+    assert np.array_equal(out[0], out[2]) and np.array_equal(out[0], out[3]), "a hint changed the result"
