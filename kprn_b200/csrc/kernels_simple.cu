@@ -458,8 +458,8 @@ __global__ void wcolsum_fin_kernel(const float* __restrict__ part, int nparts, i
 
 static int wcolsum(kprn_ctx* ctx, const float* X, int64_t ld, const float* w, int64_t rows, int cols, float* out) {
     if (rows <= 0) return KPRN_OK;
-    int64_t rpb = cdiv(rows, 296);
-    if (rpb < 64) rpb = 64;
+    int64_t rpb = cdiv(rows, 1184);        // 8 row ranges per SM and column block: the loop is a dependent chain of strided loads
+    if (rpb < 32) rpb = 32;
     dim3 grid((unsigned)cdiv(cols, 128), (unsigned)cdiv(rows, rpb));
     KPRN_TRY(ensure(ctx->ws_part, sizeof(float) * (size_t)grid.y * cols));
     wcolsum_kernel<<<grid, 128, 0, ctx->stream>>>(X, ld, w, rows, cols, rpb, ctx->ws_part.as<float>());

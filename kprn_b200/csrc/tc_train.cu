@@ -976,6 +976,7 @@ struct EgArgs {
     const uint32_t* keys; const uint32_t* vals; int64_t n; int64_t n_chunks;
     const float* dX; int ldx; int d_e;
     float* target; const int32_t* rows;       // target row of slot s: rows ? rows[s] - 1 : s   (dense table / compact buffer)
+    int assign;                               // compact buffer of a sparse step: every slot has exactly one writer, which stores (no zero-fill pass, no read)
     float* part;                              // [chunk][2][d_e]: 0 = run touching the chunk's begin, 1 = run touching its end
     int32_t* flags;                           // [chunk][4]: head key (-1 none), head continues into the next chunk, tail key (-1 none), unused
 };
@@ -1007,7 +1008,7 @@ __global__ void __launch_bounds__(256) eg_reduce_kernel(EgArgs a) {
             dst = a.target + (size_t)(a.rows ? a.rows[cur] - 1 : cur) * a.d_e;
 #pragma unroll
             for (int i = 0; i < NV4; ++i) {
-                float4 o = *reinterpret_cast<float4*>(dst + i * 128 + lane * 4);
+                float4 o = a.assign ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<float4*>(dst + i * 128 + lane * 4);
                 o.x += acc[i].x; o.y += acc[i].y; o.z += acc[i].z; o.w += acc[i].w;
                 *reinterpret_cast<float4*>(dst + i * 128 + lane * 4) = o;
             }
@@ -1089,7 +1090,7 @@ __global__ void __launch_bounds__(512) eg_fixup_kernel(EgArgs a) {
         for (int q = 0; q < NV4; ++q) {
             float4 t = *reinterpret_cast<const float4*>(t0 + q * 128 + lane * 4);
             for (int ww = 0; ww < 16; ++ww) { const float4 v = red[ww][q][lane]; t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w; }
-            float4 o = *reinterpret_cast<float4*>(dst + q * 128 + lane * 4);
+            float4 o = a.assign ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<float4*>(dst + q * 128 + lane * 4);
             o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w;
             *reinterpret_cast<float4*>(dst + q * 128 + lane * 4) = o;
         }
@@ -1266,7 +1267,7 @@ int tc_backward(kprn_ctx* ctx, float scale) {
         ctx->launches += 4;
         EgArgs ea;
         ea.keys = k_out; ea.vals = v_out; ea.n = n_order; ea.n_chunks = cdiv(n_order, EG_CHUNK);
-        ea.dX = tt->dX.as<float>(); ea.ldx = KE; ea.d_e = c.d_e; ea.target = eg_target; ea.rows = eg_rows;
+        ea.dX = tt->dX.as<float>(); ea.ldx = KE; ea.d_e = c.d_e; ea.target = eg_target; ea.rows = eg_rows; ea.assign = ctx->sparse_gE ? 1 : 0;
         KPRN_TRY(ensure(tt->eg_part, sizeof(float) * (size_t)ea.n_chunks * 2 * c.d_e));
         KPRN_TRY(ensure(tt->eg_flags, sizeof(int32_t) * (size_t)ea.n_chunks * 4));
         ea.part = tt->eg_part.as<float>(); ea.flags = tt->eg_flags.as<int32_t>();

@@ -569,8 +569,10 @@ static int train_step_device(kprn_ctx* ctx, const int32_t* d_ids, const int32_t*
     KPRN_TRY(zero_pad_rows(ctx, pads));
     KPRN_CUDA(cudaMemsetAsync(ctx->d_grads, 0, sizeof(float) * (size_t)l.E_e, ctx->stream));
     KPRN_CUDA(cudaMemsetAsync(ctx->d_grads + l.E_r, 0, sizeof(float) * (size_t)(l.total - l.E_r), ctx->stream));
-    zero_rows_kernel<<<148 * 8, 256, 0, ctx->stream>>>(tr->gE.as<float>(), tr->es.count.as<int32_t>(), c.d_e);
-    KPRN_LAUNCH_CHECK(ctx);
+    if (!tc_train_supported(ctx)) {     // the generic backward scatter-adds into the compact rows; the tensor-core one stores every slot once
+        zero_rows_kernel<<<148 * 8, 256, 0, ctx->stream>>>(tr->gE.as<float>(), tr->es.count.as<int32_t>(), c.d_e);
+        KPRN_LAUNCH_CHECK(ctx);
+    }
     // 5. forward (training caches) -> criterion -> backward; the entity gradient lands in gE[slot]
     ctx->sparse_gE = tr->gE.as<float>(); ctx->sparse_pos = tr->es.pos.as<uint32_t>(); ctx->sparse_slot_of = tr->es.slot_of.as<uint32_t>();
     tr->sparse_grads = true; tr->sparse_N = N;
