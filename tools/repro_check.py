@@ -1,3 +1,5 @@
+"""Bit-reproducibility check of the training step (and of the next-batch hint): runs the same 6 steps several times, prints the
+number of parameters that differ between runs (expected: 0).  usage: python tools/repro_check.py  (one B200)"""
 import sys, os
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
