@@ -3,16 +3,20 @@
 //
 //   forward (tc_path.cu, recur_kernel<.., TRAIN>) leaves   cache  = i, g, f, o, c of every (path, step, unit)   (fp32)
 //                                                          hcache = h_t as bf16 hi/lo in the UMMA operand layout
-//   for t = T-1 .. 0:
-//     cell_bwd_kernel   dG_t from (cache_t, c_{t-1}, dh_t, dc)           -> dgop[tile][t] = dG_t as bf16 hi/lo, operand layout
-//     bgemm_kernel      [dh_{t-1} | dX_t] = dG_t [Wh | Wx_e]             (M = paths, N = Hp + KE, K = 4Hp; cta_group::2, bf16x3)
-//                       dh -> fp32 buffer for the next cell_bwd;  dX rows are added (red.global.add.v4.f32) to the entity
-//                       gradient: the compact per-slot buffer of a sparse training step or the dense table
+//   bptt_kernel         the whole time loop t = T-1 .. 0 in one persistent launch: cell warps turn (cache_t, c_{t-1}, dh_t, dc) into
+//                       dG_t, written as bf16 hi/lo straight into the shared-memory operand stage (and to dgop for wgrad_kernel);
+//                       [dh_{t-1} | dX_t] = dG_t [Wh | Wx_e]   (M = paths, N = Hp + KE, K = 4Hp; cta_group::2, bf16x3);
+//                       dh -> tile-private fp32 buffer for the next step; dX rows -> staging, one row per path-step
+//                       (tc_bptt_steps.cuh holds the same loop as a pair of launches per step: the cross-check, KPRN_TC_FUSED=0)
+//   entity gradient     radix sort of (slot, path-step) + eg_reduce_kernel + eg_fixup_kernel: the staged dX rows summed per distinct
+//                       entity row in a fixed order (no atomics), into the compact per-slot buffer of a sparse training step or
+//                       the dense table
 //   wgrad_kernel        gWh += dG^T h_{t-1}, gWx_e += dG^T x_e, gP += dG^T onehot(type,relation)   (M = 4Hp gate columns,
 //                       K = all path-steps: the SAME bytes of dgop read as an MN-major operand; split-K over CTA pairs)
-//   wgrad_reduce_kernel fixed-order sum of the K-split partials into the flat gradient; ptr_grad_kernel turns gP (the
+//   wgrad_reduce_kernel fixed-order sum of the K-split partials into the flat gradient; ptr_sums / ptr_embed / ptr_wx turn gP (the
 //                       gradient of the hoisted (type,relation) table) into gE_type, gE_relation, gWx[:, type|relation], gbx.
-// The head / pool / loss gradients stay on the fp32 kernels of kernels_simple.cu (0.2 % of the flops).
+// The head / pool / loss gradients stay on the fp32 kernels of kernels_simple.cu (0.2 % of the flops).  Nothing on this path uses
+// floating-point atomics: a training step is bit-reproducible.
 #include <cub/device/device_radix_sort.cuh>
 
 #include <stdio.h>
