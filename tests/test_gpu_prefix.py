@@ -52,3 +52,19 @@ def test_prefix_reuse_scores_only_path_and_shuffled_batch():
     off, _ = _run(o, params, ids, seg, 0)
     assert_rel(on, ref["scores"], what="scores, default options")
     assert_rel(on, off, rtol=1e-5, what="scores on vs off")
+
+
+def test_prefix_reuse_with_deduplication_off():
+    """Both knobs are independent: with the projection running on every step of the SORTED batch (dedup off) the recurrence
+    reads its own rows of XW, and tiles still start from the shared state chain."""
+    o, params, ids, seg, _ = make_case(N=1300, seed=77, d_t=16, d_e=128, d_r=16, H=128, V_e=2000, length_mode="realistic")
+    ref = o.forward(params, ids, seg)
+    e = engine_for(o, precision=1)
+    e.set_option("prefix", 1)
+    e.set_option("dedup", 0)
+    e.set_params(params)
+    sc, _ = e.forward(ids, seg, want_logits=True)
+    pl = e.path_logits(ids.shape[0])
+    e.close()
+    assert_rel(sc, ref["scores"], what="scores, prefix on / dedup off")
+    assert_rel(pl, ref["path_logits"], what="path logits, prefix on / dedup off")
